@@ -1,0 +1,131 @@
+"""ctypes binding of libaps_b200.so (the C ABI declared in include/aps_b200.h).
+
+There is NO fallback: if the library is missing or a tensor is not on a CUDA device the
+callers raise RuntimeError.  The library is built in-tree by `python -m aps_b200.build`
+(or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Dict, Tuple
+
+import numpy as np
+import torch as th
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaps_b200.so")
+ABI_VERSION = 1
+
+
+class StftDesc(Structure):
+    """mirror of `aps_b200_stft_desc`"""
+    _fields_ = [("nfft", c_int32), ("frame_width", c_int32), ("hop", c_int32), ("center_pad", c_int32),
+                ("rescale", c_int32), ("utt_preemph", c_float), ("frame_preemph", c_float),
+                ("frame_one_minus", c_float), ("scale", c_float), ("window", c_void_p),
+                ("twiddles", c_void_p)]
+
+
+class FeatDesc(Structure):
+    """mirror of `aps_b200_feat_desc`"""
+    _fields_ = [("power", c_int32), ("num_mels", c_int32), ("mel_start", c_void_p), ("mel_len", c_void_p),
+                ("mel_weight", c_void_p), ("mel_stride", c_int32), ("log_mode", c_int32),
+                ("log_eps", c_float), ("log_lower_bound", c_float), ("cmvn_mode", c_int32),
+                ("norm_mean", c_int32), ("norm_var", c_int32), ("cmvn_eps", c_float), ("gmean", c_void_p),
+                ("gstd", c_void_p), ("nan_count", c_void_p)]
+
+
+_SIGNATURES = {
+    "aps_b200_abi_version": (c_int, []),
+    "aps_b200_init": (c_int, [c_int]),
+    "aps_b200_last_error": (c_int, [c_char_p, c_size_t]),
+    "aps_b200_fft_table_floats": (c_int64, [c_int]),
+    "aps_b200_fft_tables_host": (c_int, [c_int, c_int, c_void_p]),
+    "aps_b200_num_frames": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "aps_b200_feats_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(StftDesc), POINTER(FeatDesc),
+                                   c_void_p, c_void_p]),
+    "aps_b200_stft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(StftDesc), c_int, c_float,
+                                  c_void_p, c_void_p]),
+    "aps_b200_istft_num_samples": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "aps_b200_istft_fwd": (c_int, [c_void_p, c_int64, c_int64, POINTER(StftDesc), c_int, c_float, c_void_p,
+                                   c_void_p]),
+    "aps_b200_spec_feats_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
+                                        POINTER(FeatDesc), c_void_p, c_int64, c_void_p]),
+    "aps_b200_ipd_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p, c_int64, c_int64, c_void_p]),
+    "aps_b200_cmvn_allband": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
+}
+
+_lib = None
+_inited = set()
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m aps_b200.build` "
+                               "(aps_b200 has no CPU / PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.aps_b200_abi_version() != ABI_VERSION:
+            raise RuntimeError("libaps_b200.so ABI version mismatch; rebuild with `python -m aps_b200.build`")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    load().aps_b200_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"aps_b200: {last_error()} (code {rc})")
+
+
+def require_cuda(t: th.Tensor, what: str = "input") -> th.device:
+    """The product path is CUDA only; anything else is an error, never a fallback."""
+    if not isinstance(t, th.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"aps_b200 kernels need a CUDA tensor for {what}; got "
+                           f"{getattr(t, 'device', type(t))} (there is no CPU fallback)")
+    dev = t.device
+    if dev.index not in _inited:
+        with th.cuda.device(dev):
+            check(load().aps_b200_init(dev.index))
+        _inited.add(dev.index)
+    return dev
+
+
+def stream_ptr(dev: th.device) -> int:
+    return th.cuda.current_stream(dev).cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------- cached device tables
+_tables: Dict[Tuple[int, int, int], th.Tensor] = {}
+
+
+def fft_tables(nfft: int, inverse: bool, dev: th.device) -> th.Tensor:
+    key = (nfft, int(inverse), dev.index)
+    if key not in _tables:
+        lib = load()
+        n = lib.aps_b200_fft_table_floats(nfft)
+        if n <= 0:
+            raise RuntimeError(f"aps_b200: unsupported FFT size {nfft} (need a power of two in [64, 1024])")
+        host = np.empty(n, dtype=np.float32)
+        check(lib.aps_b200_fft_tables_host(nfft, int(inverse), host.ctypes.data))
+        _tables[key] = th.from_numpy(host).to(dev)
+    return _tables[key]

@@ -1,0 +1,51 @@
+// common.cu — library bookkeeping: ABI version, device init, per-thread error text.
+#include "../../include/aps_b200.h"
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace apsb {
+
+thread_local char g_last_error[512] = {0};
+static int g_num_sms = 0;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int num_sms() {
+    if (g_num_sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+}  // namespace apsb
+
+extern "C" int aps_b200_abi_version(void) { return APS_B200_ABI_VERSION; }
+
+extern "C" int aps_b200_init(int device) {
+    APSB_CUDA(cudaSetDevice(device));
+    int major = 0, minor = 0, sms = 0;
+    APSB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    APSB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    APSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10)
+        return apsb::set_error(-2, "libaps_b200 is built for sm_100a only; device %d is sm_%d%d", device, major, minor);
+    apsb::g_num_sms = sms;
+    return 0;
+}
+
+extern "C" int aps_b200_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return -1;
+    strncpy(buf, apsb::g_last_error, len - 1);
+    buf[len - 1] = 0;
+    return 0;
+}

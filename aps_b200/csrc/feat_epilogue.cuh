@@ -1,0 +1,110 @@
+// feat_epilogue.cuh — shared tail of the feature kernels: banded mel filterbank, log, per-frame or
+// global CMVN and the coalesced store of one frame's feature vector by a group of G lanes.
+//
+// Replaces /root/reference/aps/transform/asr.py:416-428 (MelTransform.forward, a dense GEMM on a
+// 97.6 %-sparse matrix), :453-464 (LogTransform), :576-585 + :607-611 (CmvnTransform per-band/global).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace apsb {
+
+struct FeatParams {
+    int power, M, mel_stride, log_mode, cmvn_mode, norm_mean, norm_var, D;
+    const int* mel_start;
+    const int* mel_len;
+    const float* mel_w;
+    int mel_in_smem;
+    float log_eps, log_lb, cmvn_eps;
+    const float* gmean;
+    const float* gstd;
+    int* nan_count;   // optional device counter of NaN feature values (asr.py:41 check_valid)
+};
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
+// mag      : this frame's |X| or |X|^2, D_in = F values (shared memory)
+// sm_mel_i : [2*M] band start / length (shared);  mel_w: [M, mel_stride] weights (shared or global)
+// o        : output row of this frame (D floats) or nullptr to skip the store
+template <int G, int FI>
+__device__ __forceinline__ void feature_epilogue(const FeatParams& p, const float* __restrict__ mag,
+                                                 const int* __restrict__ sm_mel_i,
+                                                 const float* __restrict__ mel_w, int l, unsigned mask,
+                                                 float* __restrict__ o) {
+    float feat[FI];
+    const int D = p.D;
+#pragma unroll
+    for (int i = 0; i < FI; ++i) {
+        const int d = l + G * i;
+        float acc = 0.f;
+        if (d < D) {
+            if (p.M > 0) {
+                const int s0 = sm_mel_i[d], n = sm_mel_i[p.M + d];
+                const float* wr = mel_w + d * p.mel_stride;
+                for (int t = 0; t < n; ++t) acc = fmaf(wr[t], mag[s0 + t], acc);
+            } else {
+                acc = mag[d];
+            }
+            if (p.log_mode == 1) acc = logf(acc < p.log_eps ? p.log_eps : acc);
+            else if (p.log_mode == 2) acc = logf(p.log_lb + acc);
+        }
+        feat[i] = acc;
+    }
+    if (p.cmvn_mode == 1) {
+        const float invD = 1.0f / (float)D;
+        float mean = 0.f;
+        if (p.norm_mean || p.norm_var) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < FI; ++i) s += (l + G * i < D) ? feat[i] : 0.f;
+            mean = group_sum<G>(s, mask) * invD;
+        }
+        if (p.norm_mean) {
+#pragma unroll
+            for (int i = 0; i < FI; ++i) feat[i] -= mean;
+        }
+        if (p.norm_var) {
+            const float ctr = p.norm_mean ? 0.f : mean;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < FI; ++i) {
+                const float dlt = feat[i] - ctr;
+                s += (l + G * i < D) ? dlt * dlt : 0.f;
+            }
+            const float var = group_sum<G>(s, mask) * invD;
+            const float den = sqrtf(var + p.cmvn_eps);
+#pragma unroll
+            for (int i = 0; i < FI; ++i) feat[i] = feat[i] / den;
+        }
+    } else if (p.cmvn_mode == 2) {
+#pragma unroll
+        for (int i = 0; i < FI; ++i) {
+            const int d = l + G * i;
+            if (d < D) {
+                if (p.norm_mean) feat[i] -= __ldg(p.gmean + d);
+                if (p.norm_var) feat[i] = feat[i] / __ldg(p.gstd + d);
+            }
+        }
+    }
+    if (o != nullptr) {
+        int bad = 0;
+#pragma unroll
+        for (int i = 0; i < FI; ++i) {
+            const int d = l + G * i;
+            if (d < D) {
+                o[d] = feat[i];
+                bad += (feat[i] != feat[i]) ? 1 : 0;
+            }
+        }
+        if (p.nan_count != nullptr && bad) atomicAdd(p.nan_count, bad);
+    }
+}
+
+// host-side validation + copy of the public descriptor; returns 0 or an error code
+int fill_feat_params(FeatParams& p, const struct aps_b200_feat_desc* feat, int num_bins);
+
+}  // namespace apsb

@@ -1,0 +1,483 @@
+// frontend.cu — F1 (fused framing + pre-emphasis + window + rFFT + |X| + mel + log + CMVN) and
+// F2 (complex STFT) for sm_100a.
+//
+// Replaces, in ONE kernel per call, the reference's nn.Sequential
+//   SpectrogramTransform -> MagnitudeTransform -> TFTransposeTransform -> PowerTransform
+//   -> MelTransform -> LogTransform -> CmvnTransform
+// (/root/reference/aps/transform/asr.py:225-618, driven by utils.py:227-290 _forward_stft).
+//
+// Work decomposition
+//   * persistent grid: CTA b walks chunks b, b+grid, ...; a chunk = TC consecutive frames of one
+//     waveform row.  The chunk's sample span ((TC-1)*hop + nfft floats) is staged ONCE into shared
+//     memory with coalesced loads (rescale, utterance pre-emphasis, reflect padding and the
+//     per-frame Kaldi pre-emphasis y[m] = x[m] - a x[m-1] are applied while staging; the frame's
+//     first sample (1-a) x[0] is kept in a side array), so HBM sees every sample ~once and the
+//     3.2x frame overlap is served from shared memory.
+//   * a group of G = nfft/32 lanes transforms one frame with the register FFT of fft_core.cuh.
+//   * F1 epilogue: magnitudes go to the group's (now free) exchange buffer, the banded mel
+//     filterbank is applied with lane = band, then log, per-frame CMVN (group shuffle reduction)
+//     and ONE coalesced store of the feature vector: 960 B/frame of algorithmic HBM traffic at
+//     hop 160 / 80 mels instead of the reference's ~8 KB/frame of materialised intermediates.
+//   * F2 epilogue: the one-sided spectrum is transposed through a shared tile [bin][frame] so the
+//     [rows, F, T, 2] layout of the reference is written in full 8*TC-byte runs.
+#include "../../include/aps_b200.h"
+#include "common.cuh"
+#include "fft_core.cuh"
+#include "feat_epilogue.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace apsb {
+
+constexpr int kThreads = 256;
+
+struct FrontendParams {
+    const float* wav;
+    long long ld;
+    long long rows;
+    long long S;          // samples per row
+    int nfft, width, hop, pad, rescale;
+    float utt_pre, frm_pre, frm_one_minus, scale;
+    const float* window;
+    const float2* tables;
+    // geometry
+    int T;                // frames per row
+    int TC;               // frames per chunk
+    int chunks_per_row;
+    long long total_chunks;
+    // F1
+    FeatParams ft;
+    int ld_out;           // floats between consecutive frames of the output
+    // F2
+    int polar;
+    float polar_eps;
+    float* out;
+};
+
+// ---- shared memory carve-up (byte offsets computed identically on host and device) -------------
+struct SmemLayout {
+    int y, first, win, tw, ptw, mel_i, mel_w, buf, tile, total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+template <int NC, int MODE>
+__host__ __device__ inline SmemLayout make_layout(int nfft, int hop, int TC, int M, int mel_stride, int mel_in_smem) {
+    using P = FFTPlan<NC>;
+    SmemLayout s;
+    int off = 0;
+    s.y = off;      off = align16(off + ((TC - 1) * hop + nfft + 4) * 4);
+    s.first = off;  off = align16(off + TC * 4);
+    s.win = off;    off = align16(off + nfft * 4);
+    s.tw = off;     off = align16(off + P::TW_TOTAL * 8);
+    s.ptw = off;    off = align16(off + NC * 8);
+    s.mel_i = off;  off = align16(off + (MODE == 0 ? 2 * M * 4 : 0));
+    s.mel_w = off;  off = align16(off + ((MODE == 0 && mel_in_smem) ? M * mel_stride * 4 : 0));
+    s.buf = off;    off = align16(off + (kThreads / P::G) * P::BUF * 8);
+    s.tile = off;   off = align16(off + (MODE == 1 ? (NC + 1) * (TC + 1) * 8 : 0));
+    s.total = off;
+    return s;
+}
+
+// padded-signal sample P(i): rescale -> utterance pre-emphasis -> reflect padding; 0 outside
+__device__ __forceinline__ float sample_P(const FrontendParams& p, const float* __restrict__ x, long long i) {
+    if (i < 0 || i >= p.S + 2LL * p.pad) return 0.f;
+    long long j = i - p.pad;
+    if (j < 0) j = -j;
+    else if (j >= p.S) j = 2 * (p.S - 1) - j;
+    float v = __ldg(x + j);
+    if (p.rescale) v = rintf(__fmul_rn(v, 32767.0f));
+    if (p.utt_pre != 0.f && j >= 1) {
+        float u = __ldg(x + j - 1);
+        if (p.rescale) u = rintf(__fmul_rn(u, 32767.0f));
+        v = __fsub_rn(v, __fmul_rn(p.utt_pre, u));
+    }
+    return v;
+}
+
+// MODE 0: features, MODE 1: complex STFT.  FI = feature values per lane (MODE 0).
+template <int NC, int MODE, int FI>
+__global__ void __launch_bounds__(kThreads) frontend_kernel(const __grid_constant__ FrontendParams p) {
+    using P = FFTPlan<NC>;
+    constexpr int G = P::G;
+    constexpr int NGROUPS = kThreads / G;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemLayout L = make_layout<NC, MODE>(p.nfft, p.hop, p.TC, p.ft.M, p.ft.mel_stride, p.ft.mel_in_smem);
+    float* sm_y = reinterpret_cast<float*>(smem + L.y);
+    float* sm_first = reinterpret_cast<float*>(smem + L.first);
+    float2* sm_win = reinterpret_cast<float2*>(smem + L.win);
+    float2* sm_tw = reinterpret_cast<float2*>(smem + L.tw);
+    float2* sm_ptw = reinterpret_cast<float2*>(smem + L.ptw);
+    int* sm_mel_i = reinterpret_cast<int*>(smem + L.mel_i);
+    float* sm_mel_w = reinterpret_cast<float*>(smem + L.mel_w);
+    float2* sm_tile = reinterpret_cast<float2*>(smem + L.tile);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int l = tid & (G - 1);
+    const int group = tid / G;
+    const unsigned mask = group_mask(G, lane);
+    float2* buf = reinterpret_cast<float2*>(smem + L.buf) + group * P::BUF;
+
+    // ---- per-CTA constant tables ----------------------------------------------------------------
+    {
+        float* w = reinterpret_cast<float*>(sm_win);
+        for (int i = tid; i < p.nfft; i += kThreads) w[i] = (i < p.width) ? __ldg(p.window + i) : 0.f;
+        for (int i = tid; i < P::TW_TOTAL; i += kThreads) sm_tw[i] = __ldg(p.tables + i);
+        const float h = 0.5f * p.scale;
+        for (int i = tid; i < NC; i += kThreads) {
+            float2 t = __ldg(p.tables + P::TW_TOTAL + i);
+            sm_ptw[i] = make_float2(h * t.x, h * t.y);
+        }
+        if (MODE == 0 && p.ft.M > 0) {
+            for (int i = tid; i < p.ft.M; i += kThreads) {
+                sm_mel_i[i] = __ldg(p.ft.mel_start + i);
+                sm_mel_i[p.ft.M + i] = __ldg(p.ft.mel_len + i);
+            }
+            if (p.ft.mel_in_smem)
+                for (int i = tid; i < p.ft.M * p.ft.mel_stride; i += kThreads) sm_mel_w[i] = __ldg(p.ft.mel_w + i);
+        }
+    }
+    const float half = 0.5f * p.scale;
+    const float* mel_w = (MODE == 0 && p.ft.mel_in_smem) ? sm_mel_w : p.ft.mel_w;
+    const bool hop_even = (p.hop & 1) == 0;
+
+    for (long long chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        const long long row = chunk / p.chunks_per_row;
+        const int c = (int)(chunk - row * p.chunks_per_row);
+        const int t0 = c * p.TC;
+        const int nf = min(p.TC, p.T - t0);
+        const long long start = (long long)t0 * p.hop;
+        const int len = (nf - 1) * p.hop + p.nfft;
+        const float* __restrict__ x = p.wav + row * p.ld;
+
+        __syncthreads();  // previous chunk fully consumed (also orders the table writes above)
+        // ---- stage samples: y[m] = P[m] - a P[m-1] -------------------------------------------------
+        if (p.frm_pre != 0.f) {
+            for (int i = tid; i < len; i += kThreads) {
+                const float cur = sample_P(p, x, start + i);
+                const float prv = sample_P(p, x, start + i - 1);
+                sm_y[i] = __fsub_rn(cur, __fmul_rn(p.frm_pre, prv));
+            }
+            for (int f = tid; f < nf; f += kThreads)
+                sm_first[f] = __fmul_rn(sample_P(p, x, start + (long long)f * p.hop), p.frm_one_minus);
+        } else {
+            for (int i = tid; i < len; i += kThreads) sm_y[i] = sample_P(p, x, start + i);
+        }
+        __syncthreads();
+
+        const int nf_round = (nf + NGROUPS - 1) / NGROUPS * NGROUPS;
+        for (int f = group; f < nf_round; f += NGROUPS) {
+            const int fe = min(f, nf - 1);
+            const float* ys = sm_y + fe * p.hop;
+            float2 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int n = l + G * q;
+                const float2 w = sm_win[n];
+                float2 s;
+                if (hop_even) s = *reinterpret_cast<const float2*>(ys + 2 * n);
+                else s = make_float2(ys[2 * n], ys[2 * n + 1]);
+                if (q == 0 && l == 0 && p.frm_pre != 0.f) s.x = sm_first[fe];
+                v[q] = make_float2(s.x * w.x, s.y * w.y);
+            }
+            group_fft<NC, false>(v, buf, sm_tw, l, mask);
+            float2 pr[16];
+            fetch_partner<NC>(v, pr, lane, l, mask);
+
+            if constexpr (MODE == 1) {
+                // ---- F2: write the one-sided spectrum into the transposed tile ------------------------
+                const int ts = p.TC + 1;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = l + G * q;
+                    float2 X = rfft_split(v[q], pr[q], sm_ptw[k], half);
+                    if (p.polar) X = make_float2(sqrtf(fmaf(X.x, X.x, fmaf(X.y, X.y, p.polar_eps))), atan2f(X.y, X.x));
+                    if (f < nf) sm_tile[k * ts + f] = X;
+                }
+                if (l == 0 && f < nf) {
+                    float2 X = make_float2((v[0].x - v[0].y) * p.scale, 0.f);
+                    if (p.polar) X = make_float2(sqrtf(fmaf(X.x, X.x, p.polar_eps)), atan2f(0.f, X.x));
+                    sm_tile[NC * ts + f] = X;
+                }
+                __syncwarp(mask);
+            } else {
+                // ---- F1: |X| (or |X|^2) -> group buffer ----------------------------------------------
+                float* mag = reinterpret_cast<float*>(buf);
+                __syncwarp(mask);  // every lane finished reading the exchange buffer
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = l + G * q;
+                    const float2 X = rfft_split(v[q], pr[q], sm_ptw[k], half);
+                    const float pw = fmaf(X.x, X.x, X.y * X.y);
+                    mag[k] = (p.ft.power == 2) ? pw : sqrtf(pw);
+                }
+                if (l == 0) {
+                    const float xn = (v[0].x - v[0].y) * p.scale;
+                    mag[NC] = (p.ft.power == 2) ? xn * xn : fabsf(xn);
+                }
+                __syncwarp(mask);
+
+                float* o = (f < nf) ? p.out + ((long long)row * p.T + (t0 + f)) * p.ld_out : nullptr;
+                feature_epilogue<G, FI>(p.ft, mag, sm_mel_i, mel_w, l, mask, o);
+                __syncwarp(mask);  // mags consumed before the next frame reuses the buffer
+            }
+        }
+
+        if constexpr (MODE == 1) {
+            __syncthreads();
+            const int ts = p.TC + 1;
+            float2* o = reinterpret_cast<float2*>(p.out) + (long long)row * (NC + 1) * p.T + t0;
+            for (int idx = tid; idx < (NC + 1) * nf; idx += kThreads) {
+                const int k = idx / nf, f = idx - k * nf;
+                o[(long long)k * p.T + f] = sm_tile[k * ts + f];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "all band" CMVN: statistics over (T, dims) of each row, in place (asr.py:587-596)
+__global__ void __launch_bounds__(1024) cmvn_allband_kernel(float* __restrict__ x, long long n, int norm_mean,
+                                                            int norm_var, float eps) {
+    __shared__ float red[32];
+    __shared__ float bcast;
+    float* r = x + (long long)blockIdx.x * n;
+    auto block_sum = [&](float v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) bcast = t;
+        }
+        __syncthreads();
+        return bcast;
+    };
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += r[i];
+    const float mean = block_sum(s) / (float)n;
+    const float sub = norm_mean ? mean : 0.f;
+    float den = 1.f;
+    if (norm_var) {
+        float q = 0.f;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const float d = r[i] - mean;
+            q += d * d;
+        }
+        den = sqrtf(block_sum(q) / (float)n + eps);
+    }
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) r[i] = (r[i] - sub) / den;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int log2i(int v) {
+    int r = 0;
+    while ((1 << r) < v) ++r;
+    return r;
+}
+
+template <int NC, int MODE, int FI>
+static int launch_frontend(FrontendParams& p, cudaStream_t st) {
+    auto kern = frontend_kernel<NC, MODE, FI>;
+    constexpr int G = FFTPlan<NC>::G;
+    constexpr int NGROUPS = kThreads / G;
+    // frames per chunk: a multiple of the groups per CTA, sized so that >= 2 CTAs fit per SM
+    int TC = (MODE == 0) ? 2 * NGROUPS : NGROUPS;
+    if (MODE == 0 && TC < 32) TC = 32;
+    while (TC > NGROUPS && TC / 2 >= p.T) TC /= 2;
+    p.ft.mel_in_smem = (p.ft.M * p.ft.mel_stride * 4 <= 24 * 1024) ? 1 : 0;
+    SmemLayout L = make_layout<NC, MODE>(p.nfft, p.hop, TC, p.ft.M, p.ft.mel_stride, p.ft.mel_in_smem);
+    while (L.total > 100 * 1024 && TC > NGROUPS) {
+        TC -= NGROUPS;
+        L = make_layout<NC, MODE>(p.nfft, p.hop, TC, p.ft.M, p.ft.mel_stride, p.ft.mel_in_smem);
+    }
+    APSB_CHECK_ARG(L.total <= 227 * 1024, "frontend: shared memory need %d B exceeds 227 KB (hop %d too large?)",
+                   L.total, p.hop);
+    p.TC = TC;
+    p.chunks_per_row = (p.T + TC - 1) / TC;
+    p.total_chunks = p.rows * p.chunks_per_row;
+    static int smem_set = -1, occ_smem = -1, occ_cached = 1;  // per instantiation; one GPU per process
+    if (L.total > smem_set) {
+        APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        smem_set = L.total;
+    }
+    if (L.total != occ_smem) {
+        int o = 0;
+        APSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, L.total));
+        occ_cached = o < 1 ? 1 : o;
+        occ_smem = L.total;
+    }
+    const int occ = occ_cached;
+    long long grid = (long long)num_sms() * occ;
+    if (grid > p.total_chunks) grid = p.total_chunks;
+    kern<<<(unsigned)grid, kThreads, L.total, st>>>(p);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE>
+static int dispatch_frontend(FrontendParams& p, cudaStream_t st) {
+    const int G = p.nfft / 32;
+    const int fi = (MODE == 0) ? (p.ft.D + G - 1) / G : 1;
+#define APSB_CASE(NC_)                                                                  \
+    case 2 * NC_:                                                                       \
+        if constexpr (MODE == 1) {                                                      \
+            return launch_frontend<NC_, MODE, 1>(p, st);                                \
+        } else {                                                                        \
+            if (fi <= 8) return launch_frontend<NC_, MODE, 8>(p, st);                   \
+            return launch_frontend<NC_, MODE, 17>(p, st);                               \
+        }
+    switch (p.nfft) {
+        APSB_CASE(32)
+        APSB_CASE(64)
+        APSB_CASE(128)
+        APSB_CASE(256)
+        APSB_CASE(512)
+        default:
+            return set_error(-1, "unsupported FFT size %d (need a power of two in [64, 1024])", p.nfft);
+    }
+#undef APSB_CASE
+}
+
+static int fill_params(FrontendParams& p, const float* wav, int64_t rows, int64_t S, int64_t ld,
+                       const aps_b200_stft_desc* d) {
+    APSB_CHECK_ARG(wav && d && d->window && d->twiddles, "null pointer argument");
+    APSB_CHECK_ARG(rows > 0 && S > 0 && ld >= S, "bad shape rows=%lld samples=%lld ld=%lld", (long long)rows,
+                   (long long)S, (long long)ld);
+    APSB_CHECK_ARG(d->nfft >= 64 && d->nfft <= 1024 && (1 << log2i(d->nfft)) == d->nfft,
+                   "unsupported FFT size %d (need a power of two in [64, 1024])", d->nfft);
+    APSB_CHECK_ARG(d->frame_width > 0 && d->frame_width <= d->nfft, "frame_width %d not in (0, nfft]", d->frame_width);
+    APSB_CHECK_ARG(d->hop > 0, "hop must be positive");
+    APSB_CHECK_ARG(d->center_pad >= 0 && d->center_pad < S, "reflect padding %d needs more than %d samples",
+                   d->center_pad, d->center_pad);
+    const int64_t T = aps_b200_num_frames(S, d->frame_width, d->hop, d->center_pad);
+    APSB_CHECK_ARG(T >= 1 && T < (1LL << 30), "no complete frame: samples=%lld frame_width=%d", (long long)S,
+                   d->frame_width);
+    p.wav = wav; p.ld = ld; p.rows = rows; p.S = S;
+    p.nfft = d->nfft; p.width = d->frame_width; p.hop = d->hop; p.pad = d->center_pad; p.rescale = d->rescale;
+    p.utt_pre = d->utt_preemph; p.frm_pre = d->frame_preemph; p.frm_one_minus = d->frame_one_minus;
+    p.scale = d->scale;
+    p.window = d->window;
+    p.tables = reinterpret_cast<const float2*>(d->twiddles);
+    p.T = (int)T;
+    return 0;
+}
+
+int fill_feat_params(FeatParams& p, const aps_b200_feat_desc* feat, int num_bins) {
+    APSB_CHECK_ARG(feat->power == 1 || feat->power == 2, "power must be 1 or 2");
+    p.power = feat->power;
+    p.M = feat->num_mels;
+    p.D = p.M > 0 ? p.M : num_bins;
+    if (p.M > 0)
+        APSB_CHECK_ARG(feat->mel_start && feat->mel_len && feat->mel_weight && feat->mel_stride > 0,
+                       "mel tables missing");
+    p.mel_start = feat->mel_start; p.mel_len = feat->mel_len; p.mel_w = feat->mel_weight;
+    p.mel_stride = p.M > 0 ? feat->mel_stride : 1;
+    p.mel_in_smem = 0;
+    p.log_mode = feat->log_mode; p.log_eps = feat->log_eps; p.log_lb = feat->log_lower_bound;
+    p.cmvn_mode = feat->cmvn_mode; p.norm_mean = feat->norm_mean; p.norm_var = feat->norm_var;
+    p.cmvn_eps = feat->cmvn_eps; p.gmean = feat->gmean; p.gstd = feat->gstd;
+    p.nan_count = feat->nan_count;
+    APSB_CHECK_ARG(p.cmvn_mode != 2 || ((!p.norm_mean || p.gmean) && (!p.norm_var || p.gstd)),
+                   "global cmvn statistics missing");
+    return 0;
+}
+
+}  // namespace apsb
+
+using namespace apsb;
+
+extern "C" int64_t aps_b200_num_frames(int64_t num_samples, int frame_width, int hop, int center_pad) {
+    // utils.py:653-662: trunc((len [+ 2*pad] - win_length) / hop) + 1.  NOTE the reference adds
+    // win_length (not 2*pad) when center=True; for the dense modes pad = win_length//2 so the two
+    // agree for even win_length.  The Python shell passes the reference's own integer rule for the
+    // user-visible num_frames; this function defines how many frames the KERNEL emits.
+    const int64_t eff = num_samples + 2LL * center_pad;
+    if (eff < frame_width) return 0;
+    return (eff - frame_width) / hop + 1;
+}
+
+extern "C" int64_t aps_b200_fft_table_floats(int nfft) {
+    switch (nfft) {
+        case 64: return 2 * (FFTPlan<32>::TW_TOTAL + 32);
+        case 128: return 2 * (FFTPlan<64>::TW_TOTAL + 64);
+        case 256: return 2 * (FFTPlan<128>::TW_TOTAL + 128);
+        case 512: return 2 * (FFTPlan<256>::TW_TOTAL + 256);
+        case 1024: return 2 * (FFTPlan<512>::TW_TOTAL + 512);
+        default: return 0;
+    }
+}
+
+template <int NC>
+static void fill_tables(int inverse, float* out) {
+    using P = FFTPlan<NC>;
+    const double sgn = inverse ? 1.0 : -1.0;
+    int o = 0;
+    auto pass = [&](int R, int Ns) {
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const double a = 2.0 * M_PI * (double)k * (double)r / ((double)Ns * (double)R);
+                out[2 * (o + (r - 1) * Ns + k)] = (float)cos(a);
+                out[2 * (o + (r - 1) * Ns + k) + 1] = (float)(sgn * sin(a));
+            }
+        o += (R - 1) * Ns;
+    };
+    pass(P::R1, P::NS1);
+    if (P::NPASS == 3) pass(P::R2, P::NS2);
+    for (int k = 0; k < NC; ++k) {  // split/merge table: (cos(pi k/NC), -sin(pi k/NC)) in both directions
+        const double a = M_PI * (double)k / (double)NC;
+        out[2 * (o + k)] = (float)cos(a);
+        out[2 * (o + k) + 1] = (float)(-sin(a));
+    }
+}
+
+extern "C" int aps_b200_fft_tables_host(int nfft, int inverse, float* out_host) {
+    APSB_CHECK_ARG(out_host, "null output");
+    switch (nfft) {
+        case 64: fill_tables<32>(inverse, out_host); break;
+        case 128: fill_tables<64>(inverse, out_host); break;
+        case 256: fill_tables<128>(inverse, out_host); break;
+        case 512: fill_tables<256>(inverse, out_host); break;
+        case 1024: fill_tables<512>(inverse, out_host); break;
+        default: return set_error(-1, "unsupported FFT size %d (need a power of two in [64, 1024])", nfft);
+    }
+    return 0;
+}
+
+extern "C" int aps_b200_feats_fwd(const float* wav, int64_t rows, int64_t num_samples, int64_t ld_wav,
+                                  const aps_b200_stft_desc* stft, const aps_b200_feat_desc* feat, float* out,
+                                  void* stream) {
+    FrontendParams p{};
+    if (int rc = fill_params(p, wav, rows, num_samples, ld_wav, stft)) return rc;
+    APSB_CHECK_ARG(feat && out, "null pointer argument");
+    if (int rc = fill_feat_params(p.ft, feat, p.nfft / 2 + 1)) return rc;
+    APSB_CHECK_ARG(p.ft.D <= 17 * (p.nfft / 32), "num_mels %d too large for nfft %d", p.ft.M, p.nfft);
+    p.ld_out = p.ft.D;
+    p.out = out;
+    return dispatch_frontend<0>(p, (cudaStream_t)stream);
+}
+
+extern "C" int aps_b200_stft_fwd(const float* wav, int64_t rows, int64_t num_samples, int64_t ld_wav,
+                                 const aps_b200_stft_desc* stft, int polar, float polar_eps, float* out,
+                                 void* stream) {
+    FrontendParams p{};
+    if (int rc = fill_params(p, wav, rows, num_samples, ld_wav, stft)) return rc;
+    APSB_CHECK_ARG(out, "null pointer argument");
+    p.polar = polar; p.polar_eps = polar_eps; p.out = out;
+    p.ft.M = 0; p.ft.D = p.nfft / 2 + 1; p.ft.mel_stride = 1;
+    return dispatch_frontend<1>(p, (cudaStream_t)stream);
+}
+
+extern "C" int aps_b200_cmvn_allband(float* x, int64_t rows, int64_t T, int64_t dims, int norm_mean, int norm_var,
+                                     float eps, void* stream) {
+    APSB_CHECK_ARG(x && rows > 0 && T > 0 && dims > 0, "bad arguments");
+    if (!norm_mean && !norm_var) return 0;
+    cmvn_allband_kernel<<<(unsigned)rows, 1024, 0, (cudaStream_t)stream>>>(x, (long long)T * dims, norm_mean,
+                                                                          norm_var, eps);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of this repo.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one synthetic batch.  Workload at every N (weak scaling,
+per-GPU work fixed): BASELINE.json configs[1] — AsrTransform STFT -> 80-mel fbank -> log -> per-frame
+CMVN on B = 256 x 4 s @ 16 kHz per GPU ("fbank-log-cmvn", frame 400 / hop 160, hamming,
+pre-emphasis 0.97, stft_mode librosa => 397 frames per utterance).  The batch is sharded per
+utterance: rank r owns its own 256 utterances, there is no data-path collective; one NCCL all-reduce
+carries {frames, max elapsed} after the timed region.
+
+Prints ONE JSON line on rank 0.  `value` = frames/s with inputs resident in HBM (CUDA events on the
+launching stream, max over ranks); `e2e` = the same metric through the public AsrTransform call with
+pinned HOST buffers, H2D of the waveforms and D2H of the features inside the timed region;
+`roofline` = algorithmic HBM bytes of the fused kernel / its event-timed duration against the measured
+copy bandwidth in MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle (a port of the reference's
+dense-DFT algorithm, oracle/transform.py) on a bounded sample with all host threads.
+
+`--impl reference` times that CPU port alone (the reference itself is PyTorch-on-CPU code that cannot
+travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch as th
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, SECONDS, BATCH, HOP, NFFT, MELS = 16000, 4, 256, 160, 512, 80
+S = SR * SECONDS
+T = (S - NFFT) // HOP + 1            # 397 (librosa mode)
+CFG = dict(feats="fbank-log-cmvn", frame_len=400, frame_hop=HOP, window="hamm", pre_emphasis=0.97,
+           num_mels=MELS, stft_mode="librosa")
+WORKLOAD = "AsrTransform fbank-log-cmvn (400/160, hamm, preemph 0.97, librosa), B=256 x 4 s @ 16 kHz per GPU"
+ALG_BYTES_PER_STEP = BATCH * S * 4 + BATCH * T * MELS * 4   # read every sample once + write 80 floats/frame
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_frames_per_s(seconds: float, batch: int = 32):
+    """The CPU oracle (port of the reference algorithm) on a bounded sample of the same workload."""
+    from oracle.transform import AsrFeatCfg, AsrFeatures
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    f = AsrFeatures(AsrFeatCfg(**CFG))
+    g = th.Generator().manual_seed(0)
+    x = 0.1 * th.randn(batch, S, generator=g)
+    lens = th.full((batch,), S, dtype=th.int64)
+    with th.no_grad():
+        f(x, lens)                                       # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            f(x, lens)
+            n += 1
+            el = time.perf_counter() - t0
+            if el >= seconds or n >= 200:
+                break
+    return batch * T * n / el, cores, f"{n} passes of B={batch} x 4 s ({el:.1f} s wall, torch CPU fp32, {cores} threads)"
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU algorithm (oracle port) on this box's host cores."""
+    if rank != 0:
+        return
+    from oracle.transform import AsrFeatCfg, AsrFeatures
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    batch = 32
+    f = AsrFeatures(AsrFeatCfg(**CFG))
+    x = 0.1 * th.randn(batch, S, generator=th.Generator().manual_seed(0))
+    lens = th.full((batch,), S, dtype=th.int64)
+    with th.no_grad():
+        for _ in range(args.warmup):
+            f(x, lens)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            f(x, lens)
+        el = time.perf_counter() - t0
+    val = batch * T * args.steps / el
+    sample = f"each step = B={batch} x 4 s of the same workload on {cores} host threads (torch CPU fp32)"
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    import torch.distributed as dist
+    from aps_b200 import _lib
+    from aps_b200.transform import AsrTransform
+    assert th.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()                                          # fail loudly if the CUDA library is missing
+    transform = AsrTransform(**CFG).to(dev).eval()
+    lens = th.full((BATCH,), S, dtype=th.int64)          # host-side lengths (the loader's egs["src_len"])
+
+    # ---- inputs: R distinct resident batches so a step never finds its input in the 126 MB L2 ------------
+    R = 4
+    gen = th.Generator(device=dev).manual_seed(1234 + rank)
+    wavs = [0.1 * th.randn(BATCH, S, device=dev, generator=gen) for _ in range(R)]
+    launches = 0
+
+    def step(i):
+        feats, nf = transform(wavs[i % R], None)
+        return feats
+
+    stream = th.cuda.current_stream(dev)
+    for i in range(args.warmup):
+        out = step(i)
+    th.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident timing: K steps, CUDA events on the launching stream ---------------------------
+    th.cuda.synchronize(dev)
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        out = step(i)
+        launches += 1
+    e1.record(stream)
+    th.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    frames = BATCH * out.shape[1] * args.steps
+    assert out.shape == (BATCH, T, MELS)
+
+    # ---- end to end through the public call with pinned host buffers --------------------------------------
+    h_in = [th.empty(BATCH, S, pin_memory=True).copy_(w) for w in wavs[:2]]
+    h_out = th.empty(BATCH, T, MELS, pin_memory=True)
+    d_in = th.empty(BATCH, S, device=dev)
+
+    def e2e_step(i):
+        d_in.copy_(h_in[i % 2], non_blocking=True)
+        feats, nf = transform(d_in, lens)                # lengths on the host: no device sync for num_frames
+        h_out.copy_(feats, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    th.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    k2 = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    f0, f1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for i in range(k2):
+        e2e_step(i)
+        launches += 1
+    f1.record(stream)
+    th.cuda.synchronize(dev)
+    e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- aggregate over ranks: max time, sum frames -----------------------------------------------------------
+    stats = th.tensor([ms, e2e_ms, float(frames), float(BATCH * T * k2)], dtype=th.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, frames, e2e_frames = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+    else:
+        e2e_frames = float(stats[3])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = frames / (ms * 1e-3)
+    peak, peak_src = peaks()
+    kern_ms = ms / args.steps                            # one kernel per step
+    achieved = ALG_BYTES_PER_STEP / (kern_ms * 1e-3) / 1e9
+    cpu_v, cores, sample = cpu_port_frames_per_s(args.cpu_seconds) if world >= 1 else (None, 0, "")
+    line = {
+        "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": BATCH * T, "parallelism": f"dp{world} (batch shard, no data-path collective)",
+                   "l2": f"{R} distinct resident input batches rotate (4 x 98 MB in+out > 126 MB L2), no flush inside the timed region"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "frontend_kernel<256,0,8> (fused framing+preemph+window+rFFT+|X|+mel+log+cmvn)",
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP, "peak_source": peak_src,
+                     "kernel_ms": kern_ms},
+        "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": BATCH * S * 4,
+                "d2h_bytes_per_step": BATCH * T * MELS * 4, "steps": k2,
+                "path": "AsrTransform.forward on a pinned-host batch: H2D -> fused kernel -> D2H, one stream"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

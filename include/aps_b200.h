@@ -1,0 +1,140 @@
+/*
+ * aps_b200.h — C ABI of libaps_b200.so: the B200 (sm_100a) kernels behind the APS hot path.
+ *
+ * The reference (funcwj/aps) has no FFI: its boundary is the Python nn.Module surface
+ * (SURVEY.md §8b).  This header is the boundary a maintainer would bind from Python
+ * (ctypes — see INTEGRATION.md) underneath those modules.  Every entry point names the
+ * reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`; all tensors fp32,
+ *     row-major contiguous unless a leading dimension is passed;
+ *   - the library never allocates or frees device memory and keeps no pointer after a call
+ *     returns; scratch is caller-provided;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and return immediately;
+ *   - return value 0 = ok; < 0 = error, text via aps_b200_last_error().  CUDA failures carry the
+ *     CUDA error string (so "out of memory" stays greppable for the reference trainer's OOM
+ *     guard, aps/trainer/ddp.py:146 + aps/const.py:23).
+ */
+#ifndef APS_B200_H_
+#define APS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APS_B200_ABI_VERSION 1
+
+/* library / device ------------------------------------------------------------------------ */
+int aps_b200_abi_version(void);
+/* Selects `device`, checks it is compute capability 10.x, caches the SM count. */
+int aps_b200_init(int device);
+/* Copies the calling thread's last error message (NUL terminated) into buf. */
+int aps_b200_last_error(char* buf, size_t len);
+
+/* STFT front-end --------------------------------------------------------------------------
+ * One descriptor drives both the fused feature kernel (F1) and the complex STFT kernel (F2).
+ * Replaces aps/transform/utils.py:227-290 (_forward_stft: reflect pad :257-260, per-frame
+ * Kaldi pre-emphasis :263-272, window*DFT :262/:274, one-sided slice :281-284),
+ * utils.py:363-415 (_pytorch_stft), asr.py:84 (RescaleTransform), asr.py:111-113
+ * (PreEmphasisTransform).
+ */
+typedef struct aps_b200_stft_desc {
+    int32_t nfft;          /* FFT size, power of two in [64, 1024]                               */
+    int32_t frame_width;   /* samples covered by a frame: nfft (librosa/torch) or frame_len (kaldi) */
+    int32_t hop;           /* frame shift                                                         */
+    int32_t center_pad;    /* reflect padding on both sides in samples (0 = center False)         */
+    int32_t rescale;       /* 1: x <- rint(x*32767) first (audio_norm=False)                      */
+    float   utt_preemph;   /* utterance-level pre-emphasis ("emph" token), 0 = off                */
+    float   frame_preemph; /* per-frame Kaldi pre-emphasis coefficient, 0 = off                   */
+    float   frame_one_minus; /* float32(1 - frame_preemph) as the reference computes it            */
+    float   scale;         /* 1, or 1/sqrt(nfft) when stft_normalized                             */
+    const float* window;   /* [frame_width] analysis window (already centre-padded if needed)     */
+    const float* twiddles; /* table from aps_b200_fft_tables_host(nfft, inverse=0), on device     */
+} aps_b200_stft_desc;
+
+/* Number of floats in the twiddle table for `nfft` (0 if nfft is unsupported). */
+int64_t aps_b200_fft_table_floats(int nfft);
+/* Fills a HOST buffer of aps_b200_fft_table_floats(nfft) floats; the caller uploads it once. */
+int aps_b200_fft_tables_host(int nfft, int inverse, float* out_host);
+
+/* Number of frames for `num_samples` (bit-exact integer rule of utils.py:653-662). */
+int64_t aps_b200_num_frames(int64_t num_samples, int frame_width, int hop, int center_pad);
+
+/* Epilogue of the fused feature kernel.
+ * Replaces asr.py:296-303 (MagnitudeTransform), :216-223 (TFTranspose), :350-357 (Power),
+ * :416-428 (MelTransform), :453-464 (LogTransform), :576-618 (CmvnTransform, per-frame and
+ * global variants; "all band" runs as aps_b200_cmvn_allband afterwards).
+ */
+typedef struct aps_b200_feat_desc {
+    int32_t power;         /* 1: |X|, 2: |X|^2                                                    */
+    int32_t num_mels;      /* 0: linear spectrogram output (nfft/2+1 dims)                        */
+    const int32_t* mel_start; /* [num_mels] first bin of each band                                */
+    const int32_t* mel_len;   /* [num_mels] number of bins of each band                           */
+    const float* mel_weight;  /* [num_mels, mel_stride] band weights, zero padded                 */
+    int32_t mel_stride;
+    int32_t log_mode;      /* 0 none, 1 log(clamp(x, min=log_eps)), 2 log(log_lower_bound + x)    */
+    float   log_eps;
+    float   log_lower_bound;
+    int32_t cmvn_mode;     /* 0 none, 1 per frame over the feature axis, 2 global mean/std        */
+    int32_t norm_mean;
+    int32_t norm_var;
+    float   cmvn_eps;
+    const float* gmean;    /* [dims] (cmvn_mode 2) */
+    const float* gstd;     /* [dims] (cmvn_mode 2) */
+    int32_t* nan_count;    /* optional: += number of NaN feature values written (asr.py:41-45)   */
+} aps_b200_feat_desc;
+
+/* F1: wav [rows, num_samples] (row stride ld_wav floats) -> feats [rows, T, dims],
+ * T = aps_b200_num_frames(num_samples, ...), dims = num_mels or nfft/2+1.               */
+int aps_b200_feats_fwd(const float* wav, int64_t rows, int64_t num_samples, int64_t ld_wav,
+                       const aps_b200_stft_desc* stft, const aps_b200_feat_desc* feat,
+                       float* out, void* stream);
+
+/* F2: wav [rows, num_samples] -> packed STFT [rows, nfft/2+1, T, 2] (real, imag) or, with
+ * polar != 0, (sqrt(re^2+im^2+polar_eps), atan2(im, re)) — utils.py:285-288.             */
+int aps_b200_stft_fwd(const float* wav, int64_t rows, int64_t num_samples, int64_t ld_wav,
+                      const aps_b200_stft_desc* stft, int polar, float polar_eps,
+                      float* out, void* stream);
+
+/* F3: packed STFT [rows, nfft/2+1, T, 2] -> wav [rows, aps_b200_istft_num_samples(T, ...)].
+ * `stft->twiddles` must be the INVERSE table (aps_b200_fft_tables_host(nfft, 1, ...)),
+ * `stft->scale` = 1/nfft (or 1/sqrt(nfft) when normalized), `stft->window` the synthesis window
+ * of `frame_width` samples; hop / center_pad as in the forward transform.  `polar` != 0 reads
+ * (magnitude, phase).  Replaces aps/transform/utils.py:293-360 (_inverse_stft: Hermitian mirror
+ * :327-332, iDFT conv_transpose1d :336, window^2 overlap-add :345-349, centre trim :354-357,
+ * divide :358) and :418-469 (_pytorch_istft).                                              */
+int64_t aps_b200_istft_num_samples(int64_t num_frames, int frame_width, int hop, int center_pad);
+int aps_b200_istft_fwd(const float* spec, int64_t rows, int64_t num_frames,
+                       const aps_b200_stft_desc* stft, int polar, float eps, float* out,
+                       void* stream);
+
+/* F1b: features from a packed STFT [rows, channels, num_bins, T, 2]: reference channel ->
+ * sqrt(re^2+im^2+mag_eps) -> power -> [mel] -> [log] -> [cmvn] -> out[rows, T, ld_out] (first
+ * `dims` columns).  Replaces aps/transform/enh.py:39-49 (RefChannelTransform) + the layer chain
+ * asr.py:296-303, :216-223, :350-357, :416-428, :453-464, :576-618 as composed by
+ * enh.py:518-529 and run by enh.py:595-613.                                               */
+int aps_b200_spec_feats_fwd(const float* spec, int64_t rows, int64_t channels, int64_t ref_channel,
+                            int64_t num_bins, int64_t num_frames, float mag_eps,
+                            const aps_b200_feat_desc* feat, float* out, int64_t ld_out,
+                            void* stream);
+
+/* IPD: out[n, t, col0 + m*F + k] = cos(angle(x[n, l_m, k, t]) - angle(x[n, r_m, k, t])), and with
+ * with_sin != 0 the sines in columns col0 + (P+m)*F + k.  index_l / index_r: device int32[P].
+ * Replaces aps/transform/enh.py:67-76 (PhaseTransform) + :112-143 (IpdTransform).          */
+int aps_b200_ipd_fwd(const float* spec, int64_t batch, int64_t channels, int64_t num_bins,
+                     int64_t num_frames, const int32_t* index_l, const int32_t* index_r,
+                     int64_t num_pairs, int with_sin, float* out, int64_t ld_out, int64_t col0,
+                     void* stream);
+
+/* Utterance-level "all band" CMVN over (T, dims) in place — asr.py:587-596. x: [rows, T, dims] */
+int aps_b200_cmvn_allband(float* x, int64_t rows, int64_t T, int64_t dims, int norm_mean,
+                          int norm_var, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APS_B200_H_ */

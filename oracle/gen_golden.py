@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.npz from the LIVE reference (funcwj/aps at /root/reference).
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+Every file stores the seeded INPUTS next to the reference's OUTPUTS and the constructor kwargs
+(as a JSON string), so the tests need neither the reference nor an RNG-compatible torch build.
+The reference is imported unmodified; `oracle/ref_shims/` only supplies the three third-party
+modules that are absent from this image (librosa.filters.mel, kaldi_python_io, soundfile).
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch as th
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("APS_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_shims"), REF]
+warnings.filterwarnings("ignore")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, kwargs, **arrays):
+    arrays = {k: (v.detach().cpu().numpy() if isinstance(v, th.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kwargs=json.dumps(kwargs), **arrays)
+    print(f"{name}: " + ", ".join(f"{k}{list(v.shape)}" for k, v in arrays.items()))
+
+
+def wave(seed, *shape, kind="randn"):
+    g = th.Generator().manual_seed(seed)
+    if kind == "randn":
+        return 0.1 * th.randn(*shape, generator=g)
+    return th.rand(*shape, generator=g)
+
+
+def main():
+    from aps.transform import AsrTransform, EnhTransform
+    from aps.transform.utils import STFT, iSTFT
+    th.set_num_threads(4)
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- AsrTransform: BASELINE config[0] (1 utt x 4 s) in the three stft modes ---------------------
+    for mode in ("librosa", "kaldi", "torch"):
+        kw = dict(feats="fbank-log-cmvn", frame_len=400, frame_hop=160, window="hamm", pre_emphasis=0.97,
+                  num_mels=80, stft_mode=mode)
+        x = wave(1, 1, 64000)
+        y, n = AsrTransform(**kw)(x.clone(), th.tensor([64000]))
+        if mode == "librosa":
+            save("asr_c1_input", {}, wav=x)                      # shared by the three modes
+        save(f"asr_c1_{mode}", kw, feats=y, num_frames=n)
+    # ---- ragged batch, assorted epilogues ------------------------------------------------------------
+    grid = [
+        dict(feats="fbank-log-cmvn", stft_mode="kaldi", audio_norm=False, log_lower_bound=1.0),   # aishell 1e
+        dict(feats="spectrogram-log-cmvn", stft_mode="librosa", use_power=True, norm_per_band=False),
+        dict(feats="emph-fbank-log-cmvn", stft_mode="librosa", use_power=True, pre_emphasis=0.96),
+        dict(feats="fbank-log", stft_mode="librosa", center=True, num_mels=40, window="hann"),
+        dict(feats="spectrogram", stft_mode="torch", center=True, stft_normalized=True),
+        dict(feats="fbank-log-cmvn", stft_mode="librosa", frame_len=200, frame_hop=80, norm_var=False,
+             pre_emphasis=0.0),
+        dict(feats="fbank-log-cmvn-splice-delta", stft_mode="librosa", lctx=1, rctx=1),
+        dict(feats="mfcc", stft_mode="kaldi", lifter=22),
+    ]
+    for i, kw in enumerate(grid):
+        x = wave(10 + i, 3, 8000, kind="rand" if i % 2 else "randn")
+        lens = th.tensor([8000, 6500, 4000])
+        y, n = AsrTransform(**kw)(x.clone(), lens.clone())
+        save(f"asr_grid_{i}", kw, wav=x, lens=lens, feats=y, num_frames=n)
+    # ---- STFT / iSTFT (the reference's own test sizes, tests/python/test_transform.py:21-37) ---------
+    k = 0
+    for mode in ("librosa", "kaldi", "torch"):
+        for (fl, fh) in ((512, 256), (1024, 256), (256, 128), (400, 160)):
+            for window, center in (("sqrthann", True), ("hamm", False)):
+                if mode == "kaldi" and fl != 400:
+                    continue
+                kw = dict(frame_len=fl, frame_hop=fh, window=window, center=center, mode=mode)
+                x = wave(100 + k, 2, 3, 3000) if k % 2 else wave(100 + k, 2, 3000)
+                spec = STFT(**kw)(x)
+                save(f"stft_{k}", kw, wav=x, spec=spec)
+                if x.dim() == 2 and not (mode == "torch" and not center):
+                    rec = iSTFT(**kw)(spec)
+                    save(f"istft_{k}", kw, spec=spec, wav=rec)
+                k += 1
+    # polar in / out
+    kw = dict(frame_len=512, frame_hop=256, window="sqrthann", center=False, mode="librosa")
+    x = wave(200, 2, 4000)
+    pol = STFT(**kw)(x, return_polar=True)
+    save("stft_polar", kw, wav=x, spec=pol, rec=iSTFT(**kw)(pol, return_polar=True))
+    # ---- EnhTransform: encode / forward(+IPD) / decode ---------------------------------------------------
+    for i, kw in enumerate([
+            dict(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, window="sqrthann"),
+            dict(feats="spectrogram-log-cmvn-ipd", frame_len=512, frame_hop=256, ipd_index="0,1;0,2;0,3",
+                 cos_ipd=True, sin_ipd=True, ref_channel=1),
+            dict(feats="fbank-log-ipd", frame_len=400, frame_hop=160, ipd_index="1,0", num_mels=40, center=True),
+    ]):
+        x = wave(300 + i, 2, 4, 4000)
+        t = EnhTransform(**kw)
+        packed, n = t.encode(x, th.tensor([4000, 3500]))
+        feats = t(packed)
+        rec = t.decode([packed[:, 0]])[0]
+        save(f"enh_{i}", kw, wav=x, packed=packed, num_frames=n, feats=feats, rec=rec)
+    # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
+    t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
+                     audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)
+    sd = {k: list(v.shape) for k, v in t.state_dict().items()}
+    e = EnhTransform(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256)
+    sd_e = {k: list(v.shape) for k, v in e.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_layout.json"), "w") as fd:
+        json.dump({"asr_aishell_1e": sd, "enh_default": sd_e}, fd, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch as th
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = os.environ.get("APS_REFERENCE", "/root/reference")
+HAS_REFERENCE = os.path.isdir(os.path.join(REFERENCE, "aps"))
+FLOAT_TOL = 1e-4  # BASELINE.json north_star: |delta| <= 1e-4 relative to max|ref| per tensor
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "reference: needs the live reference tree (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    skip_ref = pytest.mark.skip(reason="live reference tree not present")
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "reference" in item.keywords and not HAS_REFERENCE:
+            item.add_marker(skip_ref)
+        if "gpu" in item.keywords and not th.cuda.is_available():
+            item.add_marker(skip_gpu)
+
+
+def load_golden(name):
+    """-> (kwargs dict, {array name: torch tensor})"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    kw = json.loads(str(z["kwargs"]))
+    arrs = {k: th.from_numpy(z[k]) for k in z.files if k != "kwargs"}
+    return kw, arrs
+
+
+def golden_names(prefix):
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith(prefix) and f.endswith(".npz"))
+
+
+def rel_err(got: th.Tensor, ref: th.Tensor) -> float:
+    """max |got - ref| / max |ref| (the tolerance metric of SURVEY.md §8d)."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    assert got.shape == ref.shape, f"shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def import_reference():
+    """Import the unmodified reference through the stand-in third-party modules."""
+    for p in (REFERENCE, os.path.join(ROOT, "oracle", "ref_shims")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings("ignore")
+    import aps  # noqa: F401
+    return aps
