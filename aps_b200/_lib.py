@@ -13,7 +13,8 @@ import numpy as np
 import torch as th
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaps_b200.so")
+# APS_B200_LIB selects a tuning build of the same ABI (see aps_b200/build.py); default: the in-tree library
+LIB_PATH = os.environ.get("APS_B200_LIB") or os.path.join(_HERE, "libaps_b200.so")
 ABI_VERSION = 1
 
 

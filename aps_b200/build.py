@@ -15,10 +15,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(ROOT, "build")
-LIB = os.path.join(HERE, "libaps_b200.so")
+# tuning builds: APS_B200_VARIANT=<tag> + APS_B200_NVCC_EXTRA="-DFOO=1" -> libaps_b200_<tag>.so, build/<tag>/
+VARIANT = os.environ.get("APS_B200_VARIANT", "")
+OBJ = os.path.join(ROOT, "build", VARIANT) if VARIANT else os.path.join(ROOT, "build")
+LIB = os.path.join(HERE, f"libaps_b200_{VARIANT}.so" if VARIANT else "libaps_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"
+              ] + os.environ.get("APS_B200_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

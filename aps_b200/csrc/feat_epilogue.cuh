@@ -28,12 +28,13 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 }
 
 // mag      : this frame's |X| or |X|^2, D_in = F values (shared memory)
-// sm_mel_i : [2*M] band start / length (shared);  mel_w: [M, mel_stride] weights (shared or global)
+// sm_mel_i : [2*M + FI] band start / length, then per lane-slot i the max length over bands d = l + G*i (shared);  sm_mel_w: [M, mel_stride] weights in shared memory
+//            (used when p.mel_in_smem, else p.mel_w in global memory)
 // o        : output row of this frame (D floats) or nullptr to skip the store
 template <int G, int FI>
 __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const float* __restrict__ mag,
                                                  const int* __restrict__ sm_mel_i,
-                                                 const float* __restrict__ mel_w, int l, unsigned mask,
+                                                 const float* __restrict__ sm_mel_w, int l, unsigned mask,
                                                  float* __restrict__ o) {
     float feat[FI];
     const int D = p.D;
@@ -44,12 +45,24 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
         if (d < D) {
             if (p.M > 0) {
                 const int s0 = sm_mel_i[d], n = sm_mel_i[p.M + d];
-                const float* wr = mel_w + d * p.mel_stride;
-                for (int t = 0; t < n; ++t) acc = fmaf(wr[t], mag[s0 + t], acc);
+                const float* mg = mag + s0;
+                if (p.mel_in_smem) {   // keep the two address spaces apart: LDS, not generic LD
+                    // uniform trip count for the whole group (weights are zero padded to mel_stride and the
+                    // magnitude buffer has slack behind bin F-1), so there is no lane divergence
+                    const float* wr = sm_mel_w + d * p.mel_stride;
+                    const int nmax = sm_mel_i[2 * p.M + i];
+#pragma unroll 4
+                    for (int t = 0; t < nmax; ++t) acc = fmaf(wr[t], mg[t], acc);
+                } else {
+                    const float* wr = p.mel_w + d * p.mel_stride;
+                    for (int t = 0; t < n; ++t) acc = fmaf(__ldg(wr + t), mg[t], acc);
+                }
             } else {
                 acc = mag[d];
             }
-            if (p.log_mode == 1) acc = logf(acc < p.log_eps ? p.log_eps : acc);
+            // clamp mode: __logf (MUFU.LG2, abs err < 4e-7) — far inside the 1e-4 budget after CMVN;
+            // lower-bound mode keeps the fully accurate logf because log(lb + x) can sit next to 0
+            if (p.log_mode == 1) acc = __logf(acc < p.log_eps ? p.log_eps : acc);
             else if (p.log_mode == 2) acc = logf(p.log_lb + acc);
         }
         feat[i] = acc;
@@ -58,10 +71,13 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
         const float invD = 1.0f / (float)D;
         float mean = 0.f;
         if (p.norm_mean || p.norm_var) {
+            // shifted mean: pivot + mean(x - pivot).  Exact for a constant frame (digital silence), where
+            // 1/sqrt(var+eps) ~ 2900 would otherwise amplify one ulp of the mean into a visible feature.
+            const float pivot = __shfl_sync(mask, feat[0], (threadIdx.x & 31) & ~(G - 1));
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < FI; ++i) s += (l + G * i < D) ? feat[i] : 0.f;
-            mean = group_sum<G>(s, mask) * invD;
+            for (int i = 0; i < FI; ++i) s += (l + G * i < D) ? feat[i] - pivot : 0.f;
+            mean = fmaf(group_sum<G>(s, mask), invD, pivot);
         }
         if (p.norm_mean) {
 #pragma unroll
@@ -76,9 +92,9 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
                 s += (l + G * i < D) ? dlt * dlt : 0.f;
             }
             const float var = group_sum<G>(s, mask) * invD;
-            const float den = sqrtf(var + p.cmvn_eps);
+            const float inv = 1.0f / sqrtf(var + p.cmvn_eps);
 #pragma unroll
-            for (int i = 0; i < FI; ++i) feat[i] = feat[i] / den;
+            for (int i = 0; i < FI; ++i) feat[i] *= inv;
         }
     } else if (p.cmvn_mode == 2) {
 #pragma unroll

@@ -139,7 +139,9 @@ struct FFTPlan {
     static constexpr int TW1 = (R1 - 1) * NS1;
     static constexpr int TW2 = (NPASS == 3) ? (R2 - 1) * NS2 : 0;
     static constexpr int TW_TOTAL = TW1 + TW2;
-    static constexpr int BUF = NC + NC / 16;                // padded exchange buffer (float2)
+    // padded exchange buffer (float2); the +8 makes consecutive groups' buffers start 64 bytes apart
+    // modulo 128, so the two half-warps of a warp (G = 16) use complementary shared-memory banks
+    static constexpr int BUF = NC + NC / 16 + 8;
 };
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
@@ -219,6 +221,16 @@ __device__ __forceinline__ void fetch_partner(const float2 (&v)[16], float2 (&p)
         const float2 own = v[(16 - q) & 15];
         p[q] = (l == 0) ? own : make_float2(sx, sy);
     }
+}
+
+// One partner value (see fetch_partner) for register q; all lanes of the group must call it together.
+template <int NC>
+__device__ __forceinline__ float2 partner_of(const float2 (&v)[16], int q_static_15_minus_q, int q_static_own,
+                                             int src, int l, unsigned mask) {
+    const float sx = __shfl_sync(mask, v[q_static_15_minus_q].x, src);
+    const float sy = __shfl_sync(mask, v[q_static_15_minus_q].y, src);
+    const float2 own = v[q_static_own];
+    return (l == 0) ? own : make_float2(sx, sy);
 }
 
 // Split the packed transform Z (length NC) into the one-sided real-input spectrum.

@@ -26,11 +26,15 @@
 #include "feat_epilogue.cuh"
 
 #include <math.h>
-#include <vector>
+#include <stdlib.h>
 
 namespace apsb {
 
 constexpr int kThreads = 256;
+#ifndef APSB_FRONTEND_MINB
+#define APSB_FRONTEND_MINB 3   // register allocation capped (80) so that 3 CTAs fit per SM
+#endif
+static const bool g_disable_tma = getenv("APS_B200_NO_TMA") != nullptr;  // debugging aid only
 
 struct FrontendParams {
     const float* wav;
@@ -38,6 +42,7 @@ struct FrontendParams {
     long long rows;
     long long S;          // samples per row
     int nfft, width, hop, pad, rescale;
+    int tma_ok;           // wav base 16-B aligned, ld % 4 == 0, (TC*hop) % 4 == 0, pad % 4 == 0
     float utt_pre, frm_pre, frm_one_minus, scale;
     const float* window;
     const float2* tables;
@@ -57,7 +62,7 @@ struct FrontendParams {
 
 // ---- shared memory carve-up (byte offsets computed identically on host and device) -------------
 struct SmemLayout {
-    int y, first, win, tw, ptw, mel_i, mel_w, buf, tile, total;
+    int raw, y, first, win, tw, ptw, mel_i, mel_w, buf, tile, mbar, total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -67,15 +72,17 @@ __host__ __device__ inline SmemLayout make_layout(int nfft, int hop, int TC, int
     using P = FFTPlan<NC>;
     SmemLayout s;
     int off = 0;
+    s.raw = off;    off = align16(off + ((TC - 1) * hop + nfft + 8) * 4);   // 4 halo floats + chunk span
     s.y = off;      off = align16(off + ((TC - 1) * hop + nfft + 4) * 4);
     s.first = off;  off = align16(off + TC * 4);
     s.win = off;    off = align16(off + nfft * 4);
     s.tw = off;     off = align16(off + P::TW_TOTAL * 8);
     s.ptw = off;    off = align16(off + NC * 8);
-    s.mel_i = off;  off = align16(off + (MODE == 0 ? 2 * M * 4 : 0));
+    s.mel_i = off;  off = align16(off + (MODE == 0 ? (2 * M + 40) * 4 : 0));
     s.mel_w = off;  off = align16(off + ((MODE == 0 && mel_in_smem) ? M * mel_stride * 4 : 0));
     s.buf = off;    off = align16(off + (kThreads / P::G) * P::BUF * 8);
     s.tile = off;   off = align16(off + (MODE == 1 ? (NC + 1) * (TC + 1) * 8 : 0));
+    s.mbar = off;   off = align16(off + 8);
     s.total = off;
     return s;
 }
@@ -96,14 +103,86 @@ __device__ __forceinline__ float sample_P(const FrontendParams& p, const float* 
     return v;
 }
 
+
+// ---- TMA (1-D bulk async copy) + mbarrier helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned; completes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Geometry of one chunk and how its raw span is fetched.
+struct ChunkGeo {
+    long long row, start, g0;  // g0: source index of raw[0] (= start - pad - 4)
+    int t0, nf, len;
+    int tma;                   // 1: raw holds plain samples fetched by a bulk copy (+ thread-filled edges)
+    int lo_off, n4;            // bulk copy: raw[lo_off .. lo_off+n4) <- x[g0+lo_off ..]
+};
+
+__device__ __forceinline__ ChunkGeo chunk_geo(const FrontendParams& p, long long chunk) {
+    ChunkGeo g;
+    g.row = chunk / p.chunks_per_row;
+    const int c = (int)(chunk - g.row * p.chunks_per_row);
+    g.t0 = c * p.TC;
+    g.nf = min(p.TC, p.T - g.t0);
+    g.start = (long long)g.t0 * p.hop;
+    g.len = (g.nf - 1) * p.hop + p.nfft;
+    g.g0 = g.start - p.pad - 4;
+    const long long end = g.g0 + 4 + g.len;  // one past the last source index touched
+    // bulk copy when no reflection is involved: the span starts inside the row (or exactly 4 before it
+    // with no padding) and, if padding is on, also ends inside the row
+    const bool head_ok = (g.g0 >= 0) || (p.pad == 0 && g.g0 == -4);
+    const bool tail_ok = (p.pad == 0) || (end <= p.S);
+    g.tma = (p.tma_ok && head_ok && tail_ok) ? 1 : 0;
+    g.lo_off = g.g0 < 0 ? 4 : 0;
+    const long long hi = min(p.S, end);
+    const long long n = hi - (g.g0 + g.lo_off);
+    g.n4 = n > 0 ? (int)(n & ~3LL) : 0;
+    if (g.n4 == 0) g.tma = 0;
+    return g;
+}
+
+// sqrt(x) for x >= 0 as ONE MUFU op: sqrt.approx.ftz.f32 (max relative error 2^-23, PTX ISA), no slow-path
+// branch; sub-normal inputs flush to 0 (an absolute error < 1.1e-19).
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // MODE 0: features, MODE 1: complex STFT.  FI = feature values per lane (MODE 0).
 template <int NC, int MODE, int FI>
-__global__ void __launch_bounds__(kThreads) frontend_kernel(const __grid_constant__ FrontendParams p) {
+__global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(const __grid_constant__ FrontendParams p) {
     using P = FFTPlan<NC>;
     constexpr int G = P::G;
     constexpr int NGROUPS = kThreads / G;
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = make_layout<NC, MODE>(p.nfft, p.hop, p.TC, p.ft.M, p.ft.mel_stride, p.ft.mel_in_smem);
+    float* sm_raw = reinterpret_cast<float*>(smem + L.raw);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.mbar);
     float* sm_y = reinterpret_cast<float*>(smem + L.y);
     float* sm_first = reinterpret_cast<float*>(smem + L.first);
     float2* sm_win = reinterpret_cast<float2*>(smem + L.win);
@@ -138,53 +217,140 @@ __global__ void __launch_bounds__(kThreads) frontend_kernel(const __grid_constan
             if (p.ft.mel_in_smem)
                 for (int i = tid; i < p.ft.M * p.ft.mel_stride; i += kThreads) sm_mel_w[i] = __ldg(p.ft.mel_w + i);
         }
+        // exchange buffers start zeroed: their pad slots are never written and the mel loop may read them
+        // (times a zero weight)
+        float* zb = reinterpret_cast<float*>(smem + L.buf);
+        for (int i = tid; i < NGROUPS * P::BUF * 2; i += kThreads) zb[i] = 0.f;
+    }
+    if (MODE == 0 && p.ft.M > 0) {
+        __syncthreads();
+        if (tid < FI) {  // longest band among the G bands that share lane slot `tid`
+            int mx = 0;
+            for (int d = G * tid; d < min(p.ft.M, G * tid + G); ++d) mx = max(mx, sm_mel_i[p.ft.M + d]);
+            sm_mel_i[2 * p.ft.M + tid] = mx;
+        }
     }
     const float half = 0.5f * p.scale;
-    const float* mel_w = (MODE == 0 && p.ft.mel_in_smem) ? sm_mel_w : p.ft.mel_w;
     const bool hop_even = (p.hop & 1) == 0;
 
+    // ---- staging pipeline: the raw span of chunk i+1 is fetched by TMA while chunk i is transformed ----
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    if (tid == 0 && (long long)blockIdx.x < p.total_chunks) {
+        const ChunkGeo g = chunk_geo(p, blockIdx.x);
+        if (g.tma) {
+            mbar_expect_tx(mbar, (uint32_t)g.n4 * 4u);
+            tma_load_1d(sm_raw + g.lo_off, p.wav + g.row * p.ld + g.g0 + g.lo_off, (uint32_t)g.n4 * 4u, mbar);
+        }
+    }
+
     for (long long chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
-        const long long row = chunk / p.chunks_per_row;
-        const int c = (int)(chunk - row * p.chunks_per_row);
-        const int t0 = c * p.TC;
-        const int nf = min(p.TC, p.T - t0);
-        const long long start = (long long)t0 * p.hop;
-        const int len = (nf - 1) * p.hop + p.nfft;
+        const ChunkGeo geo = chunk_geo(p, chunk);
+        const long long row = geo.row;
+        const int t0 = geo.t0, nf = geo.nf, len = geo.len;
+        const long long start = geo.start;
         const float* __restrict__ x = p.wav + row * p.ld;
 
-        __syncthreads();  // previous chunk fully consumed (also orders the table writes above)
-        // ---- stage samples: y[m] = P[m] - a P[m-1] -------------------------------------------------
-        if (p.frm_pre != 0.f) {
-            for (int i = tid; i < len; i += kThreads) {
-                const float cur = sample_P(p, x, start + i);
-                const float prv = sample_P(p, x, start + i - 1);
-                sm_y[i] = __fsub_rn(cur, __fmul_rn(p.frm_pre, prv));
+        // ---- raw span: raw[k] = sample at source index g0 + k (TMA) or padded-signal value P (generic) ----
+        if (geo.tma) {
+            for (int k = tid; k < geo.lo_off; k += kThreads) sm_raw[k] = 0.f;
+            for (int k = geo.lo_off + geo.n4 + tid; k < len + 4; k += kThreads) {
+                const long long j = geo.g0 + k;
+                sm_raw[k] = (j < p.S) ? __ldg(x + j) : 0.f;
             }
-            for (int f = tid; f < nf; f += kThreads)
-                sm_first[f] = __fmul_rn(sample_P(p, x, start + (long long)f * p.hop), p.frm_one_minus);
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
         } else {
-            for (int i = tid; i < len; i += kThreads) sm_y[i] = sample_P(p, x, start + i);
+#pragma unroll 4
+            for (int k = tid; k < len + 4; k += kThreads) sm_raw[k] = sample_P(p, x, start - 4 + k);
         }
-        __syncthreads();
+        __syncthreads();  // raw complete; every warp has also finished the previous chunk's frames
+
+        // ---- transform: rescale, utterance pre-emphasis (TMA spans), per-frame pre-emphasis -> y ----------
+        if (geo.tma && !p.rescale && p.utt_pre == 0.f) {
+            // common case, vectorised: y[i] = raw[4+i] - a*raw[3+i]  (raw+4 and y are 16-byte aligned)
+            const float a = p.frm_pre;
+            const float4* r4 = reinterpret_cast<const float4*>(sm_raw + 4);
+            float4* y4 = reinterpret_cast<float4*>(sm_y);
+            const int n4 = (len + 3) >> 2;   // raw/y are allocated with 4 floats of slack
+            if (a != 0.f) {
+                for (int i = tid; i < n4; i += kThreads) {
+                    const float4 c = r4[i];
+                    const float pm = sm_raw[3 + 4 * i];
+                    float4 o;
+                    o.x = __fsub_rn(c.x, __fmul_rn(a, pm));
+                    o.y = __fsub_rn(c.y, __fmul_rn(a, c.x));
+                    o.z = __fsub_rn(c.z, __fmul_rn(a, c.y));
+                    o.w = __fsub_rn(c.w, __fmul_rn(a, c.z));
+                    y4[i] = o;
+                }
+                for (int f = tid; f < nf; f += kThreads) sm_first[f] = __fmul_rn(sm_raw[4 + f * p.hop], p.frm_one_minus);
+            } else {
+                for (int i = tid; i < n4; i += kThreads) y4[i] = r4[i];
+            }
+        } else {
+            const bool plain = geo.tma != 0;  // raw holds untouched samples
+            const float a = p.frm_pre, ua = p.utt_pre;
+            auto u_at = [&](int k) -> float {  // value of the padded signal P at raw slot k
+                float r0 = sm_raw[k];
+                if (!plain) return r0;
+                if (p.rescale) r0 = rintf(__fmul_rn(r0, 32767.0f));
+                if (ua != 0.f && geo.g0 + k >= 1) {
+                    float r1 = sm_raw[k - 1];
+                    if (p.rescale) r1 = rintf(__fmul_rn(r1, 32767.0f));
+                    r0 = __fsub_rn(r0, __fmul_rn(ua, r1));
+                }
+                return r0;
+            };
+            if (a != 0.f) {
+                for (int i = tid; i < len; i += kThreads) {
+                    const float cur = u_at(4 + i);
+                    const float prv = (start + i >= 1) ? u_at(3 + i) : 0.f;
+                    sm_y[i] = __fsub_rn(cur, __fmul_rn(a, prv));
+                }
+                for (int f = tid; f < nf; f += kThreads) sm_first[f] = __fmul_rn(u_at(4 + f * p.hop), p.frm_one_minus);
+            } else {
+                for (int i = tid; i < len; i += kThreads) sm_y[i] = u_at(4 + i);
+            }
+        }
+        __syncthreads();  // y complete, raw free again
+
+        // ---- prefetch the next chunk's raw span while this chunk's frames are transformed ------------------
+        if (tid == 0 && chunk + gridDim.x < p.total_chunks) {
+            const ChunkGeo g = chunk_geo(p, chunk + gridDim.x);
+            if (g.tma) {
+                fence_async_proxy();  // generic-proxy reads of raw above happen-before the async-proxy writes
+                mbar_expect_tx(mbar, (uint32_t)g.n4 * 4u);
+                tma_load_1d(sm_raw + g.lo_off, p.wav + g.row * p.ld + g.g0 + g.lo_off, (uint32_t)g.n4 * 4u, mbar);
+            }
+        }
 
         const int nf_round = (nf + NGROUPS - 1) / NGROUPS * NGROUPS;
         for (int f = group; f < nf_round; f += NGROUPS) {
             const int fe = min(f, nf - 1);
             const float* ys = sm_y + fe * p.hop;
             float2 v[16];
+            if (hop_even) {
+                const float2* ys2 = reinterpret_cast<const float2*>(ys);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int n = l + G * q;
-                const float2 w = sm_win[n];
-                float2 s;
-                if (hop_even) s = *reinterpret_cast<const float2*>(ys + 2 * n);
-                else s = make_float2(ys[2 * n], ys[2 * n + 1]);
-                if (q == 0 && l == 0 && p.frm_pre != 0.f) s.x = sm_first[fe];
-                v[q] = make_float2(s.x * w.x, s.y * w.y);
+                for (int q = 0; q < 16; ++q) {
+                    const float2 w = sm_win[l + G * q], s2 = ys2[l + G * q];
+                    v[q] = make_float2(s2.x * w.x, s2.y * w.y);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = l + G * q;
+                    const float2 w = sm_win[n];
+                    v[q] = make_float2(ys[2 * n] * w.x, ys[2 * n + 1] * w.y);
+                }
             }
+            if (l == 0 && p.frm_pre != 0.f) v[0].x = sm_first[fe] * reinterpret_cast<const float*>(sm_win)[0];
             group_fft<NC, false>(v, buf, sm_tw, l, mask);
-            float2 pr[16];
-            fetch_partner<NC>(v, pr, lane, l, mask);
+            // partner bins come by shuffle; the first shuffle is also the point where every lane of the
+            // group is done reading the exchange buffer, so the magnitudes may overwrite it afterwards
+            const int psrc = (lane & ~(G - 1)) | ((G - l) & (G - 1));
 
             if constexpr (MODE == 1) {
                 // ---- F2: write the one-sided spectrum into the transposed tile ------------------------
@@ -192,7 +358,8 @@ __global__ void __launch_bounds__(kThreads) frontend_kernel(const __grid_constan
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = l + G * q;
-                    float2 X = rfft_split(v[q], pr[q], sm_ptw[k], half);
+                    const float2 zp = partner_of<NC>(v, 15 - q, (16 - q) & 15, psrc, l, mask);
+                    float2 X = rfft_split(v[q], zp, sm_ptw[k], half);
                     if (p.polar) X = make_float2(sqrtf(fmaf(X.x, X.x, fmaf(X.y, X.y, p.polar_eps))), atan2f(X.y, X.x));
                     if (f < nf) sm_tile[k * ts + f] = X;
                 }
@@ -205,22 +372,20 @@ __global__ void __launch_bounds__(kThreads) frontend_kernel(const __grid_constan
             } else {
                 // ---- F1: |X| (or |X|^2) -> group buffer ----------------------------------------------
                 float* mag = reinterpret_cast<float*>(buf);
-                __syncwarp(mask);  // every lane finished reading the exchange buffer
+                const float xn = (v[0].x - v[0].y) * p.scale;   // Nyquist bin (real), used by lane 0
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int k = l + G * q;
-                    const float2 X = rfft_split(v[q], pr[q], sm_ptw[k], half);
+                    const float2 zp = partner_of<NC>(v, 15 - q, (16 - q) & 15, psrc, l, mask);
+                    const float2 X = rfft_split(v[q], zp, sm_ptw[k], half);
                     const float pw = fmaf(X.x, X.x, X.y * X.y);
-                    mag[k] = (p.ft.power == 2) ? pw : sqrtf(pw);
+                    mag[k] = (p.ft.power == 2) ? pw : fast_sqrt(pw);
                 }
-                if (l == 0) {
-                    const float xn = (v[0].x - v[0].y) * p.scale;
-                    mag[NC] = (p.ft.power == 2) ? xn * xn : fabsf(xn);
-                }
+                if (l == 0) mag[NC] = (p.ft.power == 2) ? xn * xn : fabsf(xn);
                 __syncwarp(mask);
 
                 float* o = (f < nf) ? p.out + ((long long)row * p.T + (t0 + f)) * p.ld_out : nullptr;
-                feature_epilogue<G, FI>(p.ft, mag, sm_mel_i, mel_w, l, mask, o);
+                feature_epilogue<G, FI>(p.ft, mag, sm_mel_i, sm_mel_w, l, mask, o);
                 __syncwarp(mask);  // mags consumed before the next frame reuses the buffer
             }
         }
@@ -286,8 +451,12 @@ static int launch_frontend(FrontendParams& p, cudaStream_t st) {
     constexpr int G = FFTPlan<NC>::G;
     constexpr int NGROUPS = kThreads / G;
     // frames per chunk: a multiple of the groups per CTA, sized so that >= 2 CTAs fit per SM
-    int TC = (MODE == 0) ? 2 * NGROUPS : NGROUPS;
-    if (MODE == 0 && TC < 32) TC = 32;
+    int TC = NGROUPS;                    // one frame per lane group and chunk: 3 CTAs/SM fit at nfft 512
+    if (TC < 16) TC = 16;
+    if (const char* e = getenv("APS_B200_TC")) {  // tuning aid: frames per chunk (multiple of the groups per CTA)
+        const int v = atoi(e);
+        if (v >= NGROUPS && v % NGROUPS == 0) TC = v;
+    }
     while (TC > NGROUPS && TC / 2 >= p.T) TC /= 2;
     p.ft.mel_in_smem = (p.ft.M * p.ft.mel_stride * 4 <= 24 * 1024) ? 1 : 0;
     SmemLayout L = make_layout<NC, MODE>(p.nfft, p.hop, TC, p.ft.M, p.ft.mel_stride, p.ft.mel_in_smem);
@@ -300,6 +469,8 @@ static int launch_frontend(FrontendParams& p, cudaStream_t st) {
     p.TC = TC;
     p.chunks_per_row = (p.T + TC - 1) / TC;
     p.total_chunks = p.rows * p.chunks_per_row;
+    p.tma_ok = (((uintptr_t)p.wav & 15) == 0 && (p.ld & 3) == 0 && (((long long)TC * p.hop) & 3) == 0 &&
+                (p.pad & 3) == 0 && !g_disable_tma) ? 1 : 0;
     static int smem_set = -1, occ_smem = -1, occ_cached = 1;  // per instantiation; one GPU per process
     if (L.total > smem_set) {
         APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kSThreads) specfeat_kernel(const __grid_consta
     const int FS = p.F | 1;  // odd row stride: conflict-free transposed stores
     float* sm_mag = reinterpret_cast<float*>(smem);
     int* sm_mel_i = reinterpret_cast<int*>(sm_mag + kSTC * FS);
-    float* sm_mel_w = reinterpret_cast<float*>(sm_mel_i + 2 * p.ft.M);
+    float* sm_mel_w = reinterpret_cast<float*>(sm_mel_i + 2 * p.ft.M + 40);
     const int tid = threadIdx.x, lane = tid & 31, l = tid & (kSG - 1), group = tid / kSG;
     const unsigned mask = 0xffffu << (lane & 16);
 
@@ -47,8 +47,13 @@ __global__ void __launch_bounds__(kSThreads) specfeat_kernel(const __grid_consta
         }
         if (p.ft.mel_in_smem)
             for (int i = tid; i < p.ft.M * p.ft.mel_stride; i += kSThreads) sm_mel_w[i] = __ldg(p.ft.mel_w + i);
+        __syncthreads();
+        if (tid < FI) {
+            int mx = 0;
+            for (int d = kSG * tid; d < min(p.ft.M, kSG * tid + kSG); ++d) mx = max(mx, sm_mel_i[p.ft.M + d]);
+            sm_mel_i[2 * p.ft.M + tid] = mx;
+        }
     }
-    const float* mel_w = p.ft.mel_in_smem ? sm_mel_w : p.ft.mel_w;
 
     for (long long chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         const long long row = chunk / p.chunks_per_row;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(kSThreads) specfeat_kernel(const __grid_consta
         __syncthreads();
         const int f = group;  // one frame per group; invalid frames run on zeros and skip the store
         float* o = (f < nf) ? p.out + ((long long)row * p.T + (t0 + f)) * p.ld_out : nullptr;
-        feature_epilogue<kSG, FI>(p.ft, sm_mag + f * FS, sm_mel_i, mel_w, l, mask, o);
+        feature_epilogue<kSG, FI>(p.ft, sm_mag + f * FS, sm_mel_i, sm_mel_w, l, mask, o);
     }
 }
 
@@ -120,7 +125,7 @@ template <int FI>
 static int launch_specfeat(SpecFeatParams& p, cudaStream_t st) {
     auto kern = specfeat_kernel<FI>;
     p.ft.mel_in_smem = (p.ft.M * p.ft.mel_stride * 4 <= 48 * 1024) ? 1 : 0;
-    const int smem = (kSTC * (p.F | 1) + 2 * p.ft.M + (p.ft.mel_in_smem ? p.ft.M * p.ft.mel_stride : 0)) * 4 + 16;
+    const int smem = (kSTC * (p.F | 1) + 2 * p.ft.M + 40 + (p.ft.mel_in_smem ? p.ft.M * p.ft.mel_stride : 0)) * 4 + 16;
     APSB_CHECK_ARG(smem <= 227 * 1024, "specfeat: %d bins need too much shared memory", p.F);
     static int smem_set = -1;
     if (smem > smem_set) {

@@ -138,7 +138,7 @@ def test_edge_shapes():
     big = 0.1 * th.randn(4, 2, 6000, device=DEV)
     ref, _ = O.AsrFeatures(O.AsrFeatCfg())(big.cpu(), None)
     got, _ = t(big, None)
-    assert got.shape == ref.shape == (4, 2, 34, 80) and rel_err(got, ref) < FLOAT_TOL
+    assert got.shape == ref.shape == (4, 2, 35, 80) and rel_err(got, ref) < FLOAT_TOL
     got2, _ = t(big[:, 1], None)
     assert rel_err(got2, ref[:, 1]) < FLOAT_TOL
     bad = big.clone()
