@@ -53,6 +53,17 @@ _SIGNATURES = {
                                         POINTER(FeatDesc), c_void_p, c_int64, c_void_p]),
     "aps_b200_ipd_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p, c_int64, c_int64, c_void_p]),
+    "aps_b200_mask_colmax": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                     c_void_p, c_void_p]),
+    "aps_b200_covar_fwd": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int64, c_int64, c_int64, c_int64,
+                                   c_void_p, POINTER(c_int64), c_void_p, c_void_p, POINTER(c_int64), c_void_p,
+                                   c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "aps_b200_mvdr_ref_logits": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int64, c_void_p, c_void_p]),
+    "aps_b200_mvdr_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p,
+                                      c_void_p]),
+    "aps_b200_beamform_fwd": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int64, c_int64, c_int64, c_int64,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "aps_b200_cmvn_allband": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
 }
 
@@ -113,6 +124,11 @@ def stream_ptr(dev: th.device) -> int:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def i64_array(values):
+    """ctypes int64 array (e.g. tensor strides) for the C ABI."""
+    return (c_int64 * len(values))(*[int(v) for v in values])
 
 
 # ---------------------------------------------------------------------------- cached device tables

@@ -1,0 +1,290 @@
+// encoder.cu — the non-GEMM kernels of the transformer / conformer encoder forward (rows a21–a23):
+//   layernorm       : y = LN(alpha * x + res) * gamma + beta  (residual add + macaron scale fused)
+//   mhsa            : multi-head self-attention with absolute / relative ("rel") / Transformer-XL ("xl")
+//                     position terms, key-padding and additive masks, streaming (online) softmax
+//   dwconv1d        : depthwise convolution over time (+ folded BatchNorm + activation) on token-major rows
+//
+// Replaces /root/reference/aps/asr/transformer/impl.py:95-118 (context_weight), :120-131 / :240-261 /
+// :324-344 (dot_att variants; the pad/transpose/view skew of aps/asr/transformer/utils.py:14-39
+// `digit_shift` becomes an index: shifted[l, s] = term[l, s - l + L - 1]), impl.py:454-465 (conformer
+// depthwise conv + BatchNorm1d + Swish), impl.py:392-393 / :476-480 (LayerNorm with residual), and the
+// dilated depthwise convolutions of aps/sse/bss/tcn.py:141-151.
+//
+// Activations are token-major rows [N*T, D] with row(n, t) = n*stride_n + t*stride_t (the encoder keeps
+// batch-major order so no N<->T transposes are materialised).
+#include "../../include/aps_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <math.h>
+
+namespace apsb {
+
+// ------------------------------------------------------------------------------------------------
+// one warp per row
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
+                                                        const float* __restrict__ res, long long ldr, float alpha,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, long long M, int D,
+                                                        float* __restrict__ out, long long ldo) {
+    const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* xr = x + m * ldx;
+    const float* rr = res ? res + m * ldr : nullptr;
+    auto val = [&](int d) { return rr ? fmaf(alpha, xr[d], rr[d]) : alpha * xr[d]; };
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s += val(d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float c = val(d) - mean;
+        q = fmaf(c, c, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float inv = rsqrtf(q / (float)D + eps);
+    float* orow = out + m * ldo;
+    for (int d = lane; d < D; d += 32) {
+        float y = (val(d) - mean) * inv;
+        if (gamma) y = fmaf(y, __ldg(gamma + d), beta ? __ldg(beta + d) : 0.f);
+        orow[d] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct DwParams {
+    const float* x;
+    long long ldx;
+    const float* w;      // [Kw, D] (tap-major: coalesced over channels)
+    const float* bias;   // [D] or nullptr
+    int N, T, D, Kw, dil, lpad;   // out[t] = sum_k w[k] * x[t - lpad + k*dil]
+    long long sn, st;    // row(n, t) = n*sn + t*st
+    Epilogue e;
+};
+
+__global__ void __launch_bounds__(256) dwconv1d_kernel(const __grid_constant__ DwParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.N * p.T * p.D;
+    if (idx >= total) return;
+    const int d = (int)(idx % p.D);
+    const long long r = idx / p.D;
+    const int t = (int)(r % p.T), n = (int)(r / p.T);
+    float acc = p.bias ? __ldg(p.bias + d) : 0.f;
+    for (int k = 0; k < p.Kw; ++k) {
+        const int tt = t - p.lpad + k * p.dil;
+        if (tt >= 0 && tt < p.T) acc = fmaf(__ldg(p.w + (long long)k * p.D + d), __ldg(p.x + (n * p.sn + tt * p.st) * p.ldx + d), acc);
+    }
+    const long long m = n * p.sn + t * p.st;
+    float v = p.e.alpha * apply_act(acc, p.e.act, p.e, d);
+    if (p.e.res) v = fmaf(p.e.beta, __ldg(p.e.res + m * p.e.ldres + d), v);
+    p.e.out[m * p.e.ldo + d] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AttnParams {
+    const float* q;      // rows (n, t), head h at columns h*dh .. ; row stride ldq
+    const float* k;
+    const float* v;
+    const float* qpos;   // rows used for the position term (= q, or v for the reference's xl path, Q14)
+    long long ldq, ldk, ldv, ldqp;
+    long long sn, st;    // row(n, t) = n*sn + t*st (rows of q/k/v/out)
+    int N, L, H, dh;
+    int mode;            // 0 abs, 1 rel (pos [2L-1, dh] shared by heads), 2 xl (pos [2L-1, H*dh])
+    const float* pos;
+    long long ldpos;
+    const float* rel_u;  // xl: [H, dh] added to the content query
+    const float* rel_v;  // xl: [H, dh] added to the position query
+    const unsigned char* kpm;  // [N, L] key padding mask (1 = masked) or nullptr
+    float kpm_fill;      // value written on masked keys (MIN_F32 for the aps path, -inf for torch's)
+    const float* amask;  // [L, L] additive mask or nullptr
+    float scale;         // 1/sqrt(dh)
+    float* out;          // rows (n, t), columns h*dh + d
+    long long ldo;
+};
+
+constexpr int kAttnWarps = 8;    // queries per CTA
+constexpr int kKeyTile = 32;
+
+// CTA = (query tile, head, batch); one warp per query; lane = key inside the tile; dh <= 128
+template <int DH>
+__global__ void __launch_bounds__(kAttnWarps * 32) mhsa_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int LD = DH + 1;
+    __shared__ float sK[kKeyTile][LD];
+    __shared__ float sV[kKeyTile][LD];
+    __shared__ float sR[kKeyTile + kAttnWarps][LD];
+    __shared__ float sQ[kAttnWarps][DH];
+    __shared__ float sQp[kAttnWarps][DH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kAttnWarps;
+    const int i = i0 + warp;
+    const bool qok = i < p.L;
+    const int L = p.L;
+    // queries of this CTA
+    for (int idx = threadIdx.x; idx < kAttnWarps * DH; idx += blockDim.x) {
+        const int w = idx / DH, d = idx - w * DH;
+        const int ii = min(i0 + w, L - 1);
+        const long long row = n * p.sn + ii * p.st;
+        float qc = __ldg(p.q + row * p.ldq + h * DH + d);
+        float qp = p.mode ? __ldg(p.qpos + row * p.ldqp + h * DH + d) : 0.f;
+        if (p.mode == 2) {
+            // reference xl path: content term uses (X + u), position term (X + v), X = the tensor passed as
+            // "query" to dot_att — which is VALUE in the reference (impl.py:369)
+            qc = __ldg(p.qpos + row * p.ldqp + h * DH + d) + __ldg(p.rel_u + h * DH + d);
+            qp = qp + __ldg(p.rel_v + h * DH + d);
+        }
+        sQ[w][d] = qc;
+        sQp[w][d] = qp;
+    }
+    float mrun = -INFINITY, lrun = 0.f;
+    float acc[(DH + 31) / 32];
+#pragma unroll
+    for (int c = 0; c < (DH + 31) / 32; ++c) acc[c] = 0.f;
+
+    for (int j0 = 0; j0 < L; j0 += kKeyTile) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kKeyTile * DH; idx += blockDim.x) {
+            const int j = idx / DH, d = idx - j * DH;
+            const int jj = j0 + j;
+            float kv = 0.f, vv = 0.f;
+            if (jj < L) {
+                const long long row = n * p.sn + jj * p.st;
+                kv = __ldg(p.k + row * p.ldk + h * DH + d);
+                vv = __ldg(p.v + row * p.ldv + h * DH + d);
+            }
+            sK[j][d] = kv;
+            sV[j][d] = vv;
+        }
+        if (p.mode) {
+            // position rows x = j - i + L - 1 for i in [i0, i0+W), j in [j0, j0+32): x0 = j0 - (i0+W-1) + L - 1
+            const int x0 = j0 - (i0 + kAttnWarps - 1) + L - 1;
+            for (int idx = threadIdx.x; idx < (kKeyTile + kAttnWarps) * DH; idx += blockDim.x) {
+                const int r = idx / DH, d = idx - r * DH;
+                const int x = x0 + r;
+                float pv = 0.f;
+                if (x >= 0 && x < 2 * L - 1)
+                    pv = __ldg(p.pos + (long long)x * p.ldpos + (p.mode == 2 ? h * DH : 0) + d);
+                sR[r][d] = pv;
+            }
+        }
+        __syncthreads();
+        const int j = j0 + lane;
+        float s = -INFINITY;
+        if (qok && j < L) {
+            float a = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < DH; ++d) a = fmaf(sQ[warp][d], sK[lane][d], a);
+            if (p.mode) {
+                // row index inside sR: x - x0 = (j - i + L - 1) - x0 = lane + (kAttnWarps - 1 - warp)
+                const float* rr = sR[lane + kAttnWarps - 1 - warp];
+                float b = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < DH; ++d) b = fmaf(sQp[warp][d], rr[d], b);
+                a += b;
+            }
+            s = a * p.scale;
+            if (p.kpm && p.kpm[(long long)n * L + j]) s = p.kpm_fill;
+            if (p.amask) s += __ldg(p.amask + (long long)i * L + j);
+        }
+        // online softmax update
+        float tmax = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        const float mnew = fmaxf(mrun, tmax);
+        const float corr = (mrun == -INFINITY) ? 0.f : __expf(mrun - mnew);
+        const float pj = (s == -INFINITY) ? 0.f : __expf(s - mnew);
+        float psum = pj;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        if (mnew != -INFINITY) {
+            lrun = lrun * corr + psum;
+#pragma unroll
+            for (int c = 0; c < (DH + 31) / 32; ++c) acc[c] *= corr;
+            for (int jj = 0; jj < kKeyTile; ++jj) {
+                const float pb = __shfl_sync(0xffffffffu, pj, jj);
+#pragma unroll
+                for (int c = 0; c < (DH + 31) / 32; ++c) {
+                    const int d = lane + 32 * c;
+                    if (d < DH) acc[c] = fmaf(pb, sV[jj][d], acc[c]);
+                }
+            }
+            mrun = mnew;
+        }
+    }
+    if (qok) {
+        // a fully masked row (all -inf) gives NaN in the reference's softmax too
+        const float inv = 1.f / lrun;
+        float* o = p.out + (n * p.sn + i * p.st) * p.ldo + h * DH;
+#pragma unroll
+        for (int c = 0; c < (DH + 31) / 32; ++c) {
+            const int d = lane + 32 * c;
+            if (d < DH) o[d] = (lrun > 0.f) ? acc[c] * inv : NAN;
+        }
+    }
+}
+
+}  // namespace apsb
+
+using namespace apsb;
+
+extern "C" int aps_b200_layernorm_fwd(const float* x, int64_t ld_x, const float* residual, int64_t ld_residual,
+                                      float alpha, const float* gamma, const float* beta, float eps, int64_t rows,
+                                      int64_t dim, float* out, int64_t ld_out, void* stream) {
+    APSB_CHECK_ARG(x && out && rows > 0 && dim > 0 && ld_x >= dim && ld_out >= dim, "bad arguments");
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        x, ld_x, residual, ld_residual, alpha, gamma, beta, eps, rows, (int)dim, out, ld_out);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
+                                     int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
+                                     int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
+                                     int64_t ld_out, void* stream) {
+    APSB_CHECK_ARG(x && weight_kd && epi && out, "null pointer argument");
+    APSB_CHECK_ARG(batch > 0 && num_frames > 0 && channels > 0 && kernel > 0 && dilation > 0 && left_pad >= 0,
+                   "bad shape");
+    APSB_CHECK_ARG(epi->act != ACT_GLU, "GLU is not available for the depthwise convolution");
+    DwParams p{};
+    p.x = x; p.ldx = ld_x; p.w = weight_kd; p.bias = bias;
+    p.N = (int)batch; p.T = (int)num_frames; p.D = (int)channels; p.Kw = kernel; p.dil = dilation; p.lpad = left_pad;
+    p.sn = stride_n; p.st = stride_t;
+    p.e.bias = nullptr; p.e.act = epi->act; p.e.alpha = epi->alpha; p.e.slope = epi->prelu_slope;
+    p.e.slope_stride = epi->prelu_per_channel ? 1 : 0; p.e.leak = epi->leaky_slope;
+    p.e.res = epi->residual; p.e.ldres = epi->ld_residual; p.e.beta = epi->beta; p.e.out = out; p.e.ldo = ld_out;
+    APSB_CHECK_ARG(epi->act != ACT_PRELU || epi->prelu_slope, "PReLU slope missing");
+    const long long total = (long long)batch * num_frames * channels;
+    dwconv1d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_t ld_out, void* stream) {
+    APSB_CHECK_ARG(d && out && d->q && d->k && d->v, "null pointer argument");
+    APSB_CHECK_ARG(d->batch > 0 && d->length > 0 && d->heads > 0, "bad shape");
+    APSB_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "unknown attention mode %d", d->mode);
+    APSB_CHECK_ARG(d->mode == 0 || (d->pos && d->qpos), "relative attention needs position rows");
+    APSB_CHECK_ARG(d->mode != 2 || (d->rel_u && d->rel_v), "xl attention needs rel_u / rel_v");
+    APSB_CHECK_ARG(d->batch <= 65535 && d->heads <= 65535, "grid too large");
+    AttnParams p{};
+    p.q = d->q; p.k = d->k; p.v = d->v; p.qpos = d->qpos;
+    p.ldq = d->ld_q; p.ldk = d->ld_k; p.ldv = d->ld_v; p.ldqp = d->ld_qpos;
+    p.sn = d->stride_n; p.st = d->stride_t;
+    p.N = (int)d->batch; p.L = (int)d->length; p.H = (int)d->heads; p.dh = (int)d->head_dim; p.mode = d->mode;
+    p.pos = d->pos; p.ldpos = d->ld_pos; p.rel_u = d->rel_u; p.rel_v = d->rel_v;
+    p.kpm = d->key_padding_mask; p.kpm_fill = d->padding_fill; p.amask = d->attn_mask;
+    p.scale = d->scale; p.out = out; p.ldo = ld_out;
+    dim3 grid((unsigned)((p.L + kAttnWarps - 1) / kAttnWarps), (unsigned)p.H, (unsigned)p.N);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p.dh) {
+        case 32: mhsa_kernel<32><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
+        case 64: mhsa_kernel<64><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
+        case 96: mhsa_kernel<96><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
+        case 128: mhsa_kernel<128><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
+        default: return set_error(-1, "unsupported head dimension %d (32, 64, 96, 128)", p.dh);
+    }
+    APSB_LAUNCH_CHECK();
+    return 0;
+}

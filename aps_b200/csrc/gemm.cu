@@ -1,0 +1,86 @@
+// gemm.cu — entry points of the fp32 GEMM core: dense layers and NHWC implicit-GEMM convolutions.
+//
+// Replaces (forward, inference) torch.nn.functional.linear / conv1d(k=1) / conv2d as used by
+// /root/reference/aps/asr/transformer/impl.py:388-393,454-475 (feed-forward and point-wise conv layers),
+// impl.py:62-83 (attention in/out projections), aps/asr/base/component.py:251-307 (Conv2d block, with the
+// eval-mode BatchNorm folded into weight/bias by the caller), aps/asr/base/encoder.py:415-441
+// (Conv2dEncoder.outp), aps/sse/bss/tcn.py:112-159 (1x1 convolutions of Conv1dBlock).
+#include "../../include/aps_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace apsb {
+
+template <typename ALoader>
+int launch_gemm(const ALoader& a, const float* Wt, long long ldw, int M, int N, int K, const Epilogue& e,
+                cudaStream_t st) {
+    const int wvec = (((uintptr_t)Wt & 15) == 0 && (ldw & 3) == 0 && (K & 3) == 0) ? 1 : 0;
+    // big tiles when they still fill the machine, else 64x64
+    const long long big = (long long)((M + 127) / 128) * ((N + 127) / 128);
+    if (big >= 2LL * num_sms()) {
+        dim3 grid((N + 127) / 128, (M + 127) / 128);
+        gemm_kernel<128, 128, ALoader><<<grid, kGemmThreads, 0, st>>>(a, Wt, ldw, wvec, M, N, K, e);
+    } else {
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        gemm_kernel<64, 64, ALoader><<<grid, kGemmThreads, 0, st>>>(a, Wt, ldw, wvec, M, N, K, e);
+    }
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* out, int64_t ldo) {
+    APSB_CHECK_ARG(d && out, "null pointer argument");
+    APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_LEAKY, "unknown activation %d", d->act);
+    APSB_CHECK_ARG(d->act != ACT_GLU || (N % 2 == 0), "GLU needs an even number of columns");
+    APSB_CHECK_ARG(d->act != ACT_PRELU || d->prelu_slope, "PReLU slope missing");
+    e.bias = d->bias; e.act = d->act; e.alpha = d->alpha;
+    e.slope = d->prelu_slope; e.slope_stride = d->prelu_per_channel ? 1 : 0; e.leak = d->leaky_slope;
+    e.res = d->residual; e.ldres = d->ld_residual; e.beta = d->beta;
+    e.out = out; e.ldo = ldo;
+    const int ncols = d->act == ACT_GLU ? N / 2 : N;
+    APSB_CHECK_ARG(ldo >= ncols, "ld_out %lld smaller than %d columns", (long long)ldo, ncols);
+    APSB_CHECK_ARG(!d->residual || d->ld_residual >= ncols, "ld_residual too small");
+    return 0;
+}
+
+}  // namespace apsb
+
+using namespace apsb;
+
+extern "C" int aps_b200_linear_fwd(const float* x, int64_t rows, int64_t in_features, int64_t ld_x,
+                                   const float* weight, int64_t ld_w, int64_t out_features,
+                                   const aps_b200_epilogue* epi, float* out, int64_t ld_out, void* stream) {
+    APSB_CHECK_ARG(x && weight, "null pointer argument");
+    APSB_CHECK_ARG(rows > 0 && in_features > 0 && out_features > 0 && ld_x >= in_features && ld_w >= in_features,
+                   "bad shape");
+    APSB_CHECK_ARG(rows < (1LL << 31) && out_features < (1LL << 31), "shape too large");
+    Epilogue e{};
+    if (int rc = fill_epilogue(e, epi, (int)out_features, out, ld_out)) return rc;
+    PlainA a{x, ld_x, (int)rows, (int)in_features,
+             (((uintptr_t)x & 15) == 0 && (ld_x & 3) == 0 && (in_features & 3) == 0) ? 1 : 0};
+    return launch_gemm(a, weight, ld_w, (int)rows, (int)out_features, (int)in_features, e, (cudaStream_t)stream);
+}
+
+extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                        int64_t in_channels, const float* weight, int64_t out_channels,
+                                        int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                                        int dil_h, int dil_w, const aps_b200_epilogue* epi, float* out, void* stream) {
+    APSB_CHECK_ARG(x && weight, "null pointer argument");
+    APSB_CHECK_ARG(batch > 0 && height > 0 && width > 0 && in_channels > 0 && out_channels > 0, "bad shape");
+    APSB_CHECK_ARG(kernel_h > 0 && kernel_w > 0 && stride_h > 0 && stride_w > 0 && dil_h > 0 && dil_w > 0 &&
+                       pad_h >= 0 && pad_w >= 0, "bad convolution geometry");
+    const int64_t OH = (height + 2 * pad_h - dil_h * (kernel_h - 1) - 1) / stride_h + 1;
+    const int64_t OW = (width + 2 * pad_w - dil_w * (kernel_w - 1) - 1) / stride_w + 1;
+    APSB_CHECK_ARG(OH > 0 && OW > 0, "convolution output is empty");
+    const int64_t M = batch * OH * OW, K = (int64_t)kernel_h * kernel_w * in_channels;
+    APSB_CHECK_ARG(M < (1LL << 31) && K < (1LL << 31), "shape too large");
+    Epilogue e{};
+    const int ncols = (int)out_channels;
+    if (int rc = fill_epilogue(e, epi, ncols, out, epi && epi->act == ACT_GLU ? ncols / 2 : ncols)) return rc;
+    ConvA a{};
+    a.x = x; a.Nb = (int)batch; a.H = (int)height; a.W = (int)width; a.Cin = (int)in_channels;
+    a.KH = kernel_h; a.KW = kernel_w; a.sh = stride_h; a.sw = stride_w; a.ph = pad_h; a.pw = pad_w;
+    a.dh = dil_h; a.dw = dil_w; a.OH = (int)OH; a.OW = (int)OW; a.M = (int)M; a.K = (int)K;
+    a.vec = (((uintptr_t)x & 15) == 0 && (in_channels & 3) == 0) ? 1 : 0;
+    return launch_gemm(a, weight, K, (int)M, ncols, (int)K, e, (cudaStream_t)stream);
+}

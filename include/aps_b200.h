@@ -134,6 +134,86 @@ int aps_b200_ipd_fwd(const float* spec, int64_t batch, int64_t channels, int64_t
 int aps_b200_cmvn_allband(float* x, int64_t rows, int64_t T, int64_t dims, int norm_mean,
                           int norm_var, float eps, void* stream);
 
+/* Multi-channel front-end (MVDR) ------------------------------------------------------------
+ * Complex spectrograms are passed as separate real / imaginary base pointers plus the element
+ * strides {n, c, f, t} of the [N, C, F, T] view (aps.cplx.ComplexTensor keeps two real tensors,
+ * aps/cplx.py:18-33; they are normally the two halves of a packed STFT, stride_t = 2).
+ * Masks are [N, T, F] or [N, F, T] views given by their strides {n, t, f}. 2 <= C <= 6.
+ */
+
+/* out[n, f] = max_t |mask[n, t, f]| over t < lens[n] (lens may be NULL).
+ * Replaces the th.norm(mask, inf, dim=1) of aps/asr/filter/mvdr.py:112-113 (+ padding :109-111). */
+int aps_b200_mask_colmax(const float* mask, int64_t stride_n, int64_t stride_t, int64_t stride_f,
+                         int64_t batch, int64_t num_frames, int64_t num_bins, const int64_t* lens,
+                         float* out, void* stream);
+
+/* F4: Rs[n,f] = sum_t ms X X^H / max(sum_t ms, den_eps), Rn likewise with the noise mask, where
+ * ms = (t < lens[n] ? mask_s : 0) / (max_s[n,f] + norm_eps) (max_s NULL: no normalisation) and the
+ * noise mask is mask_n processed the same way or, when mask_n is NULL, 1 - ms.  Rs / Rn are
+ * [N, F, C, C, 2] (Rn may be NULL).  Replaces mvdr.py:103-116 (_process_mask) + :42-61
+ * (estimate_covar, four real batched GEMMs per covariance through aps/cplx.py:242-252).        */
+int aps_b200_covar_fwd(const float* x_real, const float* x_imag, const int64_t* x_strides,
+                       int64_t batch, int64_t channels, int64_t num_bins, int64_t num_frames,
+                       const float* mask_s, const int64_t* mask_s_strides, const float* max_s,
+                       const float* mask_n, const int64_t* mask_n_strides, const float* max_n,
+                       const int64_t* lens, float norm_eps, float den_eps, float* Rs, float* Rn,
+                       void* stream);
+
+/* logits[n, c] of the reference-channel attention: gvec . tanh(proj . |offdiag-mean(Rs)[n, c, :]| + b).
+ * Replaces mvdr.py:158-173 (ChannelAttention.forward up to the softmax).                      */
+int aps_b200_mvdr_ref_logits(const float* Rs, int64_t batch, int64_t num_bins, int64_t channels,
+                             const float* proj_weight, const float* proj_bias,
+                             const float* gvec_weight, const float* gvec_bias, int64_t att_dim,
+                             float* logits, void* stream);
+
+/* F5: weight[n, f, :, 2] = (Rn + eps I)^-1 Rs u / (tr((Rn + eps I)^-1 Rs) + eps), u = softmax(logits[n]).
+ * Replaces mvdr.py:174 (softmax), :75-101 (_derive_weight), aps/cplx.py:268-278 (inverse through
+ * the real 2C x 2C matrix), mvdr.py:19-26 (trace), aps/cplx.py:221-226 (complex division).      */
+int aps_b200_mvdr_weights(const float* Rs, const float* Rn, const float* logits, int64_t batch,
+                          int64_t num_bins, int64_t channels, float eps, float* weight,
+                          void* stream);
+
+/* Y[n, f, t] = sum_c conj(weight[n, f, c]) X[n, c, f, t]; y_real / y_imag contiguous [N, F, T].
+ * Replaces mvdr.py:29-39 (beamform).                                                          */
+int aps_b200_beamform_fwd(const float* x_real, const float* x_imag, const int64_t* x_strides,
+                          int64_t batch, int64_t channels, int64_t num_bins, int64_t num_frames,
+                          const float* weight, float* y_real, float* y_imag, void* stream);
+
+/* Dense layers ---------------------------------------------------------------------------------
+ * out[m, n] = alpha * act(sum_k x[m, k] * weight[n, k] + bias[n]) + beta * residual[m, n]
+ * (exact fp32 accumulate).  act: 0 none, 1 relu, 2 swish, 3 tanh, 4 sigmoid, 5 prelu, 6 glu (column
+ * pairs (2j, 2j+1) -> out[:, j] = v0 * sigmoid(v1)), 7 leaky relu.
+ */
+typedef struct aps_b200_epilogue {
+    const float* bias;         /* [N] or NULL */
+    int32_t act;
+    float   alpha;
+    const float* prelu_slope;  /* [1] or [N] (prelu_per_channel) */
+    int32_t prelu_per_channel;
+    float   leaky_slope;
+    const float* residual;     /* [M, ld_residual] or NULL */
+    int64_t ld_residual;
+    float   beta;
+} aps_b200_epilogue;
+
+/* x [rows, in_features] (row stride ld_x), weight [out_features, in_features] (torch Linear layout,
+ * row stride ld_w).  Replaces F.linear / 1x1 Conv1d of aps/asr/transformer/impl.py:388-393, :454-475,
+ * :62-83, aps/asr/base/encoder.py:415-441 (outp), aps/sse/bss/tcn.py:112-159.               */
+int aps_b200_linear_fwd(const float* x, int64_t rows, int64_t in_features, int64_t ld_x,
+                        const float* weight, int64_t ld_w, int64_t out_features,
+                        const aps_b200_epilogue* epi, float* out, int64_t ld_out, void* stream);
+
+/* Implicit-GEMM convolution on channels-last data: x [B, H, W, Cin], weight [Cout, KH, KW, Cin],
+ * out [B, OH, OW, Cout] with OH = (H + 2 pad - dil (K-1) - 1) / stride + 1.  Replaces the
+ * Conv2d(+BatchNorm eval, folded by the caller)+ReLU block of aps/asr/base/component.py:251-307 and
+ * the complex convolutions of aps/sse/enh/dcunet.py:24-45 (as one real convolution on stacked
+ * real/imaginary channels).                                                                   */
+int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                             int64_t in_channels, const float* weight, int64_t out_channels,
+                             int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,
+                             int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
+                             float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,26 @@ def main():
         feats = t(packed)
         rec = t.decode([packed[:, 0]])[0]
         save(f"enh_{i}", kw, wav=x, packed=packed, num_frames=n, feats=feats, rec=rec)
+    # ---- MVDR front-end (aps/asr/filter/mvdr.py): covariance, reference attention, weights, beamforming -----
+    from aps.asr.filter.mvdr import MvdrBeamformer, estimate_covar
+    from aps.cplx import ComplexTensor
+    for i, (N, C, Fb, T, use_n, use_len, norm) in enumerate([(2, 4, 65, 30, False, True, True),
+                                                             (3, 5, 33, 47, True, True, True),
+                                                             (2, 2, 129, 20, True, False, False)]):
+        g = th.Generator().manual_seed(400 + i)
+        net = MvdrBeamformer(Fb, att_dim=24, mask_norm=norm).eval()
+        with th.no_grad():
+            for prm in net.parameters():
+                prm.copy_(th.randn(prm.shape, generator=g) * 0.3)
+        xr, xi = th.randn(N, C, Fb, T, generator=g), th.randn(N, C, Fb, T, generator=g)
+        ms, mn = th.rand(N, T, Fb, generator=g), th.rand(N, T, Fb, generator=g)
+        lens = th.tensor([T, T - 7, T - 11][:N])
+        with th.no_grad():
+            y = net(ms, ComplexTensor(xr, xi), mask_n=mn if use_n else None, x_len=lens if use_len else None)
+            R = estimate_covar(ms.transpose(1, 2), ComplexTensor(xr, xi))
+        arrays = dict(xr=xr, xi=xi, mask_s=ms, mask_n=mn, lens=lens, yr=y.real, yi=y.imag, Rr=R.real, Ri=R.imag)
+        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        save(f"mvdr_{i}", dict(num_bins=Fb, att_dim=24, mask_norm=norm, use_n=use_n, use_len=use_len), **arrays)
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)
