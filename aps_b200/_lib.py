@@ -35,6 +35,25 @@ class FeatDesc(Structure):
                 ("gstd", c_void_p), ("nan_count", c_void_p)]
 
 
+class Epilogue(Structure):
+    """mirror of `aps_b200_epilogue`"""
+    _fields_ = [("bias", c_void_p), ("act", c_int32), ("alpha", c_float), ("prelu_slope", c_void_p),
+                ("prelu_per_channel", c_int32), ("leaky_slope", c_float), ("residual", c_void_p),
+                ("ld_residual", c_int64), ("beta", c_float)]
+
+
+class AttnDesc(Structure):
+    """mirror of `aps_b200_attn_desc`"""
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("qpos", c_void_p), ("ld_q", c_int64),
+                ("ld_k", c_int64), ("ld_v", c_int64), ("ld_qpos", c_int64), ("stride_n", c_int64),
+                ("stride_t", c_int64), ("batch", c_int64), ("length", c_int64), ("heads", c_int64),
+                ("head_dim", c_int64), ("mode", c_int32), ("pos", c_void_p), ("ld_pos", c_int64),
+                ("rel_u", c_void_p), ("rel_v", c_void_p), ("key_padding_mask", c_void_p),
+                ("padding_fill", c_float), ("attn_mask", c_void_p), ("scale", c_float)]
+
+
+ACT = {"none": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4, "prelu": 5, "glu": 6, "leaky_relu": 7, "gelu": 8}
+
 _SIGNATURES = {
     "aps_b200_abi_version": (c_int, []),
     "aps_b200_init": (c_int, [c_int]),
@@ -64,6 +83,16 @@ _SIGNATURES = {
                                       c_void_p]),
     "aps_b200_beamform_fwd": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int64, c_int64, c_int64, c_int64,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aps_b200_linear_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(Epilogue),
+                                    c_void_p, c_int64, c_void_p]),
+    "aps_b200_conv2d_nhwc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Epilogue), c_void_p,
+                                         c_void_p]),
+    "aps_b200_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_float,
+                                       c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "aps_b200_dwconv1d_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                      c_void_p, c_int, c_int, c_int, POINTER(Epilogue), c_void_p, c_int64, c_void_p]),
+    "aps_b200_mhsa_fwd": (c_int, [POINTER(AttnDesc), c_void_p, c_int64, c_void_p]),
     "aps_b200_cmvn_allband": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
 }
 

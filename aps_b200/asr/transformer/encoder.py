@@ -1,0 +1,500 @@
+"""Transformer / Conformer encoder with the constructor, `forward(inp_pad, inp_len)` contract and
+`state_dict` layout of /root/reference/aps/asr/transformer/encoder.py:18-106, executed by the sm_100a
+kernels (csrc/gemm.cu, csrc/encoder.cu) through the C ABI.
+
+The sub-modules below are PARAMETER CONTAINERS that reproduce the reference's module tree name for
+name (`proj.conv.enc_layers.{i}.conv|norm.norm`, `proj.conv.outp`, `pose.embed|div_term`,
+`encoder.layers.{l}.self_attn.in_proj_weight|…`, `…feedforward{1,2}.{0,3}`, `…convolution.{0,2,3,5}`,
+`…norm_*`, `encoder.norm`, `outp` — aps/asr/transformer/impl.py, proj.py, pose.py,
+aps/asr/base/encoder.py:368-441, component.py:251-307) so checkpoints load with strict=True.  The
+forward pass never calls them: `TransformerEncoder.forward` runs a fused inference schedule on
+batch-major token rows [N*T', D]:
+
+  conv2d front   : NHWC implicit-GEMM convolutions with eval-BatchNorm folded into weight/bias + ReLU
+  FFN            : GEMM(+bias+activation) -> GEMM(+bias) -> LayerNorm(alpha*y + x)
+  attention      : GEMM (packed QKV) -> mhsa kernel (abs / rel / xl, masks) -> GEMM(+bias + residual)
+  conv module    : LayerNorm -> GEMM with interleaved GLU epilogue -> depthwise conv (+BN folded, Swish)
+                   -> GEMM(+bias + residual)
+
+Inference only (`eval()`): train-mode BatchNorm statistics / dropout / autograd are outside the
+forward hot path this package covers.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch as th
+import torch.nn as nn
+
+from ... import _lib, ops
+
+MIN_F32 = th.finfo(th.float32).min
+
+
+class Swish(nn.Module):
+    def forward(self, x):
+        return x * th.sigmoid(x)
+
+
+def _activation(name: str) -> nn.Module:
+    if name == "relu":
+        return nn.ReLU()
+    if name == "gelu":
+        return nn.GELU()
+    if name == "swish":
+        return Swish()
+    raise RuntimeError(f"activation should be relu/gelu, not {name}")
+
+
+def _relative_uv(shape) -> nn.Parameter:
+    p = nn.Parameter(th.empty(*shape))
+    nn.init.xavier_uniform_(p)
+    return p
+
+
+# ------------------------------------------------------------------------------------ containers: front
+class Normalize2d(nn.Module):
+    def __init__(self, name: str, features: int):
+        super().__init__()
+        name = name.upper()
+        if name not in ("BN", "IN"):
+            raise ValueError(f"Unknown type of Normalize2d: {name}")
+        self.norm = nn.BatchNorm2d(features) if name == "BN" else nn.InstanceNorm2d(features)
+
+
+class Normalize1d(nn.Module):
+    def __init__(self, name: str, features: int):
+        super().__init__()
+        name = name.upper()
+        if name not in ("BN", "LN"):
+            raise ValueError(f"Unknown type of Normalize1d: {name}")
+        self.norm = nn.BatchNorm1d(features) if name == "BN" else nn.GroupNorm(1, features)
+
+
+class Conv2d(nn.Module):
+    """Conv2d -> Norm -> ReLU block (component.py:251-307)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=2, dilation=1, norm="BN",
+                 for_streaming=False):
+        super().__init__()
+        two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+        kernel_size, dilation = two(kernel_size), two(dilation)
+        padding = tuple((d * (k - 1)) // 2 for d, k in zip(dilation, kernel_size))
+        if for_streaming:
+            padding = (0, padding[-1])
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                              dilation=dilation)
+        self.norm = Normalize2d(norm, out_channels)
+        self.kernel_size, self.padding, self.dilation, self.stride = kernel_size, padding, dilation, two(stride)
+
+    def compute_outp_dim(self, dim: th.Tensor, axis: int) -> th.Tensor:
+        """The reference's own length rule, `dim + 2p - d*k` (component.py:290-297, Q17) — kept verbatim."""
+        return th.div(dim + 2 * self.padding[axis] - self.dilation[axis] * self.kernel_size[axis],
+                      self.stride[axis], rounding_mode="trunc") + 1
+
+
+class Conv2dEncoder(nn.Module):
+    """Stack of Conv2d blocks + output projection (aps/asr/base/encoder.py:368-441)."""
+
+    def __init__(self, inp_features, out_features, channel=32, in_channels=1, norm="BN", num_layers=3, kernel=3,
+                 stride=2, for_streaming=False):
+        super().__init__()
+
+        def per_layer(v):
+            if isinstance(v, int):
+                return [(v, v)] * num_layers
+            return [(p, p) for p in v] if isinstance(v[0], int) else list(v)
+
+        self.kernel, self.stride = per_layer(kernel), per_layer(stride)
+        channel = [channel] * num_layers if isinstance(channel, int) else channel
+        self.enc_layers = nn.ModuleList([
+            Conv2d(in_channels if i == 0 else channel[i - 1], channel[i], kernel_size=self.kernel[i], norm=norm,
+                   stride=self.stride[i], for_streaming=for_streaming) for i in range(num_layers)
+        ])
+        freq = th.IntTensor([inp_features])
+        for c in self.enc_layers:
+            freq = c.compute_outp_dim(freq, 1)
+        fxc = freq.item() * channel[-1]
+        self.inp_features = inp_features
+        if out_features > 0:
+            self.out_features = out_features
+            self.outp = nn.Linear(fxc, out_features)
+        else:
+            self.out_features = fxc
+            self.outp = None
+
+
+class Conv2dProj(nn.Module):
+    """proj.py:104-140"""
+
+    def __init__(self, input_size, embed_dim, norm="BN", kernel=3, stride=2, num_layers=2, in_channels=1,
+                 conv_channels=256, for_streaming=False):
+        super().__init__()
+        assert num_layers in (2, 3, 4)
+        self.conv = Conv2dEncoder(input_size, embed_dim, channel=conv_channels, in_channels=in_channels,
+                                  num_layers=num_layers, norm=norm, kernel=kernel, stride=stride,
+                                  for_streaming=for_streaming)
+
+
+class LinearProj(nn.Module):
+    """proj.py:31-57"""
+
+    def __init__(self, input_size, embed_dim, dropout=0.0, norm="LN"):
+        super().__init__()
+        self.proj = nn.Linear(input_size, embed_dim)
+        self.norm = Normalize1d(norm, embed_dim)
+        self.drop = nn.Dropout(p=dropout)
+
+
+# ------------------------------------------------------------------------------------ containers: pose
+class SinPosEncoding(nn.Module):
+    """pose.py:28-62 ("xl") / :93-122 ("abs")"""
+
+    def __init__(self, embed_dim, dropout=0.0, scaled=False):
+        super().__init__()
+        div = th.exp(-math.log(10000.0) * th.arange(0, embed_dim, 2.0) / embed_dim)
+        self.div_term = nn.Parameter(div, requires_grad=False)
+        self.dropout = nn.Dropout(p=dropout)
+        self.factor = embed_dim**0.5 if scaled else 1
+
+    def encode(self, position: th.Tensor) -> th.Tensor:
+        seq = position[:, None] * self.div_term
+        return th.stack([th.sin(seq), th.cos(seq)], -1).view(position.shape[0], -1)
+
+
+class RelPosEncoding(nn.Module):
+    """pose.py:65-90"""
+
+    def __init__(self, embed_dim, dropout=0.0, lradius=128, rradius=128):
+        super().__init__()
+        self.embed = nn.Embedding(lradius + rradius + 1, embed_dim)
+        self.dropout = nn.Dropout(p=dropout)
+        self.lradius, self.rradius = lradius, rradius
+
+    def encode(self, position: th.Tensor) -> th.Tensor:
+        position = th.clamp(position, max=self.rradius, min=-self.lradius)
+        return self.embed.weight.detach()[position + self.lradius]
+
+
+# ------------------------------------------------------------------------------------ containers: layers
+class MultiheadAttention(nn.Module):
+    """Parameters of ApsMultiheadAttention / Rel… / Xl… (impl.py:22-50, :299-322)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0, xl=False, rel_u=None, rel_v=None):
+        super().__init__()
+        assert embed_dim % num_heads == 0, "embed_dim must be divisible by num_heads"
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.in_proj_weight = nn.Parameter(th.empty(3 * embed_dim, embed_dim))
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        self.in_proj_bias = nn.Parameter(th.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=True)
+        self.dropout = nn.Dropout(p=dropout)
+        if xl:
+            shape = (num_heads, self.head_dim)
+            self.rel_u = _relative_uv(shape) if rel_u is None else rel_u
+            self.rel_v = _relative_uv(shape) if rel_v is None else rel_v
+            self.rel_proj = nn.Linear(embed_dim, embed_dim, bias=False)
+
+
+def _ffn(att_dim, ffn_dim, dropout, activation):
+    return nn.Sequential(nn.Linear(att_dim, ffn_dim), _activation(activation), nn.Dropout(dropout),
+                         nn.Linear(ffn_dim, att_dim), nn.Dropout(dropout))
+
+
+class TransformerLayer(nn.Module):
+    """impl.py:377-429"""
+
+    def __init__(self, att_dim, self_attn, feedforward_dim=2048, dropout=0.1, activation="relu", pre_norm=False):
+        super().__init__()
+        self.self_attn = self_attn
+        self.feedforward = _ffn(att_dim, feedforward_dim, dropout, activation)
+        self.norm1 = nn.LayerNorm(att_dim)
+        self.norm2 = nn.LayerNorm(att_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.pre_norm, self.activation = pre_norm, activation
+
+
+class ConformerLayer(nn.Module):
+    """impl.py:432-497"""
+
+    def __init__(self, att_dim, self_attn, feedforward_dim=2048, dropout=0.1, kernel_size=15, macaron=True,
+                 pre_norm=True, casual_conv1d=False, activation="swish"):
+        super().__init__()
+        assert kernel_size % 2 == 1
+        self.self_attn = self_attn
+        if macaron:
+            self.norm_ffn1 = nn.LayerNorm(att_dim)
+            self.macaron_factor = 0.5
+            self.feedforward1 = _ffn(att_dim, feedforward_dim, dropout, activation)
+        else:
+            self.macaron_factor = 1
+            self.norm_ffn1 = None
+            self.feedforward1 = None
+        self.convolution = nn.Sequential(
+            nn.Conv1d(att_dim, att_dim * 2, 1), nn.GLU(dim=-2),
+            nn.Conv1d(att_dim, att_dim, kernel_size, groups=att_dim,
+                      padding=0 if casual_conv1d else (kernel_size - 1) // 2), nn.BatchNorm1d(att_dim),
+            _activation(activation), nn.Conv1d(att_dim, att_dim, 1), nn.Dropout(p=dropout))
+        self.norm_ffn2 = nn.LayerNorm(att_dim)
+        self.feedforward2 = _ffn(att_dim, feedforward_dim, dropout, activation)
+        self.norm_attn = nn.LayerNorm(att_dim)
+        self.norm_conv = nn.LayerNorm(att_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.padding = kernel_size - 1 if casual_conv1d else 0
+        self.kernel_size = kernel_size
+        self.pre_norm, self.activation = pre_norm, activation
+
+
+class LayerStack(nn.Module):
+    """ApsTransformerEncoder (impl.py:718-756): `layers` + optional final `norm`."""
+
+    def __init__(self, layers: List[nn.Module], norm: Optional[nn.Module]):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.num_layers = len(layers)
+        self.norm = norm
+
+
+def _build_layers(arch: str, pose: str, num_layers: int, kw: Dict) -> LayerStack:
+    """get_xfmr_encoder (impl.py:759-787)."""
+    if arch not in ("xfmr", "cfmr") or pose not in ("abs", "rel", "xl"):
+        raise ValueError(f"Unknown type of the encoders: {arch}_{pose}")
+    kw = dict(kw)
+    att_dim, nhead = kw.pop("att_dim"), kw.pop("nhead")
+    att_dropout, ffn_dropout = kw.pop("att_dropout", 0.1), kw.pop("ffn_dropout", 0.1)
+    tie = kw.pop("tie", False) if pose == "xl" else False
+    kw.pop("rel_u", None), kw.pop("rel_v", None)
+    pre_norm = kw.get("pre_norm", arch == "cfmr")
+    final_norm = nn.LayerNorm(att_dim) if pre_norm else None
+    shared = (_relative_uv((nhead, att_dim // nhead)), _relative_uv((nhead, att_dim // nhead))) if tie else None
+    layers = []
+    for _ in range(num_layers):
+        u, v = shared if shared else (None, None)
+        attn = MultiheadAttention(att_dim, nhead, dropout=att_dropout, xl=(pose == "xl"), rel_u=u, rel_v=v)
+        if arch == "xfmr":
+            layers.append(TransformerLayer(att_dim, attn, dropout=ffn_dropout, **kw))
+        else:
+            layers.append(ConformerLayer(att_dim, attn, dropout=ffn_dropout, **kw))
+    return LayerStack(layers, final_norm)
+
+
+def _context_mask(T: int, chunk: int, lctx: int, rctx: int, device) -> th.Tensor:
+    """Additive (-inf / 0) T x T context mask (aps/asr/transformer/utils.py:61-98)."""
+    lctx = T if lctx < 0 else lctx
+    rctx = T if rctx < 0 else rctx
+    idx = th.arange(T, device=device)
+    fl = th.div(idx, chunk, rounding_mode="floor")
+    right = (fl + rctx + 1) * chunk
+    left = th.clamp_min((fl - lctx) * chunk, 0)
+    cols = idx[None, :].expand(T, T)
+    bad = (cols >= right[:, None]) | (cols < left[:, None])
+    return th.zeros(T, T, device=device).masked_fill(bad, float("-inf"))
+
+
+# ------------------------------------------------------------------------------------ the encoder
+class TransformerEncoder(nn.Module):
+    """Transformer based encoders: arch {xfmr|cfmr}, pose {abs|rel|xl}, proj {conv2d|linear|none}."""
+
+    def __init__(self, arch: str, input_size: int, output_proj: int = -1, num_layers: int = 6, lctx: int = -1,
+                 rctx: int = -1, chunk_size: int = 1, proj: str = "conv2d", proj_kwargs: Dict = {},
+                 pose: str = "abs", pose_kwargs: Dict = {}, arch_kwargs: Dict = {}):
+        super().__init__()
+        att_dim = arch_kwargs["att_dim"]
+        if proj == "none":
+            self.proj = None
+        elif proj == "conv2d":
+            self.proj = Conv2dProj(input_size, att_dim, **proj_kwargs)
+        elif proj == "linear":
+            self.proj = LinearProj(input_size, att_dim, **proj_kwargs)
+        else:
+            raise ValueError(f"Unsupported projection layer: {proj} (aps_b200 provides conv2d | linear | none)")
+        if pose == "rel":
+            self.pose = RelPosEncoding(att_dim // arch_kwargs["nhead"], **pose_kwargs)
+        elif pose in ("abs", "xl"):
+            self.pose = SinPosEncoding(att_dim, **pose_kwargs)
+        else:
+            raise ValueError(f"Unsupported pose layer: {pose} (aps_b200 provides abs | rel | xl)")
+        self.pose_type, self.arch = pose, arch
+        self.encoder = _build_layers(arch, pose, num_layers, arch_kwargs)
+        self.lctx, self.rctx, self.chunk_size = lctx, rctx, chunk_size
+        self.outp = nn.Linear(att_dim, output_proj) if output_proj > 0 else None
+        self.att_dim, self.nhead = att_dim, arch_kwargs["nhead"]
+        self._packs = None
+        self.register_load_state_dict_post_hook(lambda m, k: m._drop_packs())
+
+    # ---- repacked weights (BatchNorm folding, layout changes); rebuilt after load_state_dict / .to() ------
+    def _drop_packs(self):
+        self._packs = None
+
+    def _apply(self, fn, *a, **k):
+        self._packs = None
+        return super()._apply(fn, *a, **k)
+
+    @staticmethod
+    def _fold_bn(w: th.Tensor, b: Optional[th.Tensor], bn) -> Tuple[th.Tensor, th.Tensor]:
+        scale = bn.weight.detach() / th.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        b0 = b.detach() if b is not None else th.zeros_like(shift)
+        return w.detach() * scale.view(-1, *([1] * (w.dim() - 1))), b0 * scale + shift
+
+    def _build_packs(self, dev):
+        pk = {"dev": dev, "layers": []}
+        if isinstance(self.proj, Conv2dProj):
+            convs = []
+            for blk in self.proj.conv.enc_layers:
+                if not isinstance(blk.norm.norm, nn.BatchNorm2d):
+                    raise RuntimeError("aps_b200: only norm='BN' is implemented for the conv2d projection")
+                w, b = self._fold_bn(blk.conv.weight, blk.conv.bias, blk.norm.norm)
+                convs.append((w.permute(0, 2, 3, 1).contiguous(), b.contiguous(), blk.stride, blk.padding))
+            pk["convs"] = convs
+            outp = self.proj.conv.outp
+            if outp is not None:
+                C = self.proj.conv.enc_layers[-1].conv.out_channels
+                Fq = outp.in_features // C
+                # reference flattens [C, F'] (channel-major); our activations are NHWC, i.e. [F', C]
+                pk["front_w"] = outp.weight.detach().view(-1, C, Fq).permute(0, 2, 1).reshape(outp.out_features, -1).contiguous()
+                pk["front_b"] = outp.bias.detach()
+        for lay in self.encoder.layers:
+            d = {}
+            if isinstance(lay, ConformerLayer):
+                c = lay.convolution
+                D = c[0].in_channels
+                w0 = c[0].weight.detach().view(2 * D, D)
+                d["pw1_w"] = th.stack([w0[:D], w0[D:]], 1).reshape(2 * D, D).contiguous()      # interleave for GLU
+                d["pw1_b"] = th.stack([c[0].bias.detach()[:D], c[0].bias.detach()[D:]], 1).reshape(-1).contiguous()
+                wdw, bdw = self._fold_bn(c[2].weight, c[2].bias, c[3])
+                d["dw_w"] = wdw.view(D, -1).t().contiguous()                                   # [K, D]
+                d["dw_b"] = bdw.contiguous()
+                d["pw2_w"] = c[5].weight.detach().view(D, D).contiguous()
+                d["pw2_b"] = c[5].bias.detach()
+            pk["layers"].append(d)
+        return pk
+
+    # ---- pieces ---------------------------------------------------------------------------------------------
+    def _front(self, x: th.Tensor, lens: Optional[th.Tensor], pk):
+        if self.proj is None:
+            return x, lens
+        if isinstance(self.proj, LinearProj):
+            nrm = self.proj.norm.norm
+            if not isinstance(nrm, nn.BatchNorm1d):
+                raise RuntimeError("aps_b200: LinearProj(norm='LN') (a GroupNorm over time) is not implemented; "
+                                   "use norm='BN'")
+            N, T, Fi = x.shape
+            w, b = self._fold_bn(self.proj.proj.weight, self.proj.proj.bias, nrm)
+            y = ops.linear(ops.rows2d(x), w.contiguous(), b.contiguous(), act="relu")
+            return y.view(N, T, -1), lens
+        x4 = x[:, None] if x.dim() == 3 else x                      # N x C x T x F
+        nhwc = x4.permute(0, 2, 3, 1).contiguous()
+        for (w, b, stride, padding), blk in zip(pk["convs"], self.proj.conv.enc_layers):
+            nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu")
+            if lens is not None:
+                lens = blk.compute_outp_dim(lens, 0)
+        N, T, Fq, C = nhwc.shape
+        flat = nhwc.view(N * T, Fq * C)
+        if "front_w" in pk:
+            flat = ops.linear(flat, pk["front_w"], pk["front_b"])
+        else:   # no output projection: restore the reference's channel-major feature order
+            flat = nhwc.permute(0, 1, 3, 2).reshape(N * T, C * Fq)
+        return flat.view(N, T, -1), lens
+
+    def _attention(self, a, x, res, N, T, inj, kpm, amask):
+        """res + SelfAttention(x) with the parameters of container `a`."""
+        qkv = ops.linear(x, a.in_proj_weight.detach(), a.in_proj_bias.detach())
+        if self.pose_type == "rel":
+            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=1, pos=inj, kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask)
+        elif self.pose_type == "xl":
+            pos = ops.linear(inj, a.rel_proj.weight.detach())
+            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=2, pos=pos, rel_u=a.rel_u.detach().contiguous(),
+                           rel_v=a.rel_v.detach().contiguous(), kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask,
+                           qpos_is_value=True)
+        else:
+            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=0, kpm=kpm, kpm_fill=float("-inf"), attn_mask=amask)
+        return ops.linear(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach(), residual=res)
+
+    @staticmethod
+    def _ffn_out(seq, x, act):
+        h = ops.linear(x, seq[0].weight.detach(), seq[0].bias.detach(), act=act)
+        return h, seq[3]
+
+    @staticmethod
+    def _ln(norm, x, residual=None, alpha=1.0):
+        return ops.layernorm(x, norm.weight.detach(), norm.bias.detach(), norm.eps, residual=residual, alpha=alpha)
+
+    def _xfmr_layer(self, lay, pk, x, N, T, inj, kpm, amask):
+        act = lay.activation
+        if lay.pre_norm:
+            x = self._attention(lay.self_attn, self._ln(lay.norm1, x), x, N, T, inj, kpm, amask)
+            h, l2 = self._ffn_out(lay.feedforward, self._ln(lay.norm2, x), act)
+            return ops.linear(h, l2.weight.detach(), l2.bias.detach(), residual=x)
+        x = self._ln(lay.norm1, self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask))
+        h, l2 = self._ffn_out(lay.feedforward, x, act)
+        return self._ln(lay.norm2, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x)
+
+    def _conv_module(self, lay, d, u, x, N, T):
+        g = ops.linear(u, d["pw1_w"], d["pw1_b"], act="glu")
+        K = lay.kernel_size
+        c = ops.dwconv1d(g, N, T, d["dw_w"], d["dw_b"], dilation=1, left_pad=(K - 1) if lay.padding else (K - 1) // 2,
+                         act=lay.activation)
+        return ops.linear(c, d["pw2_w"], d["pw2_b"], residual=x)                # conv(u) + x
+
+    def _cfmr_layer(self, lay, d, x, N, T, inj, kpm, amask):
+        act, mac = lay.activation, lay.macaron_factor
+        if lay.feedforward1 is not None:
+            if lay.pre_norm:
+                h, l2 = self._ffn_out(lay.feedforward1, self._ln(lay.norm_ffn1, x), act)
+                x = ops.linear(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
+            else:
+                h, l2 = self._ffn_out(lay.feedforward1, x, act)
+                x = self._ln(lay.norm_ffn1, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
+        if lay.pre_norm:
+            x = self._attention(lay.self_attn, self._ln(lay.norm_attn, x), x, N, T, inj, kpm, amask)
+            x = self._conv_module(lay, d, self._ln(lay.norm_conv, x), x, N, T)
+            h, l2 = self._ffn_out(lay.feedforward2, self._ln(lay.norm_ffn2, x), act)
+            return ops.linear(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
+        x = self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask)
+        x = self._conv_module(lay, d, self._ln(lay.norm_attn, x), x, N, T)       # impl.py:536 reuses norm_attn
+        x = self._ln(lay.norm_conv, x)
+        h, l2 = self._ffn_out(lay.feedforward2, x, act)
+        return self._ln(lay.norm_ffn2, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def forward(self, inp_pad: th.Tensor, inp_len: Optional[th.Tensor]):
+        """inp_pad N x Ti x F (or N x C x Ti x F), inp_len N or None -> (N x To x D, lengths)."""
+        if self.training:
+            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
+        dev = _lib.require_cuda(inp_pad, "encoder input")
+        if self._packs is None or self._packs["dev"] != dev:
+            if next(self.parameters()).device != dev:
+                raise RuntimeError(f"encoder parameters on {next(self.parameters()).device}, input on {dev}")
+            self._packs = self._build_packs(dev)
+        pk = self._packs
+        x = inp_pad.detach().float()
+        x, inp_len = self._front(x, inp_len, pk)
+        N, T, D = x.shape
+        kpm = None
+        if inp_len is not None:
+            steps = th.arange(int(inp_len.max()), device=dev)
+            if steps.numel() != T:
+                raise RuntimeError(f"padding mask length {steps.numel()} does not match {T} encoder frames")
+            kpm = (steps[None, :] >= inp_len.to(dev)[:, None]).to(th.uint8).contiguous()
+        inj = None
+        if self.pose_type == "abs":
+            enc = self.pose.encode(th.arange(0, T, 1.0, device=dev))
+            x = x * self.pose.factor + enc
+        elif self.pose_type == "rel":
+            inj = self.pose.encode(th.arange(-T + 1, T, device=dev)).contiguous()
+        else:
+            inj = self.pose.encode(th.arange(0, 2 * T - 1, 1.0, device=dev)).contiguous()
+        amask = None
+        if self.lctx != -1 or self.rctx != -1:
+            amask = _context_mask(T, self.chunk_size, self.lctx, self.rctx, dev).contiguous()
+        rows = x.reshape(N * T, D).contiguous()
+        for lay, d in zip(self.encoder.layers, pk["layers"]):
+            if isinstance(lay, ConformerLayer):
+                rows = self._cfmr_layer(lay, d, rows, N, T, inj, kpm, amask)
+            else:
+                rows = self._xfmr_layer(lay, d, rows, N, T, inj, kpm, amask)
+        if self.encoder.norm is not None:
+            rows = self._ln(self.encoder.norm, rows)
+        if self.outp is not None:
+            rows = ops.linear(rows, self.outp.weight.detach(), self.outp.bias.detach())
+        return rows.view(N, T, -1), inp_len

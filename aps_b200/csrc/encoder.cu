@@ -281,9 +281,7 @@ extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_
     switch (p.dh) {
         case 32: mhsa_kernel<32><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
         case 64: mhsa_kernel<64><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
-        case 96: mhsa_kernel<96><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
-        case 128: mhsa_kernel<128><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
-        default: return set_error(-1, "unsupported head dimension %d (32, 64, 96, 128)", p.dh);
+        default: return set_error(-1, "unsupported head dimension %d (32 or 64)", p.dh);
     }
     APSB_LAUNCH_CHECK();
     return 0;

@@ -30,7 +30,7 @@ int launch_gemm(const ALoader& a, const float* Wt, long long ldw, int M, int N, 
 
 static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* out, int64_t ldo) {
     APSB_CHECK_ARG(d && out, "null pointer argument");
-    APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_LEAKY, "unknown activation %d", d->act);
+    APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_GELU, "unknown activation %d", d->act);
     APSB_CHECK_ARG(d->act != ACT_GLU || (N % 2 == 0), "GLU needs an even number of columns");
     APSB_CHECK_ARG(d->act != ACT_PRELU || d->prelu_slope, "PReLU slope missing");
     e.bias = d->bias; e.act = d->act; e.alpha = d->alpha;

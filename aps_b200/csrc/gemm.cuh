@@ -18,7 +18,7 @@
 namespace apsb {
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_PRELU = 5, ACT_GLU = 6,
-                 ACT_LEAKY = 7 };
+                 ACT_LEAKY = 7, ACT_GELU = 8 };
 
 struct Epilogue {
     const float* bias;     // [N] or nullptr
@@ -42,6 +42,7 @@ __device__ __forceinline__ float apply_act(float v, int act, const Epilogue& e, 
         case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
         case ACT_PRELU: return v >= 0.f ? v : v * __ldg(e.slope + (long long)n * e.slope_stride);
         case ACT_LEAKY: return v >= 0.f ? v : v * e.leak;
+        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
         default: return v;
     }
 }

@@ -1,0 +1,123 @@
+"""Thin Python wrappers over the dense-layer / normalisation / attention entry points of the C ABI.
+Every function takes CUDA fp32 tensors, allocates the output with torch and launches on the current
+stream; there is no fallback path."""
+from typing import Optional
+
+import torch as th
+
+from . import _lib
+
+
+def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=None, beta=1.0):
+    e = _lib.Epilogue()
+    e.bias = _lib.ptr(bias)
+    e.act = _lib.ACT[act]
+    e.alpha = float(alpha)
+    e.prelu_slope = _lib.ptr(slope)
+    e.prelu_per_channel = int(slope is not None and slope.numel() > 1)
+    e.leaky_slope = float(leaky)
+    e.residual = _lib.ptr(residual)
+    e.ld_residual = residual.stride(0) if residual is not None else 0
+    e.beta = float(beta)
+    return e
+
+
+def rows2d(x: th.Tensor) -> th.Tensor:
+    """View `x` as [rows, cols] with unit column stride (copies only if it has to)."""
+    x = x.reshape(-1, x.shape[-1])
+    return x if x.stride(1) == 1 else x.contiguous()
+
+
+def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, act: str = "none", alpha: float = 1.0,
+           slope=None, leaky: float = 0.0, residual: Optional[th.Tensor] = None, beta: float = 1.0,
+           out: Optional[th.Tensor] = None) -> th.Tensor:
+    """out[m, :] = alpha * act(x[m, :] @ weight.T + bias) + beta * residual[m, :]   (x: [M, K], weight: [N, K])"""
+    dev = _lib.require_cuda(x, "linear input")
+    M, K = x.shape
+    N = weight.shape[0]
+    ncol = N // 2 if act == "glu" else N
+    if out is None:
+        out = th.empty((M, ncol), dtype=th.float32, device=dev)
+    e = _epilogue(bias, act, alpha, slope, leaky, residual, beta)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
+                                                   N, e, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
+    return out
+
+
+def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
+                act: str = "none", slope=None, leaky: float = 0.0) -> th.Tensor:
+    """x [B, H, W, Cin] contiguous, weight [Cout, KH, KW, Cin] contiguous -> [B, OH, OW, Cout]."""
+    dev = _lib.require_cuda(x, "conv input")
+    B, H, W, Cin = x.shape
+    Cout, KH, KW, _ = weight.shape
+    OH = (H + 2 * padding[0] - dilation[0] * (KH - 1) - 1) // stride[0] + 1
+    OW = (W + 2 * padding[1] - dilation[1] * (KW - 1) - 1) // stride[1] + 1
+    if OH <= 0 or OW <= 0:
+        raise RuntimeError(f"convolution output is empty for input {tuple(x.shape)}")
+    out = th.empty((B, OH, OW, Cout // 2 if act == "glu" else Cout), dtype=th.float32, device=dev)
+    e = _epilogue(bias, act, 1.0, slope, leaky)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_conv2d_nhwc_fwd(x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW,
+                                                        stride[0], stride[1], padding[0], padding[1], dilation[0],
+                                                        dilation[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
+    return out
+
+
+def layernorm(x: th.Tensor, gamma, beta, eps: float = 1e-5, residual: Optional[th.Tensor] = None,
+              alpha: float = 1.0) -> th.Tensor:
+    """LayerNorm(alpha * x + residual) over the last axis of [M, D] rows."""
+    dev = _lib.require_cuda(x, "layernorm input")
+    M, D = x.shape
+    out = th.empty((M, D), dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_layernorm_fwd(x.data_ptr(), x.stride(0), _lib.ptr(residual),
+                                                      residual.stride(0) if residual is not None else 0, float(alpha),
+                                                      _lib.ptr(gamma), _lib.ptr(beta), float(eps), M, D, out.data_ptr(),
+                                                      out.stride(0), _lib.stream_ptr(dev)))
+    return out
+
+
+def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
+             stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
+             residual=None) -> th.Tensor:
+    """Depthwise conv over time on token rows [N*T, D] (row(n, t) = n*stride_n + t*stride_t)."""
+    dev = _lib.require_cuda(x, "dwconv input")
+    D = x.shape[1]
+    Kw = weight_kd.shape[0]
+    out = th.empty_like(x)
+    e = _epilogue(None, act, 1.0, slope, 0.0, residual, 1.0)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_dwconv1d_fwd(x.data_ptr(), x.stride(0), N, T, D,
+                                                     T if stride_n is None else stride_n, stride_t,
+                                                     weight_kd.data_ptr(), _lib.ptr(bias), Kw, dilation, left_pad, e,
+                                                     out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
+    return out
+
+
+def mhsa(qkv: th.Tensor, N: int, L: int, H: int, mode: int = 0, pos: Optional[th.Tensor] = None,
+         rel_u=None, rel_v=None, kpm: Optional[th.Tensor] = None, kpm_fill: float = float("-inf"),
+         attn_mask: Optional[th.Tensor] = None, qpos_is_value: bool = False) -> th.Tensor:
+    """Self-attention on the packed projection qkv [N*L, 3E] (rows batch-major) -> context [N*L, E]."""
+    dev = _lib.require_cuda(qkv, "attention input")
+    E = qkv.shape[1] // 3
+    dh = E // H
+    out = th.empty((N * L, E), dtype=th.float32, device=dev)
+    d = _lib.AttnDesc()
+    base, ld = qkv.data_ptr(), qkv.stride(0)
+    d.q, d.k, d.v = base, base + 4 * E, base + 8 * E
+    d.qpos = d.v if qpos_is_value else d.q
+    d.ld_q = d.ld_k = d.ld_v = d.ld_qpos = ld
+    d.stride_n, d.stride_t = L, 1
+    d.batch, d.length, d.heads, d.head_dim = N, L, H, dh
+    d.mode = mode
+    d.pos = _lib.ptr(pos)
+    d.ld_pos = pos.stride(0) if pos is not None else 0
+    d.rel_u, d.rel_v = _lib.ptr(rel_u), _lib.ptr(rel_v)
+    d.key_padding_mask = _lib.ptr(kpm)
+    d.padding_fill = kpm_fill
+    d.attn_mask = _lib.ptr(attn_mask)
+    d.scale = 1.0 / dh**0.5
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_mhsa_fwd(d, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
+    return out

@@ -182,7 +182,7 @@ int aps_b200_beamform_fwd(const float* x_real, const float* x_imag, const int64_
 /* Dense layers ---------------------------------------------------------------------------------
  * out[m, n] = alpha * act(sum_k x[m, k] * weight[n, k] + bias[n]) + beta * residual[m, n]
  * (exact fp32 accumulate).  act: 0 none, 1 relu, 2 swish, 3 tanh, 4 sigmoid, 5 prelu, 6 glu (column
- * pairs (2j, 2j+1) -> out[:, j] = v0 * sigmoid(v1)), 7 leaky relu.
+ * pairs (2j, 2j+1) -> out[:, j] = v0 * sigmoid(v1)), 7 leaky relu, 8 gelu (erf).
  */
 typedef struct aps_b200_epilogue {
     const float* bias;         /* [N] or NULL */
@@ -213,6 +213,50 @@ int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int6
                              int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,
                              int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
                              float* out, void* stream);
+
+/* Encoder (non-GEMM) kernels ---------------------------------------------------------------------
+ * Activations are token-major rows; row(n, t) = n*stride_n + t*stride_t.
+ */
+
+/* out = LayerNorm(alpha * x + residual) * gamma + beta over the last `dim` values of every row
+ * (residual / gamma / beta may be NULL).  Replaces nn.LayerNorm + the residual / macaron-factor
+ * arithmetic of aps/asr/transformer/impl.py:424-428 and :508-540.                              */
+int aps_b200_layernorm_fwd(const float* x, int64_t ld_x, const float* residual, int64_t ld_residual,
+                           float alpha, const float* gamma, const float* beta, float eps,
+                           int64_t rows, int64_t dim, float* out, int64_t ld_out, void* stream);
+
+/* Depthwise 1-D convolution over time: out[n, t, d] = epi(bias[d] + sum_k w[k, d] * x[n, t - left_pad
+ * + k*dilation, d]) (zeros outside [0, T)); `weight_kd` is [kernel, channels] (tap-major).
+ * Replaces the grouped nn.Conv1d (+ eval BatchNorm1d folded by the caller + activation) of
+ * aps/asr/transformer/impl.py:456-465 and aps/sse/bss/tcn.py:141-151.                         */
+int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames,
+                          int64_t channels, int64_t stride_n, int64_t stride_t,
+                          const float* weight_kd, const float* bias, int kernel, int dilation,
+                          int left_pad, const aps_b200_epilogue* epi, float* out, int64_t ld_out,
+                          void* stream);
+
+/* Multi-head self-attention, softmax((q.k + pos_term) * scale [masked]) . v per (batch, head).
+ * mode 0: no position term (aps/asr/transformer/impl.py:120-131 / torch MHA);
+ * mode 1: "rel"  pos [2L-1, head_dim], term[l, s] = qpos[l] . pos[s - l + L - 1] (impl.py:240-261 with
+ *         the digit_shift skew of aps/asr/transformer/utils.py:14-39 done by indexing);
+ * mode 2: "xl"   pos [2L-1, heads*head_dim] (already projected), content query = qpos + rel_u,
+ *         position query = qpos + rel_v (impl.py:324-344; the reference passes VALUE as qpos,
+ *         impl.py:369).
+ * key_padding_mask [batch, L] (1 = masked -> logit := padding_fill), attn_mask [L, L] additive.
+ * Softmax, masking and context follow impl.py:95-118.  head_dim in {32, 64}.                   */
+typedef struct aps_b200_attn_desc {
+    const float* q; const float* k; const float* v; const float* qpos;
+    int64_t ld_q, ld_k, ld_v, ld_qpos;
+    int64_t stride_n, stride_t;
+    int64_t batch, length, heads, head_dim;
+    int32_t mode;
+    const float* pos; int64_t ld_pos;
+    const float* rel_u; const float* rel_v;
+    const uint8_t* key_padding_mask; float padding_fill;
+    const float* attn_mask;
+    float scale;
+} aps_b200_attn_desc;
+int aps_b200_mhsa_fwd(const aps_b200_attn_desc* desc, float* out, int64_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -122,6 +122,41 @@ def main():
         arrays = dict(xr=xr, xi=xi, mask_s=ms, mask_n=mn, lens=lens, yr=y.real, yi=y.imag, Rr=R.real, Ri=R.imag)
         arrays.update({"p." + k: v for k, v in net.state_dict().items()})
         save(f"mvdr_{i}", dict(num_bins=Fb, att_dim=24, mask_norm=norm, use_n=use_n, use_len=use_len), **arrays)
+    # ---- transformer / conformer encoders (aps/asr/transformer/encoder.py) -------------------------------------
+    import copy
+    from aps.asr.transformer.encoder import TransformerEncoder
+    ak_c = dict(att_dim=64, nhead=2, feedforward_dim=96, att_dropout=0.1, ffn_dropout=0.1, kernel_size=15)
+    ak_x = dict(att_dim=64, nhead=2, feedforward_dim=96, att_dropout=0.1, ffn_dropout=0.1)
+    variants = [
+        ("cfmr", "rel", False, dict(conv_channels=16, num_layers=3), dict(lradius=12, rradius=9), 77, -1),
+        ("cfmr", "rel", True, dict(conv_channels=16, num_layers=2), dict(lradius=40, rradius=40), 61, 20),
+        ("cfmr", "abs", False, dict(conv_channels=16, num_layers=2), dict(), 61, -1),
+        ("cfmr", "xl", False, dict(conv_channels=16, num_layers=2), dict(), 61, -1),
+        ("xfmr", "abs", False, dict(conv_channels=16, num_layers=2), dict(scaled=True), 61, -1),
+        ("xfmr", "rel", True, dict(conv_channels=16, num_layers=2), dict(lradius=40, rradius=40), 61, -1),
+        ("xfmr", "xl", True, dict(conv_channels=16, num_layers=2), dict(), 61, -1),
+    ]
+    for i, (arch, pose, pre, pkw, posekw, T, outp) in enumerate(variants):
+        g = th.Generator().manual_seed(500 + i)
+        cfg = dict(arch=arch, input_size=40, output_proj=outp, num_layers=2, proj="conv2d", proj_kwargs=pkw,
+                   pose=pose, pose_kwargs=posekw, arch_kwargs=dict(ak_c if arch == "cfmr" else ak_x, pre_norm=pre))
+        net = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+        with th.no_grad():                                  # non-trivial BatchNorm statistics and biases
+            for name, buf in net.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+                if name.endswith("running_var"):
+                    buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+            for name, prm in net.named_parameters():
+                if name.endswith("bias") or "norm" in name:
+                    prm.add_(0.1 * th.randn(prm.shape, generator=g))
+        x = th.randn(3, T, 40, generator=g)
+        lens = th.tensor([T, T - 8, T - 23])
+        with th.no_grad():
+            y, yl = net(x, lens.clone())
+        arrays = dict(x=x, lens=lens, y=y, ylens=yl)
+        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        save(f"enc_{i}", cfg, **arrays)
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)

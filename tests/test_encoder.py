@@ -1,0 +1,158 @@
+"""Transformer / conformer encoder (rows a20-a23): oracle vs golden (CPU), CUDA path vs golden + oracle (GPU)."""
+import copy
+import json
+
+import pytest
+import torch as th
+
+from conftest import FLOAT_TOL, golden_names, import_reference, load_golden, rel_err
+from oracle.encoder import EncoderOracle, digit_shift
+
+DEV = "cuda:0"
+
+
+def _sd(g):
+    return {k[2:]: v for k, v in g.items() if k.startswith("p.")}
+
+
+@pytest.mark.parametrize("name", golden_names("enc_"))
+def test_oracle_encoder_golden(name):
+    cfg, g = load_golden(name)
+    y, yl = EncoderOracle(cfg, _sd(g))(g["x"], g["lens"].clone())
+    assert th.equal(yl, g["ylens"])                         # subsampled lengths: integers, exact (Q17)
+    assert rel_err(y, g["y"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names("enc_"))
+def test_state_dict_layout_matches_golden(name):
+    from aps_b200.asr.transformer import TransformerEncoder
+    cfg, g = load_golden(name)
+    net = TransformerEncoder(**copy.deepcopy(cfg))
+    want = {k: tuple(v.shape) for k, v in _sd(g).items()}
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == want
+    net.load_state_dict(_sd(g), strict=True)
+
+
+def test_training_mode_and_cpu_are_refused():
+    from aps_b200.asr.transformer import TransformerEncoder
+    cfg, g = load_golden("enc_0")
+    net = TransformerEncoder(**copy.deepcopy(cfg))
+    with pytest.raises(RuntimeError, match="inference forward only"):
+        net.train()(g["x"], None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.eval()(g["x"], None)
+
+
+@pytest.mark.reference
+def test_digit_shift_and_oracle_vs_live_reference():
+    import_reference()
+    from aps.asr.transformer.encoder import TransformerEncoder
+    from aps.asr.transformer.utils import digit_shift as ref_shift
+    t = th.randn(7, 2, 3, 13)
+    assert th.equal(digit_shift(t), ref_shift(t))
+    th.manual_seed(0)
+    ak = dict(att_dim=64, nhead=4, feedforward_dim=128, att_dropout=0.1, ffn_dropout=0.1, kernel_size=15, pre_norm=False)
+    for pose, pk in (("rel", dict(lradius=20, rradius=20)), ("abs", {}), ("xl", {})):
+        cfg = dict(arch="cfmr", input_size=80, output_proj=-1, num_layers=2, proj="conv2d",
+                   proj_kwargs=dict(conv_channels=32, num_layers=2), pose=pose, pose_kwargs=pk, arch_kwargs=dict(ak))
+        enc = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+        x, lens = th.randn(3, 67, 80), th.tensor([67, 58, 37])
+        with th.no_grad():
+            y, yl = enc(x, lens.clone())
+        o, ol = EncoderOracle(cfg, enc.state_dict())(x, lens.clone())
+        assert th.equal(yl, ol) and rel_err(o, y) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names("enc_"))
+def test_encoder_golden_gpu(name):
+    from aps_b200.asr.transformer import TransformerEncoder
+    cfg, g = load_golden(name)
+    net = TransformerEncoder(**copy.deepcopy(cfg))
+    net.load_state_dict(_sd(g), strict=True)
+    net = net.to(DEV).eval()
+    y, yl = net(g["x"].to(DEV), g["lens"].to(DEV))
+    assert th.equal(yl.cpu(), g["ylens"])
+    assert y.shape == g["y"].shape
+    assert rel_err(y, g["y"]) < FLOAT_TOL
+    # no lengths: no key padding mask
+    y2, _ = net(g["x"].to(DEV), None)
+    o2, _ = EncoderOracle(cfg, _sd(g))(g["x"], None)
+    assert rel_err(y2, o2) < FLOAT_TOL
+
+
+@pytest.mark.gpu
+def test_dense_kernels_vs_torch():
+    """GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the CPU."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    th.manual_seed(1)
+    for (M, K, N) in ((37, 257, 50), (300, 256, 512), (1000, 96, 64), (5, 8, 6), (129, 2304, 256)):
+        x, w, b, r = th.randn(M, K), th.randn(N, K) / K**0.5, th.randn(N), th.randn(M, N)
+        ref = F.linear(x, w, b)
+        xg, wg, bg, rg = x.to(DEV), w.to(DEV), b.to(DEV), r.to(DEV)
+        assert rel_err(ops.linear(xg, wg, bg), ref) < 1e-5
+        assert rel_err(ops.linear(xg, wg, bg, act="swish", alpha=0.5, residual=rg), 0.5 * ref * th.sigmoid(ref) + r) < 1e-5
+        assert rel_err(ops.linear(xg, wg, None, act="relu"), F.relu(F.linear(x, w))) < 1e-5
+        assert rel_err(ops.linear(xg, wg, bg, act="gelu"), F.gelu(ref)) < 1e-5
+        assert rel_err(ops.linear(xg, wg, bg, act="tanh"), th.tanh(ref)) < 1e-5
+        slope = th.rand(N)
+        assert rel_err(ops.linear(xg, wg, bg, act="prelu", slope=slope.to(DEV)), th.where(ref >= 0, ref, ref * slope)) < 1e-5
+        if N % 2 == 0:
+            wi = th.stack([w[:N // 2], w[N // 2:]], 1).reshape(N, K)
+            bi = th.stack([b[:N // 2], b[N // 2:]], 1).reshape(N)
+            assert rel_err(ops.linear(xg, wi.to(DEV), bi.to(DEV), act="glu"), F.glu(ref, -1)) < 1e-5
+    # strided input rows (a column slice of a wider matrix)
+    big = th.randn(64, 300)
+    assert rel_err(ops.linear(big.to(DEV)[:, 20:148], wg[:, :128].contiguous()), F.linear(big[:, 20:148], w[:, :128])) < 1e-5
+    # implicit-GEMM convolutions (NHWC) incl. Cin = 1 and dilation / asymmetric stride
+    for (B, H, W, Ci, Co, k, s, p, d) in ((2, 33, 20, 1, 16, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                          (3, 17, 11, 8, 24, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                          (2, 20, 9, 4, 6, (5, 2), (2, 1), (2, 0), (1, 1)),
+                                          (1, 40, 1, 12, 10, (3, 1), (1, 1), (2, 0), (2, 1))):
+        x, w, b = th.randn(B, Ci, H, W), th.randn(Co, Ci, *k) * 0.2, th.randn(Co)
+        ref = F.relu(F.conv2d(x, w, b, stride=s, padding=p, dilation=d)).permute(0, 2, 3, 1)
+        got = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV),
+                              b.to(DEV), stride=s, padding=p, dilation=d, act="relu")
+        assert got.shape == ref.shape and rel_err(got, ref) < 1e-5
+    # LayerNorm(alpha * x + res)
+    x, r, g_, b_ = th.randn(77, 256), th.randn(77, 256), th.rand(256) + 0.5, th.randn(256)
+    ref = F.layer_norm(0.5 * x + r, (256,), g_, b_)
+    assert rel_err(ops.layernorm(x.to(DEV), g_.to(DEV), b_.to(DEV), residual=r.to(DEV), alpha=0.5), ref) < 1e-5
+    # depthwise conv over time on batch-major rows
+    N, T, D, K = 3, 29, 40, 15
+    x, w, b = th.randn(N, T, D), th.randn(D, 1, K), th.randn(D)
+    ref = F.conv1d(x.transpose(1, 2), w, b, padding=7, groups=D).transpose(1, 2)
+    got = ops.dwconv1d(x.reshape(N * T, D).to(DEV), N, T, w.view(D, K).t().contiguous().to(DEV), b.to(DEV), left_pad=7)
+    assert rel_err(got.view(N, T, D), ref) < 1e-5
+    ref = F.conv1d(x.transpose(1, 2), w[..., :3], b, padding=4, dilation=4, groups=D).transpose(1, 2)
+    got = ops.dwconv1d(x.reshape(N * T, D).to(DEV), N, T, w.view(D, K)[:, :3].t().contiguous().to(DEV), b.to(DEV),
+                       dilation=4, left_pad=4)
+    assert rel_err(got.view(N, T, D), ref) < 1e-5
+
+
+@pytest.mark.gpu
+def test_c4_conformer_full_size_subset_vs_oracle():
+    """BASELINE config[3]: conformer 12L d=256 h=4 rel-pos, conv2d x3 front, B=64 on 80-d fbank [64, 398, 80].
+    Parity of sampled utterances against the CPU oracle + batch-shard invariance (bit identical rows)."""
+    from aps_b200.asr.transformer import TransformerEncoder
+    cfg = dict(arch="cfmr", input_size=80, output_proj=-1, num_layers=12, proj="conv2d",
+               proj_kwargs=dict(conv_channels=256, num_layers=3), pose="rel",
+               pose_kwargs=dict(dropout=0.1, lradius=256, rradius=256),
+               arch_kwargs=dict(att_dim=256, nhead=4, feedforward_dim=2048, att_dropout=0.1, ffn_dropout=0.1,
+                                kernel_size=15, pre_norm=False))
+    th.manual_seed(0)
+    net = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+    x = th.randn(64, 398, 80)
+    lens = th.full((64,), 398, dtype=th.int64)
+    lens[1::2] = 301
+    dev_net = copy.deepcopy(net).to(DEV)
+    y, yl = dev_net(x.to(DEV), lens.to(DEV))
+    assert y.shape == (64, 50, 256) and yl.tolist()[:2] == [50, 38]
+    rows = [0, 1]
+    # the key padding mask spans max(len): run the oracle on rows that include a full-length utterance
+    o, ol = EncoderOracle(cfg, net.state_dict())(x[rows], lens[rows].clone())
+    assert th.equal(ol, yl[rows].cpu())
+    assert rel_err(y[rows], o) < FLOAT_TOL
+    alone, _ = dev_net(x[rows].to(DEV), lens[rows].to(DEV))
+    assert th.equal(alone, y[rows])
