@@ -39,7 +39,7 @@ class Epilogue(Structure):
     """mirror of `aps_b200_epilogue`"""
     _fields_ = [("bias", c_void_p), ("act", c_int32), ("alpha", c_float), ("prelu_slope", c_void_p),
                 ("prelu_per_channel", c_int32), ("leaky_slope", c_float), ("residual", c_void_p),
-                ("ld_residual", c_int64), ("beta", c_float)]
+                ("ld_residual", c_int64), ("beta", c_float), ("post_scale", c_void_p), ("post_shift", c_void_p)]
 
 
 class AttnDesc(Structure):

@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(const __grid_constant__ D
         if (tt >= 0 && tt < p.T) acc = fmaf(__ldg(p.w + (long long)k * p.D + d), __ldg(p.x + (n * p.sn + tt * p.st) * p.ldx + d), acc);
     }
     const long long m = n * p.sn + t * p.st;
-    float v = p.e.alpha * apply_act(acc, p.e.act, p.e, d);
+    float v = apply_act(acc, p.e.act, p.e, d);
+    if (p.e.post_scale) v = fmaf(v, __ldg(p.e.post_scale + d), __ldg(p.e.post_shift + d));
+    v *= p.e.alpha;
     if (p.e.res) v = fmaf(p.e.beta, __ldg(p.e.res + m * p.e.ldres + d), v);
     p.e.out[m * p.e.ldo + d] = v;
 }
@@ -254,6 +256,8 @@ extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch
     p.e.bias = nullptr; p.e.act = epi->act; p.e.alpha = epi->alpha; p.e.slope = epi->prelu_slope;
     p.e.slope_stride = epi->prelu_per_channel ? 1 : 0; p.e.leak = epi->leaky_slope;
     p.e.res = epi->residual; p.e.ldres = epi->ld_residual; p.e.beta = epi->beta; p.e.out = out; p.e.ldo = ld_out;
+    p.e.post_scale = epi->post_scale; p.e.post_shift = epi->post_shift;
+    APSB_CHECK_ARG(!epi->post_scale == !epi->post_shift, "post_scale and post_shift come together");
     APSB_CHECK_ARG(epi->act != ACT_PRELU || epi->prelu_slope, "PReLU slope missing");
     const long long total = (long long)batch * num_frames * channels;
     dwconv1d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);

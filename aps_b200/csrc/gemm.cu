@@ -36,6 +36,9 @@ static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* 
     e.bias = d->bias; e.act = d->act; e.alpha = d->alpha;
     e.slope = d->prelu_slope; e.slope_stride = d->prelu_per_channel ? 1 : 0; e.leak = d->leaky_slope;
     e.res = d->residual; e.ldres = d->ld_residual; e.beta = d->beta;
+    e.post_scale = d->post_scale; e.post_shift = d->post_shift;
+    APSB_CHECK_ARG(!d->post_scale == !d->post_shift, "post_scale and post_shift come together");
+    APSB_CHECK_ARG(!(d->post_scale && d->act == ACT_GLU), "post affine is not available with GLU");
     e.out = out; e.ldo = ldo;
     const int ncols = d->act == ACT_GLU ? N / 2 : N;
     APSB_CHECK_ARG(ldo >= ncols, "ld_out %lld smaller than %d columns", (long long)ldo, ncols);

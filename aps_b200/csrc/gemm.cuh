@@ -27,6 +27,8 @@ struct Epilogue {
     const float* slope;    // PReLU slopes: [1] or [N] (slope_stride 0 / 1); LeakyReLU: negative slope in `leak`
     int slope_stride;
     float leak;
+    const float* post_scale;  // optional per-column affine applied right after the activation:
+    const float* post_shift;  //   v = act(.) * post_scale[n] + post_shift[n]   (eval BatchNorm behind a PReLU)
     const float* res;      // optional residual, added AFTER activation and alpha: out = v + beta * res[m, n]
     long long ldres;
     float beta;
@@ -233,7 +235,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const ALoader a, con
                 const int n = n0 + (j / HN) * (BN / 2) + tx * HN + (j % HN);
                 if (n >= N) continue;
                 float v = acc[i][j] + (e.bias ? __ldg(e.bias + n) : 0.f);
-                v = e.alpha * apply_act(v, e.act, e, n);
+                v = apply_act(v, e.act, e, n);
+                if (e.post_scale) v = fmaf(v, __ldg(e.post_scale + n), __ldg(e.post_shift + n));
+                v *= e.alpha;
                 if (e.res) v = fmaf(e.beta, __ldg(e.res + (long long)m * e.ldres + n), v);
                 e.out[(long long)m * e.ldo + n] = v;
             }

@@ -8,7 +8,7 @@ import torch as th
 from . import _lib
 
 
-def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=None, beta=1.0):
+def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=None, beta=1.0, post=None):
     e = _lib.Epilogue()
     e.bias = _lib.ptr(bias)
     e.act = _lib.ACT[act]
@@ -19,6 +19,7 @@ def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=
     e.residual = _lib.ptr(residual)
     e.ld_residual = residual.stride(0) if residual is not None else 0
     e.beta = float(beta)
+    e.post_scale, e.post_shift = (_lib.ptr(post[0]), _lib.ptr(post[1])) if post is not None else (0, 0)
     return e
 
 
@@ -30,7 +31,7 @@ def rows2d(x: th.Tensor) -> th.Tensor:
 
 def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, act: str = "none", alpha: float = 1.0,
            slope=None, leaky: float = 0.0, residual: Optional[th.Tensor] = None, beta: float = 1.0,
-           out: Optional[th.Tensor] = None) -> th.Tensor:
+           out: Optional[th.Tensor] = None, post=None) -> th.Tensor:
     """out[m, :] = alpha * act(x[m, :] @ weight.T + bias) + beta * residual[m, :]   (x: [M, K], weight: [N, K])"""
     dev = _lib.require_cuda(x, "linear input")
     M, K = x.shape
@@ -38,7 +39,7 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
     ncol = N // 2 if act == "glu" else N
     if out is None:
         out = th.empty((M, ncol), dtype=th.float32, device=dev)
-    e = _epilogue(bias, act, alpha, slope, leaky, residual, beta)
+    e = _epilogue(bias, act, alpha, slope, leaky, residual, beta, post)
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
                                                    N, e, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
@@ -80,13 +81,13 @@ def layernorm(x: th.Tensor, gamma, beta, eps: float = 1e-5, residual: Optional[t
 
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
              stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
-             residual=None) -> th.Tensor:
+             residual=None, post=None) -> th.Tensor:
     """Depthwise conv over time on token rows [N*T, D] (row(n, t) = n*stride_n + t*stride_t)."""
     dev = _lib.require_cuda(x, "dwconv input")
     D = x.shape[1]
     Kw = weight_kd.shape[0]
     out = th.empty_like(x)
-    e = _epilogue(None, act, 1.0, slope, 0.0, residual, 1.0)
+    e = _epilogue(None, act, 1.0, slope, 0.0, residual, 1.0, post)
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_dwconv1d_fwd(x.data_ptr(), x.stride(0), N, T, D,
                                                      T if stride_n is None else stride_n, stride_t,

@@ -1,0 +1,203 @@
+"""Frequency-domain Conv-TasNet (`sse@freq_tcn`) with the constructor, methods and `state_dict` layout of
+/root/reference/aps/sse/bss/tcn.py:361-469, executed by the sm_100a kernels through the C ABI.
+
+Module tree (names kept for strict checkpoint loading): `proj.1` (1x1 conv), `conv.repeat.{r}.{b}.`
+{`conv1`, `norm1.0` (PReLU), `norm1.1` (norm), `dconv`, `norm2.0`, `norm2.1`, `conv2`} with optional
+`.scale` scalars (ScaleLinear, tcn.py:91-109), `conv.skip_linear.{i}`, `mask.0` (PReLU), `mask.1`.
+
+Fused inference schedule on batch-major token rows [N*T, C] — three launches per block:
+  GEMM(1x1 conv * scale + bias, PReLU, BatchNorm affine)  ->  depthwise dilated conv (+bias, PReLU,
+  BatchNorm affine)  ->  GEMM(1x1 conv * scale + bias, + residual)
+Only `norm="BN"` (the default of the frequency-domain model) is implemented on this path.
+"""
+from typing import List, Optional, Union
+
+import torch as th
+import torch.nn as nn
+
+from ... import _lib, ops
+
+
+class ScaleLinear(nn.Conv1d):
+    """1x1 Conv1d with an optional learnt output scale (parameter container)."""
+
+    def __init__(self, in_features, out_features, bias=True, scale_param=1.0):
+        super().__init__(in_features, out_features, 1, bias=bias)
+        self.scale = nn.Parameter(th.tensor(scale_param)) if scale_param else 1
+
+    def packed(self):
+        s = self.scale.detach() if isinstance(self.scale, nn.Parameter) else 1.0
+        w = (self.weight.detach()[..., 0] * s).contiguous()
+        b = (self.bias.detach() * s).contiguous() if self.bias is not None else None
+        return w, b
+
+
+def _norm_layer(norm: str, channels: int) -> nn.Module:
+    if norm not in ("cLN", "IN", "gLN", "BN"):
+        raise RuntimeError(f"Unsupported normalize layer: {norm}")
+    if norm != "BN":
+        raise RuntimeError(f"aps_b200: normalisation '{norm}' needs per-utterance statistics over time and is not "
+                           "implemented on the fused path; use norm='BN'")
+    return nn.BatchNorm1d(channels)
+
+
+class Conv1dBlock(nn.Module):
+    """tcn.py:112-159 (parameter container)."""
+
+    def __init__(self, in_channels=256, conv_channels=512, kernel_size=3, dilation=1, norm="cLN", scale_param=0,
+                 causal=False):
+        super().__init__()
+        self.pad = dilation * (kernel_size - 1)
+        self.cau, self.dilation, self.kernel_size = causal, dilation, kernel_size
+        self.conv1 = ScaleLinear(in_channels, conv_channels, scale_param=scale_param)
+        self.norm1 = nn.Sequential(nn.PReLU(), _norm_layer(norm, conv_channels))
+        self.dconv = nn.Conv1d(conv_channels, conv_channels, kernel_size, groups=conv_channels,
+                               padding=self.pad if causal else self.pad // 2, dilation=dilation)
+        self.norm2 = nn.Sequential(nn.PReLU(), _norm_layer(norm, conv_channels))
+        self.conv2 = ScaleLinear(conv_channels, in_channels, scale_param=scale_param)
+
+
+class Conv1dRepeat(nn.Module):
+    """tcn.py:162-226 (parameter container)."""
+
+    def __init__(self, num_repeats, blocks_per_repeat, in_channels=128, conv_channels=128, kernel_size=3, norm="BN",
+                 skip_residual=True, scaling_param=False, causal=False):
+        super().__init__()
+        self.repeat = nn.Sequential(*[
+            nn.Sequential(*[
+                Conv1dBlock(in_channels=in_channels, conv_channels=conv_channels, kernel_size=kernel_size, norm=norm,
+                            causal=causal, dilation=2**n, scale_param=0 if scaling_param else 0.9**n)
+                for n in range(blocks_per_repeat)
+            ]) for _ in range(num_repeats)
+        ])
+        self.skip_residual = skip_residual
+        if skip_residual:
+            tot = num_repeats * (num_repeats - 1) // 2
+            self.skip_linear = nn.ModuleList([ScaleLinear(in_channels, in_channels, scale_param=1.0)
+                                              for _ in range(tot)])
+        else:
+            self.skip_linear = None
+
+
+class _Transpose(nn.Module):
+    def forward(self, x):
+        return x.transpose(-1, -2)
+
+
+def _bn_affine(bn: nn.BatchNorm1d):
+    scale = bn.weight.detach() / th.sqrt(bn.running_var + bn.eps)
+    return scale.contiguous(), (bn.bias.detach() - bn.running_mean * scale).contiguous()
+
+
+class FreqConvTasNet(nn.Module):
+    """Frequency domain ConvTasNet (arguments as in tcn.py:366-381)."""
+
+    def __init__(self, enh_transform: Optional[nn.Module] = None, in_features: int = 257, B: int = 6, K: int = 3,
+                 N: int = 3, conv_channels: int = 512, proj_channels: int = 256, norm: str = "BN", num_spks: int = 2,
+                 num_bins: int = 257, non_linear: str = "relu", causal: bool = False, scaling_param: bool = False,
+                 skip_residual: bool = False, training_mode: str = "freq") -> None:
+        super().__init__()
+        assert enh_transform is not None
+        assert training_mode in ("freq", "time")
+        if non_linear not in ("relu", "sigmoid"):
+            raise ValueError(f"Unsupported nonlinear: {non_linear}")
+        self.enh_transform = enh_transform
+        self.training_mode = training_mode
+        self.proj = nn.Sequential(_Transpose(), nn.Conv1d(in_features, proj_channels, 1))
+        self.conv = Conv1dRepeat(N, B, in_channels=proj_channels, conv_channels=conv_channels, kernel_size=K,
+                                 causal=causal, scaling_param=scaling_param, skip_residual=skip_residual, norm=norm)
+        self.mask = nn.Sequential(nn.PReLU(), nn.Conv1d(proj_channels, num_bins * num_spks, 1))
+        self.non_linear = non_linear
+        self.num_spks, self.num_bins = num_spks, num_bins
+        self._packs = None
+        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_packs", None))
+
+    def _apply(self, fn, *a, **k):
+        self._packs = None
+        return super()._apply(fn, *a, **k)
+
+    def _build_packs(self):
+        pk = {"blocks": [], "skip": []}
+        for rep in self.conv.repeat:
+            for blk in rep:
+                w1, b1 = blk.conv1.packed()
+                w2, b2 = blk.conv2.packed()
+                C = blk.dconv.weight.shape[0]
+                pk["blocks"].append(dict(
+                    w1=w1, b1=b1, a1=blk.norm1[0].weight.detach(), bn1=_bn_affine(blk.norm1[1]),
+                    wd=blk.dconv.weight.detach().view(C, -1).t().contiguous(), bd=blk.dconv.bias.detach(),
+                    a2=blk.norm2[0].weight.detach(), bn2=_bn_affine(blk.norm2[1]), w2=w2, b2=b2,
+                    dil=blk.dilation, lpad=blk.pad if blk.cau else blk.pad // 2))
+        if self.conv.skip_linear is not None:
+            pk["skip"] = [lin.packed() for lin in self.conv.skip_linear]
+        C = self.mask[1].in_channels
+        pk["ident"] = th.ones(1, C, device=self.mask[1].weight.device)
+        return pk
+
+    def _mask_rows(self, feats: th.Tensor) -> th.Tensor:
+        """feats N x T x F -> mask rows [N*T, num_bins*num_spks] (after the output non-linearity)."""
+        if self.training:
+            raise RuntimeError("aps_b200.FreqConvTasNet implements the inference forward only: call .eval()")
+        dev = _lib.require_cuda(feats, "mask network input")
+        if feats.dim() != 3:
+            raise RuntimeError(f"expect N x T x F features, got {feats.dim()}D")
+        if self._packs is None:
+            self._packs = self._build_packs()
+        pk = self._packs
+        N, T, Fi = feats.shape
+        rows = ops.rows2d(feats.detach().float())
+        x = ops.linear(rows, self.proj[1].weight.detach()[..., 0], self.proj[1].bias.detach())
+        outs, skip, bi = [x], 0, 0
+        nrep, nblk = len(self.conv.repeat), len(self.conv.repeat[0])
+        for r in range(nrep):
+            if self.conv.skip_residual:
+                for i in range(r):                       # in-place accumulation semantics of tcn.py:203-224
+                    w, b = pk["skip"][skip + i]
+                    x = ops.linear(outs[i], w, b, residual=x)
+                outs[r] = x
+                skip += r
+            for _ in range(nblk):
+                d = pk["blocks"][bi]
+                bi += 1
+                h = ops.linear(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=d["bn1"])
+                h = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
+                                 slope=d["a2"], post=d["bn2"])
+                x = ops.linear(h, d["w2"], d["b2"], residual=x)
+            outs.append(x)
+        # mask head: PReLU then 1x1 conv then relu / sigmoid
+        a = ops.dwconv1d(x, N, T, pk["ident"], None, act="prelu", slope=self.mask[0].weight.detach())
+        return ops.linear(a, self.mask[1].weight.detach()[..., 0], self.mask[1].bias.detach(), act=self.non_linear)
+
+    def _tf_mask(self, feats: th.Tensor, num_spks: int) -> List[th.Tensor]:
+        """[N x F x T, ...] (views of one N x T x (F*spks) buffer) — tcn.py:403-414."""
+        N, T, _ = feats.shape
+        m = self._mask_rows(feats).view(N, T, -1).transpose(1, 2)
+        return list(th.chunk(m, self.num_spks, 1))
+
+    def mask_predict(self, feats: th.Tensor) -> th.Tensor:
+        """feats N x T x F -> masks N x F x T (or S x N x F x T) — tcn.py:458-469."""
+        masks = th.stack(self._tf_mask(feats, self.num_spks))
+        return masks[0] if self.num_spks == 1 else masks
+
+    def _infer(self, mix: th.Tensor, mode: str):
+        """tcn.py:416-431: STFT -> features -> masks (-> masked STFT -> iSTFT in "time" mode)."""
+        stft, _ = self.enh_transform.encode(mix, None)
+        masks = self._tf_mask(self.enh_transform(stft), self.num_spks)
+        if mode == "time":
+            ref = stft[:, 0] if stft.dim() == 5 else stft
+            bss = self.enh_transform.decode([ref * m.unsqueeze(-1) for m in masks])   # aps/sse/base.py:23-49
+        else:
+            bss = masks
+        return bss[0] if self.num_spks == 1 else bss
+
+    def infer(self, mix: th.Tensor, mode: str = "time"):
+        if mix.dim() not in (1, 2):
+            raise RuntimeError(f"Expects 1/2D tensor (inference), got {mix.dim()} instead")
+        with th.no_grad():
+            ret = self._infer(mix[None, :], mode=mode)
+            return ret[0] if self.num_spks == 1 else [r[0] for r in ret]
+
+    def forward(self, mix: th.Tensor):
+        if mix.dim() not in (2, 3):
+            raise RuntimeError(f"Expects 2/3D tensor (training), got {mix.dim()} instead")
+        return self._infer(mix, mode=self.training_mode)

@@ -180,7 +180,8 @@ int aps_b200_beamform_fwd(const float* x_real, const float* x_imag, const int64_
                           const float* weight, float* y_real, float* y_imag, void* stream);
 
 /* Dense layers ---------------------------------------------------------------------------------
- * out[m, n] = alpha * act(sum_k x[m, k] * weight[n, k] + bias[n]) + beta * residual[m, n]
+ * out[m, n] = alpha * post(act(sum_k x[m, k] * weight[n, k] + bias[n])) + beta * residual[m, n],
+ * post(v) = v * post_scale[n] + post_shift[n] when given (an eval-mode BatchNorm behind the activation)
  * (exact fp32 accumulate).  act: 0 none, 1 relu, 2 swish, 3 tanh, 4 sigmoid, 5 prelu, 6 glu (column
  * pairs (2j, 2j+1) -> out[:, j] = v0 * sigmoid(v1)), 7 leaky relu, 8 gelu (erf).
  */
@@ -194,6 +195,8 @@ typedef struct aps_b200_epilogue {
     const float* residual;     /* [M, ld_residual] or NULL */
     int64_t ld_residual;
     float   beta;
+    const float* post_scale;   /* [N] or NULL (with post_shift) */
+    const float* post_shift;
 } aps_b200_epilogue;
 
 /* x [rows, in_features] (row stride ld_x), weight [out_features, in_features] (torch Linear layout,

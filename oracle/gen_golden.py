@@ -157,6 +157,35 @@ def main():
         arrays = dict(x=x, lens=lens, y=y, ylens=yl)
         arrays.update({"p." + k: v for k, v in net.state_dict().items()})
         save(f"enc_{i}", cfg, **arrays)
+    # ---- frequency-domain Conv-TasNet mask estimator (aps/sse/bss/tcn.py) -----------------------------------------
+    from aps.sse.bss.tcn import FreqConvTasNet
+    for i, kw in enumerate([dict(num_spks=2, non_linear="relu"),
+                            dict(num_spks=1, non_linear="sigmoid", skip_residual=True, scaling_param=True),
+                            dict(num_spks=1, non_linear="sigmoid", causal=True)]):
+        g = th.Generator().manual_seed(600 + i)
+        ekw = dict(feats="spectrogram-log-cmvn", frame_len=128, frame_hop=64)
+        nkw = dict(in_features=65, num_bins=65, B=3, N=3 if i == 1 else 2, K=3, conv_channels=24, proj_channels=16, **kw)
+        net = FreqConvTasNet(enh_transform=EnhTransform(**ekw), **nkw).eval()
+        with th.no_grad():
+            for name, buf in net.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+                if name.endswith("running_var"):
+                    buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+            for name, prm in net.named_parameters():
+                if not name.startswith("enh_transform") and prm.dim() <= 1:
+                    prm.add_(0.1 * th.randn(prm.shape, generator=g))
+        mix = wave(600 + i, 2, 2500)
+        with th.no_grad():
+            stft, _ = net.enh_transform.encode(mix, None)
+            feats = net.enh_transform(stft)
+            masks = net.mask_predict(feats)
+            net.training_mode = "time"
+            wav = net(mix)
+        wav = th.stack(wav) if isinstance(wav, list) else wav
+        arrays = dict(mix=mix, feats=feats, masks=masks, wav=wav)
+        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        save(f"tcn_{i}", dict(enh=ekw, net=nkw), **arrays)
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)
