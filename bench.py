@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--workload", default="fbank", choices=["fbank", "encoder", "mvdr_tcn", "stft_istft"],
+                    help="fbank = BASELINE configs[1] (the headline, default); the others are the remaining "
+                         "single-GPU configs, reported with the same JSON schema (N = 1 only)")
     return ap.parse_args()
 
 
@@ -161,8 +164,105 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def _time_steps(fn, steps, warmup, dev):
+    for i in range(warmup):
+        fn(i)
+    th.cuda.synchronize(dev)
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record(th.cuda.current_stream(dev))
+    for i in range(steps):
+        fn(i)
+    e1.record(th.cuda.current_stream(dev))
+    th.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
+
+
+def run_extra(args):
+    """Secondary workloads (BASELINE configs[2..3] + the STFT/iSTFT pair), one GPU, inputs resident."""
+    import copy
+    dev = th.device("cuda", 0)
+    th.cuda.set_device(dev)
+    gen = th.Generator(device=dev).manual_seed(1234)
+    peak_bw, peak_src = peaks()
+    tf_peak = 1590.0
+    try:
+        tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    sampler = ClockSampler(0)
+    R = 3
+    if args.workload == "encoder":
+        from aps_b200.asr.transformer import TransformerEncoder
+        cfg = dict(arch="cfmr", input_size=80, output_proj=-1, num_layers=12, proj="conv2d",
+                   proj_kwargs=dict(conv_channels=256, num_layers=3), pose="rel",
+                   pose_kwargs=dict(dropout=0.1, lradius=256, rradius=256),
+                   arch_kwargs=dict(att_dim=256, nhead=4, feedforward_dim=2048, att_dropout=0.1, ffn_dropout=0.1,
+                                    kernel_size=15, pre_norm=False))
+        th.manual_seed(0)
+        net = TransformerEncoder(**copy.deepcopy(cfg)).to(dev).eval()
+        B, T = 64, 398
+        xs = [th.randn(B, T, 80, device=dev, generator=gen) for _ in range(R)]
+        ms = _time_steps(lambda i: net(xs[i % R], None), args.steps, args.warmup, dev)
+        frames, launches = B * T, 12 * 14 + 5
+        flops = 6.18e9 * B                                   # SURVEY.md §8d without the vocabulary projection
+        ach = flops / (ms / args.steps * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": None, "kernel": "gemm_kernel<..> (exact-fp32 SIMT GEMM; tensor pipe idle this round)",
+                "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"}
+        wl = "conformer encoder 12L d=256 h=4 rel-pos, conv2d x3 front, forward on [64, 398, 80] fbank (configs[3])"
+    elif args.workload == "mvdr_tcn":
+        from aps_b200.asr.filter import MvdrBeamformer
+        from aps_b200.cplx import ComplexTensor
+        from aps_b200.sse.bss import FreqConvTasNet
+        from aps_b200.transform import EnhTransform
+        B, C = 64, 4
+        enh = EnhTransform(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, window="sqrthann")
+        tcn = FreqConvTasNet(enh_transform=enh, in_features=257, num_bins=257, num_spks=1, non_linear="sigmoid").to(dev).eval()
+        mvdr = MvdrBeamformer(257, att_dim=512).to(dev).eval()
+        xs = [0.1 * th.randn(B, C, S, device=dev, generator=gen) for _ in range(R)]
+
+        def step(i):
+            packed, _ = tcn.enh_transform.encode(xs[i % R], None)
+            mask = tcn.mask_predict(tcn.enh_transform(packed))
+            return mvdr(mask.transpose(1, 2), ComplexTensor(packed[..., 0], packed[..., 1]))
+
+        ms = _time_steps(step, args.steps, args.warmup, dev)
+        frames, launches = B * (S // HOP), 1 + 1 + 56 + 5
+        bytes_ = B * (C * S * 4 + C * 257 * 249 * 8 + 2056 * 249 + 8.96e6)   # STFT + feats + MVDR (SURVEY §8d)
+        ach = bytes_ / (ms / args.steps * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw, "traffic": None,
+                "kernel": "whole step (4-ch STFT, ref-channel feats, freq-TCN GEMMs, covar, solve, beamform); "
+                          "the TCN GEMMs (2.43 GFLOP/utt, fp32 SIMT) dominate the time",
+                "algorithmic_bytes_per_step": bytes_, "peak_source": peak_src}
+        wl = "4-ch STFT + freq-TCN sigmoid mask + MVDR, B=64 x 4 s (configs[2]); value in 10 ms frames/s"
+    else:
+        from aps_b200.transform.utils import STFT, iSTFT
+        B = 128
+        kw = dict(frame_len=512, frame_hop=256, window="sqrthann", center=True)
+        f, g = STFT(**kw).to(dev), iSTFT(**kw).to(dev)
+        xs = [0.1 * th.randn(B, S, device=dev, generator=gen) for _ in range(R)]
+        ms = _time_steps(lambda i: g(f(xs[i % R])), args.steps, args.warmup, dev)
+        frames, launches = B * (S // HOP), 2
+        bytes_ = 2 * 3080.0 * B * 251
+        ach = bytes_ / (ms / args.steps * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw, "traffic": None,
+                "kernel": "frontend_kernel<256,1,1> + istft_kernel<256>", "algorithmic_bytes_per_step": bytes_,
+                "peak_source": peak_src}
+        wl = "STFT -> iSTFT round trip 512/256 center, B=128 x 4 s (the transform pair of configs[4]); 10 ms frames/s"
+    clocks = sampler.stop()
+    print(json.dumps({
+        "metric": "frames/sec", "value": frames * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "l2": f"{R} distinct resident input batches rotate"},
+        "roofline": roof, "cpu_baseline": None, "e2e": None, "gpu_launches": launches * (args.steps + args.warmup),
+        "clocks": clocks}), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload != "fbank":
+        return run_extra(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
