@@ -88,6 +88,11 @@ _SIGNATURES = {
     "aps_b200_conv2d_nhwc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Epilogue), c_void_p,
                                          c_void_p]),
+    "aps_b200_conv_transpose2d_nhwc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                   POINTER(Epilogue), c_void_p, c_void_p]),
+    "aps_b200_cmask_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_float, c_int,
+                                   c_void_p, c_void_p]),
     "aps_b200_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_float,
                                        c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "aps_b200_dwconv1d_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,

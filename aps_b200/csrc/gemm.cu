@@ -87,3 +87,29 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
     a.vec = (((uintptr_t)x & 15) == 0 && (in_channels & 3) == 0) ? 1 : 0;
     return launch_gemm(a, weight, K, (int)M, ncols, (int)K, e, (cudaStream_t)stream);
 }
+
+extern "C" int aps_b200_conv_transpose2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                                  int64_t in_channels, const float* weight, int64_t out_channels,
+                                                  int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,
+                                                  int pad_w, int out_pad_h, int out_pad_w,
+                                                  const aps_b200_epilogue* epi, float* out, void* stream) {
+    APSB_CHECK_ARG(x && weight, "null pointer argument");
+    APSB_CHECK_ARG(batch > 0 && height > 0 && width > 0 && in_channels > 0 && out_channels > 0, "bad shape");
+    APSB_CHECK_ARG(kernel_h > 0 && kernel_w > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0 &&
+                       out_pad_h >= 0 && out_pad_w >= 0, "bad convolution geometry");
+    const int64_t OH = (height - 1) * stride_h - 2 * pad_h + kernel_h + out_pad_h;
+    const int64_t OW = (width - 1) * stride_w - 2 * pad_w + kernel_w + out_pad_w;
+    APSB_CHECK_ARG(OH > 0 && OW > 0, "transposed convolution output is empty");
+    const int64_t M = batch * OH * OW, K = (int64_t)kernel_h * kernel_w * in_channels;
+    APSB_CHECK_ARG(M < (1LL << 31) && K < (1LL << 31), "shape too large");
+    Epilogue e{};
+    const int ncols = (int)out_channels;
+    if (int rc = fill_epilogue(e, epi, ncols, out, ncols)) return rc;
+    APSB_CHECK_ARG(epi->act != ACT_GLU, "GLU is not available here");
+    TConvA a{};
+    a.x = x; a.Nb = (int)batch; a.H = (int)height; a.W = (int)width; a.Cin = (int)in_channels;
+    a.KH = kernel_h; a.KW = kernel_w; a.sh = stride_h; a.sw = stride_w; a.ph = pad_h; a.pw = pad_w;
+    a.OH = (int)OH; a.OW = (int)OW; a.M = (int)M; a.K = (int)K;
+    a.vec = (((uintptr_t)x & 15) == 0 && (in_channels & 3) == 0) ? 1 : 0;
+    return launch_gemm(a, weight, K, (int)M, ncols, (int)K, e, (cudaStream_t)stream);
+}

@@ -114,6 +114,51 @@ struct ConvA {
     }
 };
 
+// implicit gather of a TRANSPOSED convolution: out[oh, ow] = sum x[ih, iw] w[kh, kw] over oh = ih*sh - ph + kh
+struct TConvA {
+    const float* x;
+    int Nb, H, W, Cin, KH, KW, sh, sw, ph, pw, OH, OW;
+    int M, K;
+    int vec;
+    struct Row { int nb, oh, ow; bool ok; };
+    __device__ __forceinline__ Row row(int m) const {
+        Row r;
+        r.ok = m < M;
+        const int mm = r.ok ? m : 0;
+        r.ow = mm % OW;
+        const int t = mm / OW;
+        r.oh = t % OH;
+        r.nb = t / OH;
+        return r;
+    }
+    __device__ __forceinline__ const float* src(const Row& r, int k) const {
+        const int c = k % Cin, t = k / Cin;
+        const int kw = t % KW, kh = t / KW;
+        const int nh = r.oh + ph - kh, nw = r.ow + pw - kw;
+        if (nh < 0 || nw < 0 || nh % sh || nw % sw) return nullptr;
+        const int ih = nh / sh, iw = nw / sw;
+        if (ih >= H || iw >= W) return nullptr;
+        return x + (((long long)r.nb * H + ih) * W + iw) * Cin + c;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!r.ok) return v;
+        if (vec) {
+            if (k >= K) return v;
+            const float* p = src(r, k);
+            return p ? __ldg(reinterpret_cast<const float4*>(p)) : v;
+        }
+        float* o = &v.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (k + i < K) {
+                const float* p = src(r, k + i);
+                o[i] = p ? __ldg(p) : 0.f;
+            }
+        return v;
+    }
+};
+
 constexpr int kGemmThreads = 256;
 constexpr int kBK = 16;
 

@@ -121,6 +121,28 @@ __global__ void __launch_bounds__(256) ipd_kernel(const __grid_constant__ IpdPar
     }
 }
 
+// complex ratio mask (dccrn.py:217-232): m = (mr, mi) -> |m| -> g(|m|) m/|m|, optionally applied to the STFT
+__global__ void __launch_bounds__(256) cmask_kernel(const float* __restrict__ m, long long ldm, int col_r, int col_i,
+                                                    const float* __restrict__ stft, long long total, int act,
+                                                    float eps, int apply, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float mr = __ldg(m + i * ldm + col_r), mi = __ldg(m + i * ldm + col_i);
+    const float a = sqrtf(mr * mr + mi * mi + eps);
+    float g = a;
+    if (act == 4) g = 1.f / (1.f + expf(-a));
+    else if (act == 3) g = tanhf(a);
+    else if (act == 1) g = fmaxf(a, 0.f);
+    mr = g * mr / a;
+    mi = g * mi / a;
+    float2 o = make_float2(mr, mi);
+    if (apply) {
+        const float2 s = __ldg(reinterpret_cast<const float2*>(stft) + i);
+        o = make_float2(s.x * mr - s.y * mi, s.x * mi + s.y * mr);
+    }
+    reinterpret_cast<float2*>(out)[i] = o;
+}
+
 template <int FI>
 static int launch_specfeat(SpecFeatParams& p, cudaStream_t st) {
     auto kern = specfeat_kernel<FI>;
@@ -181,6 +203,17 @@ extern "C" int aps_b200_ipd_fwd(const float* spec, int64_t batch, int64_t channe
     p.ld_out = (int)ld_out; p.col0 = (int)col0;
     dim3 grid((p.T + 31) / 32, (p.F + 31) / 32, (unsigned)(batch * num_pairs));
     ipd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int aps_b200_cmask_fwd(const float* mask, int64_t ld_mask, int64_t col_real, int64_t col_imag,
+                                  const float* stft, int64_t positions, int act, float eps, int apply, float* out,
+                                  void* stream) {
+    APSB_CHECK_ARG(mask && out && positions > 0 && (!apply || stft), "bad arguments");
+    APSB_CHECK_ARG(act == 0 || act == 1 || act == 3 || act == 4, "mask non-linearity must be none/relu/tanh/sigmoid");
+    cmask_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        mask, ld_mask, (int)col_real, (int)col_imag, stft, positions, act, eps, apply, out);
     APSB_LAUNCH_CHECK();
     return 0;
 }

@@ -65,6 +65,36 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
     return out
 
 
+def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0),
+                          output_padding=(0, 0), act: str = "none", leaky: float = 0.0) -> th.Tensor:
+    """x [B, H, W, Cin], weight [Cout, KH, KW, Cin] -> [B, OH, OW, Cout] (transposed convolution)."""
+    dev = _lib.require_cuda(x, "conv input")
+    B, H, W, Cin = x.shape
+    Cout, KH, KW, _ = weight.shape
+    OH = (H - 1) * stride[0] - 2 * padding[0] + KH + output_padding[0]
+    OW = (W - 1) * stride[1] - 2 * padding[1] + KW + output_padding[1]
+    out = th.empty((B, OH, OW, Cout), dtype=th.float32, device=dev)
+    e = _epilogue(bias, act, 1.0, None, leaky)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_fwd(
+            x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW, stride[0], stride[1], padding[0], padding[1],
+            output_padding[0], output_padding[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
+    return out
+
+
+def cmask(mask: th.Tensor, col_real: int, col_imag: int, stft: Optional[th.Tensor], act: str, eps: float,
+          apply: bool) -> th.Tensor:
+    """Complex ratio mask from channels (col_real, col_imag) of mask [..., C]; returns [..., 2]."""
+    dev = _lib.require_cuda(mask, "mask")
+    pos = mask.numel() // mask.shape[-1]
+    out = th.empty(mask.shape[:-1] + (2,), dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_cmask_fwd(mask.data_ptr(), mask.shape[-1], col_real, col_imag, _lib.ptr(stft),
+                                                  pos, _lib.ACT[act], float(eps), int(apply), out.data_ptr(),
+                                                  _lib.stream_ptr(dev)))
+    return out
+
+
 def layernorm(x: th.Tensor, gamma, beta, eps: float = 1e-5, residual: Optional[th.Tensor] = None,
               alpha: float = 1.0) -> th.Tensor:
     """LayerNorm(alpha * x + residual) over the last axis of [M, D] rows."""

@@ -217,6 +217,25 @@ int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int6
                              int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
                              float* out, void* stream);
 
+/* Transposed convolution, channels-last: x [B, H, W, Cin], weight [Cout, KH, KW, Cin] (i.e. the torch
+ * ConvTranspose2d weight [Cin, Cout, KH, KW] permuted), out [B, OH, OW, Cout] with
+ * OH = (H-1)*stride - 2*pad + K + out_pad.  Replaces the nn.ConvTranspose2d pairs of
+ * aps/sse/enh/dcunet.py:48-69 (ComplexConvTranspose2d, as one real transposed convolution on stacked
+ * real/imaginary channels).                                                                   */
+int aps_b200_conv_transpose2d_nhwc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                       int64_t in_channels, const float* weight, int64_t out_channels,
+                                       int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                       int pad_h, int pad_w, int out_pad_h, int out_pad_w,
+                                       const aps_b200_epilogue* epi, float* out, void* stream);
+
+/* Complex ratio mask: per position p, (mr, mi) = mask[p*ld_mask + col_real|col_imag];
+ * a = sqrt(mr^2 + mi^2 + eps); g = act(a) (0 none, 1 relu, 3 tanh, 4 sigmoid); m' = g*m/a;
+ * out[p] = m' (apply = 0) or stft[p] * m' (complex product, apply = 1); out / stft are [positions, 2].
+ * Replaces aps/sse/bss/dccrn.py:223-231 (_sep, cplx=True).                                    */
+int aps_b200_cmask_fwd(const float* mask, int64_t ld_mask, int64_t col_real, int64_t col_imag,
+                       const float* stft, int64_t positions, int act, float eps, int apply, float* out,
+                       void* stream);
+
 /* Encoder (non-GEMM) kernels ---------------------------------------------------------------------
  * Activations are token-major rows; row(n, t) = n*stride_n + t*stride_t.
  */

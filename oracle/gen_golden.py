@@ -184,8 +184,31 @@ def main():
             wav = net(mix)
         wav = th.stack(wav) if isinstance(wav, list) else wav
         arrays = dict(mix=mix, feats=feats, masks=masks, wav=wav)
-        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})
         save(f"tcn_{i}", dict(enh=ekw, net=nkw), **arrays)
+    # ---- DCCRN (aps/sse/bss/dccrn.py), the configuration pinned by the reference's tests -------------------------
+    from aps.sse.bss.dccrn import DCCRN
+    for i, (spk, conn, nl, C) in enumerate([(1, "cat", "sigmoid", "4,8,8,8,16,16,32"), (2, "cat", "tanh", "4,8,8,8,16,16,32")]):
+        g = th.Generator().manual_seed(700 + i)
+        ekw = dict(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, center=True)
+        nkw = dict(cplx=True, K="3,3;3,3;3,3;3,3;3,3;3,3;3,3", S="2,1;2,1;2,1;2,1;2,1;2,1;2,1", P="1,1,1,1,1,0,0",
+                   O="0,0,0,0,0,0,1", C=C, num_spks=spk, rnn_resize=64, rnn_hidden=40, non_linear=nl, connection=conn)
+        net = DCCRN(enh_transform=EnhTransform(**ekw), **nkw).eval()
+        with th.no_grad():
+            for name, buf in net.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+                if name.endswith("running_var"):
+                    buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+        mix = wave(700 + i, 2, 6000, kind="rand")
+        with th.no_grad():
+            wav = net(mix)
+            net.training_mode = "freq"
+            msk = net(mix)
+        stack = lambda v: th.stack(v) if isinstance(v, list) else v
+        arrays = dict(mix=mix, wav=stack(wav), masks=stack(msk))
+        arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})  # K: 2 MB each
+        save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)

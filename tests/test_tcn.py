@@ -32,7 +32,9 @@ def _net(cfg, g):
     from aps_b200.sse.bss import FreqConvTasNet
     from aps_b200.transform import EnhTransform
     net = FreqConvTasNet(enh_transform=EnhTransform(**cfg["enh"]), **cfg["net"])
-    net.load_state_dict(_sd(g), strict=True)
+    sd = _sd(g)
+    sd.update({k: v for k, v in net.state_dict().items() if k.endswith(".K") and k not in sd})   # DFT matrices are not stored
+    net.load_state_dict(sd, strict=True)
     return net
 
 
