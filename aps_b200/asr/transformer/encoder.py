@@ -20,6 +20,7 @@ Inference only (`eval()`): train-mode BatchNorm statistics / dropout / autograd 
 forward hot path this package covers.
 """
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch as th
@@ -319,14 +320,22 @@ class TransformerEncoder(nn.Module):
         self.outp = nn.Linear(att_dim, output_proj) if output_proj > 0 else None
         self.att_dim, self.nhead = att_dim, arch_kwargs["nhead"]
         self._packs = None
+        self._splits = ops.SplitCache()
+        self._graphs = {}
+        self.use_graphs = os.environ.get("APS_B200_GRAPHS", "1") != "0"
         self.register_load_state_dict_post_hook(lambda m, k: m._drop_packs())
 
     # ---- repacked weights (BatchNorm folding, layout changes); rebuilt after load_state_dict / .to() ------
     def _drop_packs(self):
         self._packs = None
+        self._splits.clear()
+        self._graphs.clear()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
+        if hasattr(self, "_splits"):
+            self._splits.clear()
+            self._graphs.clear()
         return super()._apply(fn, *a, **k)
 
     @staticmethod
@@ -338,6 +347,13 @@ class TransformerEncoder(nn.Module):
 
     def _build_packs(self, dev):
         pk = {"dev": dev, "layers": []}
+        if isinstance(self.proj, LinearProj):
+            nrm = self.proj.norm.norm
+            if not isinstance(nrm, nn.BatchNorm1d):
+                raise RuntimeError("aps_b200: LinearProj(norm='LN') (a GroupNorm over time) is not implemented; "
+                                   "use norm='BN'")
+            w, b = self._fold_bn(self.proj.proj.weight, self.proj.proj.bias, nrm)
+            pk["lin_w"], pk["lin_b"] = w.contiguous(), b.contiguous()
         if isinstance(self.proj, Conv2dProj):
             convs = []
             for blk in self.proj.conv.enc_layers:
@@ -369,50 +385,52 @@ class TransformerEncoder(nn.Module):
             pk["layers"].append(d)
         return pk
 
+    def _lin(self, x, w, b=None, **kw):
+        return ops.linear(x, w, b, cache=self._splits, **kw)
+
     # ---- pieces ---------------------------------------------------------------------------------------------
-    def _front(self, x: th.Tensor, lens: Optional[th.Tensor], pk):
+    def _front_lens(self, lens: Optional[th.Tensor]) -> Optional[th.Tensor]:
+        """Lengths after the projection front (integer exact, the reference's own rule)."""
+        if lens is not None and isinstance(self.proj, Conv2dProj):
+            for blk in self.proj.conv.enc_layers:
+                lens = blk.compute_outp_dim(lens, 0)
+        return lens
+
+    def _front(self, x: th.Tensor, pk):
         if self.proj is None:
-            return x, lens
+            return x
         if isinstance(self.proj, LinearProj):
-            nrm = self.proj.norm.norm
-            if not isinstance(nrm, nn.BatchNorm1d):
-                raise RuntimeError("aps_b200: LinearProj(norm='LN') (a GroupNorm over time) is not implemented; "
-                                   "use norm='BN'")
             N, T, Fi = x.shape
-            w, b = self._fold_bn(self.proj.proj.weight, self.proj.proj.bias, nrm)
-            y = ops.linear(ops.rows2d(x), w.contiguous(), b.contiguous(), act="relu")
-            return y.view(N, T, -1), lens
+            y = self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"], act="relu")
+            return y.view(N, T, -1)
         x4 = x[:, None] if x.dim() == 3 else x                      # N x C x T x F
         nhwc = x4.permute(0, 2, 3, 1).contiguous()
         for (w, b, stride, padding), blk in zip(pk["convs"], self.proj.conv.enc_layers):
             nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu")
-            if lens is not None:
-                lens = blk.compute_outp_dim(lens, 0)
         N, T, Fq, C = nhwc.shape
         flat = nhwc.view(N * T, Fq * C)
         if "front_w" in pk:
-            flat = ops.linear(flat, pk["front_w"], pk["front_b"])
+            flat = self._lin(flat, pk["front_w"], pk["front_b"])
         else:   # no output projection: restore the reference's channel-major feature order
             flat = nhwc.permute(0, 1, 3, 2).reshape(N * T, C * Fq)
-        return flat.view(N, T, -1), lens
+        return flat.view(N, T, -1)
 
     def _attention(self, a, x, res, N, T, inj, kpm, amask):
         """res + SelfAttention(x) with the parameters of container `a`."""
-        qkv = ops.linear(x, a.in_proj_weight.detach(), a.in_proj_bias.detach())
+        qkv = self._lin(x, a.in_proj_weight.detach(), a.in_proj_bias.detach())
         if self.pose_type == "rel":
             ctx = ops.mhsa(qkv, N, T, self.nhead, mode=1, pos=inj, kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask)
         elif self.pose_type == "xl":
-            pos = ops.linear(inj, a.rel_proj.weight.detach())
+            pos = self._lin(inj, a.rel_proj.weight.detach())
             ctx = ops.mhsa(qkv, N, T, self.nhead, mode=2, pos=pos, rel_u=a.rel_u.detach().contiguous(),
                            rel_v=a.rel_v.detach().contiguous(), kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask,
                            qpos_is_value=True)
         else:
             ctx = ops.mhsa(qkv, N, T, self.nhead, mode=0, kpm=kpm, kpm_fill=float("-inf"), attn_mask=amask)
-        return ops.linear(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach(), residual=res)
+        return self._lin(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach(), residual=res)
 
-    @staticmethod
-    def _ffn_out(seq, x, act):
-        h = ops.linear(x, seq[0].weight.detach(), seq[0].bias.detach(), act=act)
+    def _ffn_out(self, seq, x, act):
+        h = self._lin(x, seq[0].weight.detach(), seq[0].bias.detach(), act=act)
         return h, seq[3]
 
     @staticmethod
@@ -424,62 +442,50 @@ class TransformerEncoder(nn.Module):
         if lay.pre_norm:
             x = self._attention(lay.self_attn, self._ln(lay.norm1, x), x, N, T, inj, kpm, amask)
             h, l2 = self._ffn_out(lay.feedforward, self._ln(lay.norm2, x), act)
-            return ops.linear(h, l2.weight.detach(), l2.bias.detach(), residual=x)
+            return self._lin(h, l2.weight.detach(), l2.bias.detach(), residual=x)
         x = self._ln(lay.norm1, self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask))
         h, l2 = self._ffn_out(lay.feedforward, x, act)
-        return self._ln(lay.norm2, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x)
+        return self._ln(lay.norm2, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x)
 
     def _conv_module(self, lay, d, u, x, N, T):
-        g = ops.linear(u, d["pw1_w"], d["pw1_b"], act="glu")
+        g = self._lin(u, d["pw1_w"], d["pw1_b"], act="glu")
         K = lay.kernel_size
         c = ops.dwconv1d(g, N, T, d["dw_w"], d["dw_b"], dilation=1, left_pad=(K - 1) if lay.padding else (K - 1) // 2,
                          act=lay.activation)
-        return ops.linear(c, d["pw2_w"], d["pw2_b"], residual=x)                # conv(u) + x
+        return self._lin(c, d["pw2_w"], d["pw2_b"], residual=x)                # conv(u) + x
 
     def _cfmr_layer(self, lay, d, x, N, T, inj, kpm, amask):
         act, mac = lay.activation, lay.macaron_factor
         if lay.feedforward1 is not None:
             if lay.pre_norm:
                 h, l2 = self._ffn_out(lay.feedforward1, self._ln(lay.norm_ffn1, x), act)
-                x = ops.linear(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
+                x = self._lin(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
             else:
                 h, l2 = self._ffn_out(lay.feedforward1, x, act)
-                x = self._ln(lay.norm_ffn1, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
+                x = self._ln(lay.norm_ffn1, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
         if lay.pre_norm:
             x = self._attention(lay.self_attn, self._ln(lay.norm_attn, x), x, N, T, inj, kpm, amask)
             x = self._conv_module(lay, d, self._ln(lay.norm_conv, x), x, N, T)
             h, l2 = self._ffn_out(lay.feedforward2, self._ln(lay.norm_ffn2, x), act)
-            return ops.linear(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
+            return self._lin(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
         x = self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask)
         x = self._conv_module(lay, d, self._ln(lay.norm_attn, x), x, N, T)       # impl.py:536 reuses norm_attn
         x = self._ln(lay.norm_conv, x)
         h, l2 = self._ffn_out(lay.feedforward2, x, act)
-        return self._ln(lay.norm_ffn2, ops.linear(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
+        return self._ln(lay.norm_ffn2, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
 
     # ---- forward --------------------------------------------------------------------------------------------
-    def forward(self, inp_pad: th.Tensor, inp_len: Optional[th.Tensor]):
-        """inp_pad N x Ti x F (or N x C x Ti x F), inp_len N or None -> (N x To x D, lengths)."""
-        if self.training:
-            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
-        dev = _lib.require_cuda(inp_pad, "encoder input")
-        if self._packs is None or self._packs["dev"] != dev:
-            if next(self.parameters()).device != dev:
-                raise RuntimeError(f"encoder parameters on {next(self.parameters()).device}, input on {dev}")
-            self._packs = self._build_packs(dev)
-        pk = self._packs
-        x = inp_pad.detach().float()
-        x, inp_len = self._front(x, inp_len, pk)
+    def _run(self, x: th.Tensor, lens_dev: Optional[th.Tensor]) -> th.Tensor:
+        """Device-only part of the forward (safe to capture in a CUDA graph): x N x Ti x F -> N x To x D."""
+        pk, dev = self._packs, x.device
+        x = self._front(x, pk)
         N, T, D = x.shape
         kpm = None
-        if inp_len is not None:
-            steps = th.arange(int(inp_len.max()), device=dev)
-            if steps.numel() != T:
-                raise RuntimeError(f"padding mask length {steps.numel()} does not match {T} encoder frames")
-            kpm = (steps[None, :] >= inp_len.to(dev)[:, None]).to(th.uint8).contiguous()
+        if lens_dev is not None:
+            kpm = (th.arange(T, device=dev)[None, :] >= lens_dev[:, None]).to(th.uint8).contiguous()
         inj = None
         if self.pose_type == "abs":
-            enc = self.pose.encode(th.arange(0, T, 1.0, device=dev))
-            x = x * self.pose.factor + enc
+            x = x * self.pose.factor + self.pose.encode(th.arange(0, T, 1.0, device=dev))
         elif self.pose_type == "rel":
             inj = self.pose.encode(th.arange(-T + 1, T, device=dev)).contiguous()
         else:
@@ -496,5 +502,58 @@ class TransformerEncoder(nn.Module):
         if self.encoder.norm is not None:
             rows = self._ln(self.encoder.norm, rows)
         if self.outp is not None:
-            rows = ops.linear(rows, self.outp.weight.detach(), self.outp.bias.detach())
-        return rows.view(N, T, -1), inp_len
+            rows = self._lin(rows, self.outp.weight.detach(), self.outp.bias.detach())
+        return rows.view(N, T, -1)
+
+    def _run_graphed(self, x: th.Tensor, lens_dev: Optional[th.Tensor]) -> th.Tensor:
+        """Replay a captured CUDA graph of `_run` once an input shape has been seen twice (the ~180 launches
+        of a 12-layer forward otherwise cost more host time than device time at M = 3200 tokens)."""
+        key = (tuple(x.shape), lens_dev is not None)
+        state = self._graphs.get(key)
+        if state is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            self._graphs[key] = "seen"
+            return self._run(x, lens_dev)
+        if state == "seen":
+            sx = x.clone()
+            sl = lens_dev.clone() if lens_dev is not None else None
+            graph = th.cuda.CUDAGraph()
+            th.cuda.synchronize(x.device)
+            try:
+                with th.cuda.graph(graph):
+                    out = self._run(sx, sl)
+            except Exception:
+                self.use_graphs = False
+                self._graphs.clear()
+                raise
+            state = self._graphs[key] = (graph, sx, sl, out)
+        graph, sx, sl, out = state
+        sx.copy_(x)
+        if sl is not None:
+            sl.copy_(lens_dev)
+        graph.replay()
+        return out.clone()
+
+    def forward(self, inp_pad: th.Tensor, inp_len: Optional[th.Tensor]):
+        """inp_pad N x Ti x F (or N x C x Ti x F), inp_len N or None -> (N x To x D, lengths)."""
+        if self.training:
+            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
+        dev = _lib.require_cuda(inp_pad, "encoder input")
+        if self._packs is None or self._packs["dev"] != dev:
+            if next(self.parameters()).device != dev:
+                raise RuntimeError(f"encoder parameters on {next(self.parameters()).device}, input on {dev}")
+            self._packs = self._build_packs(dev)
+            self._graphs.clear()
+        x = inp_pad.detach().float()
+        out_len = self._front_lens(inp_len)
+        lens_dev = None
+        if out_len is not None:
+            lens_dev = out_len.detach().to(device=dev, dtype=th.int64)
+        if self.use_graphs and not th.cuda.is_current_stream_capturing():
+            out = self._run_graphed(x.contiguous(), lens_dev)
+        else:
+            out = self._run(x, lens_dev)
+        if out_len is not None and int(out_len.max()) != out.shape[1]:
+            raise RuntimeError(f"padding mask length {int(out_len.max())} does not match {out.shape[1]} encoder frames")
+        return out, out_len

@@ -23,6 +23,45 @@ def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=
     return e
 
 
+import os
+
+# GEMM engine of `linear`: "tc" = tcgen05 3xTF32 tensor-core kernel when the shape allows it, "simt" = exact fp32
+GEMM_ENGINE = os.environ.get("APS_B200_GEMM", "simt")
+
+
+def tf32_split(x: th.Tensor):
+    """(hi, lo) = (rn_tf32(x), rn_tf32(x - hi)) for a [rows, cols] matrix with 16-byte aligned rows."""
+    dev = x.device
+    buf = th.empty((2, x.shape[0], x.shape[1]), dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_tf32_split(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), buf[0].data_ptr(),
+                                                   buf[1].data_ptr(), buf.stride(1), _lib.stream_ptr(dev)))
+    return buf[0], buf[1]
+
+
+class SplitCache:
+    """Per-module cache of TF32 hi/lo splits of weight tensors.  It keeps a reference to every cached weight
+    (so its address cannot be recycled under the cache) and re-splits when the tensor was modified in place."""
+
+    def __init__(self):
+        self._items = {}
+
+    def get(self, w: th.Tensor):
+        key = (w.data_ptr(), tuple(w.shape), w.stride(0))
+        hit = self._items.get(key)
+        if hit is None or hit[1] != w._version:
+            hit = self._items[key] = (w, w._version, tf32_split(w))
+        return hit[2]
+
+    def clear(self):
+        self._items.clear()
+
+
+def _tc_ok(x: th.Tensor, w: th.Tensor, M: int, K: int, N: int) -> bool:
+    return (GEMM_ENGINE == "tc" and K % 4 == 0 and K >= 32 and M >= 64 and N >= 32 and x.stride(0) % 4 == 0
+            and w.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and w.stride(1) == 1)
+
+
 def rows2d(x: th.Tensor) -> th.Tensor:
     """View `x` as [rows, cols] with unit column stride (copies only if it has to)."""
     x = x.reshape(-1, x.shape[-1])
@@ -31,7 +70,7 @@ def rows2d(x: th.Tensor) -> th.Tensor:
 
 def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, act: str = "none", alpha: float = 1.0,
            slope=None, leaky: float = 0.0, residual: Optional[th.Tensor] = None, beta: float = 1.0,
-           out: Optional[th.Tensor] = None, post=None) -> th.Tensor:
+           out: Optional[th.Tensor] = None, post=None, cache: Optional["SplitCache"] = None) -> th.Tensor:
     """out[m, :] = alpha * act(x[m, :] @ weight.T + bias) + beta * residual[m, :]   (x: [M, K], weight: [N, K])"""
     dev = _lib.require_cuda(x, "linear input")
     M, K = x.shape
@@ -40,6 +79,13 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
     if out is None:
         out = th.empty((M, ncol), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, alpha, slope, leaky, residual, beta, post)
+    if _tc_ok(x, weight, M, K, N):
+        (x_hi, x_lo), (w_hi, w_lo) = tf32_split(x), (cache.get(weight) if cache is not None else tf32_split(weight))
+        with th.cuda.device(dev):
+            _lib.check(_lib.load().aps_b200_linear_tc_fwd(x_hi.data_ptr(), x_lo.data_ptr(), M, K, x_hi.stride(0),
+                                                          w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e,
+                                                          out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
+        return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
                                                    N, e, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))

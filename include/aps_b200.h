@@ -206,6 +206,18 @@ int aps_b200_linear_fwd(const float* x, int64_t rows, int64_t in_features, int64
                         const float* weight, int64_t ld_w, int64_t out_features,
                         const aps_b200_epilogue* epi, float* out, int64_t ld_out, void* stream);
 
+/* Tensor-core variant of aps_b200_linear_fwd (tcgen05.mma kind::tf32, accumulators in TMEM, operands
+ * by TMA) with a 3xTF32 split: both operands are given as hi = rn_tf32(v) and lo = rn_tf32(v - hi)
+ * (aps_b200_tf32_split; weights once, activations per call) and hi*hi + hi*lo + lo*hi is accumulated
+ * in fp32.  Needs in_features % 4 == 0 and 16-byte aligned rows; hi and lo share the row stride.
+ * Same epilogue contract as aps_b200_linear_fwd.                                              */
+int aps_b200_tf32_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo,
+                        int64_t ld_out, void* stream);
+int aps_b200_linear_tc_fwd(const float* x_hi, const float* x_lo, int64_t rows, int64_t in_features,
+                           int64_t ld_x, const float* weight_hi, const float* weight_lo, int64_t ld_w,
+                           int64_t out_features, const aps_b200_epilogue* epi, float* out,
+                           int64_t ld_out, void* stream);
+
 /* Implicit-GEMM convolution on channels-last data: x [B, H, W, Cin], weight [Cout, KH, KW, Cin],
  * out [B, OH, OW, Cout] with OH = (H + 2 pad - dil (K-1) - 1) / stride + 1.  Replaces the
  * Conv2d(+BatchNorm eval, folded by the caller)+ReLU block of aps/asr/base/component.py:251-307 and

@@ -82,6 +82,47 @@ def test_encoder_golden_gpu(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["enc_0", "enc_3", "enc_4"])
+def test_encoder_tensor_core_engine_and_graph_replay(name, monkeypatch):
+    """Same goldens through the tcgen05 3xTF32 GEMM engine, and three calls with one shape so that the third
+    is a CUDA-graph replay (must reproduce the eager result)."""
+    from aps_b200 import ops
+    from aps_b200.asr.transformer import TransformerEncoder
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    cfg, g = load_golden(name)
+    net = TransformerEncoder(**copy.deepcopy(cfg))
+    net.load_state_dict(_sd(g), strict=True)
+    net = net.to(DEV).eval()
+    outs = [net(g["x"].to(DEV), g["lens"].to(DEV))[0] for _ in range(3)]
+    assert rel_err(outs[0], g["y"]) < FLOAT_TOL
+    assert rel_err(outs[2], outs[0]) < 1e-6 and len(net._graphs) == 1 and isinstance(list(net._graphs.values())[0], tuple)
+    # a different batch through the replayed graph
+    x2 = th.flip(g["x"], [0])
+    l2 = th.flip(g["lens"], [0])
+    y2, _ = net(x2.to(DEV), l2.to(DEV))
+    o2, _ = EncoderOracle(cfg, _sd(g))(x2, l2.clone())
+    assert rel_err(y2, o2) < FLOAT_TOL
+
+
+@pytest.mark.gpu
+def test_tensor_core_gemm_vs_fp64():
+    """tcgen05 3xTF32 GEMM: error against fp64 must stay at the fp32 level (well below TF32's 1e-3)."""
+    from aps_b200 import ops
+    th.manual_seed(2)
+    for (M, K, N) in ((128, 32, 64), (3200, 256, 2048), (3200, 2048, 256), (333, 96, 200), (700, 2304, 256)):
+        x, w, b = th.randn(M, K, device=DEV), th.randn(N, K, device=DEV) / K**0.5, th.randn(N, device=DEV)
+        ref = x.double() @ w.double().t() + b.double()
+        old = ops.GEMM_ENGINE
+        try:
+            ops.GEMM_ENGINE = "tc"
+            y = ops.linear(x, w, b)
+        finally:
+            ops.GEMM_ENGINE = old
+        # the TMEM accumulator rounds toward zero: the error grows ~K/8 * 2^-24 (1.2e-5 at K = 2048), far below TF32's 1e-3
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) < 3e-5, (M, K, N)
+
+
+@pytest.mark.gpu
 def test_dense_kernels_vs_torch():
     """GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the CPU."""
     import torch.nn.functional as F
