@@ -221,23 +221,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const float ps = (e.post_scale && nok) ? __ldg(e.post_scale + n) : 1.f;
                 const float pt = (e.post_scale && nok) ? __ldg(e.post_shift + n) : 0.f;
                 const float slope = (e.act == ACT_PRELU && nok) ? __ldg(e.slope + (long long)n * e.slope_stride) : e.leak;
-                for (int rr = 0; rr < rows; ++rr) {
-                    if (!nok) continue;
-                    const long long m = m0 + rr;
-                    float v = tile[rr * 33 + lane] + bias;
-                    switch (e.act) {
-                        case ACT_RELU: v = fmaxf(v, 0.f); break;
-                        case ACT_SWISH: v = v / (1.f + __expf(-v)); break;
-                        case ACT_TANH: v = tanhf(v); break;
-                        case ACT_SIGMOID: v = 1.f / (1.f + __expf(-v)); break;
-                        case ACT_PRELU:
-                        case ACT_LEAKY: v = v >= 0.f ? v : v * slope; break;
-                        case ACT_GELU: v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); break;
-                        default: break;
+                // rows in batches of 8: the eight residual loads are in flight together (memory-level parallelism)
+                for (int r0 = 0; r0 < rows; r0 += 8) {
+                    float v8[8], res8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = r0 + u;
+                        v8[u] = tile[min(rr, 31) * 33 + lane] + bias;
+                        res8[u] = (e.res && nok && rr < rows) ? __ldg(e.res + (long long)(m0 + rr) * e.ldres + n) : 0.f;
                     }
-                    v = fmaf(v, ps, pt) * e.alpha;
-                    if (e.res) v = fmaf(e.beta, __ldg(e.res + m * e.ldres + n), v);
-                    e.out[m * e.ldo + n] = v;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float v = v8[u];
+                        switch (e.act) {
+                            case ACT_RELU: v = fmaxf(v, 0.f); break;
+                            case ACT_SWISH: v = __fdividef(v, 1.f + __expf(-v)); break;
+                            case ACT_TANH: v = tanhf(v); break;
+                            case ACT_SIGMOID: v = __fdividef(1.f, 1.f + __expf(-v)); break;
+                            case ACT_PRELU:
+                            case ACT_LEAKY: v = v >= 0.f ? v : v * slope; break;
+                            case ACT_GELU: v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); break;
+                            default: break;
+                        }
+                        v = fmaf(v, ps, pt) * e.alpha;
+                        v = fmaf(e.beta, res8[u], v);
+                        if (nok && r0 + u < rows) e.out[(long long)(m0 + r0 + u) * e.ldo + n] = v;
+                    }
                 }
             }
         }

@@ -25,20 +25,29 @@ for (M, K, N) in ((128, 32, 64), (128, 64, 128), (3200, 256, 2048), (3200, 2048,
     y2 = ops.linear(x, w, b)
     err2 = float((y2.double() - ref).abs().max() / ref.abs().max())
     res = {}
+    r = th.randn(M, N, device=dev)
     for eng in ("tc", "simt"):
         ops.GEMM_ENGINE = eng
+        cache = ops.SplitCache()
+        f = lambda: ops.linear(x, w, b, residual=r, cache=cache)
         for _ in range(3):
-            ops.linear(x, w, b)
+            f()
+        th.cuda.synchronize()
+        g = th.cuda.CUDAGraph()
+        with th.cuda.graph(g):
+            for _ in range(20):
+                f()
+        g.replay()
         th.cuda.synchronize()
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
-            ops.linear(x, w, b)
+        for _ in range(5):
+            g.replay()
         e1.record()
         th.cuda.synchronize()
-        res[eng] = e0.elapsed_time(e1) / 10
+        res[eng] = e0.elapsed_time(e1) / 100
     fl = 2.0 * M * K * N
-    print(f"M={M} K={K} N={N}: tc err {err:.2e} simt err {err2:.2e} | tc {res['tc']*1e3:.1f} us "
+    print(f"M={M} K={K} N={N}: tc err {err:.2e} simt err {err2:.2e} | tc(graph, +split, +res) {res['tc']*1e3:.1f} us "
           f"({fl/res['tc']/1e9:.1f} TF/s eq) simt {res['simt']*1e3:.1f} us ({fl/res['simt']/1e9:.1f} TF/s)", flush=True)
 # epilogues on the tc path
 ops.GEMM_ENGINE = "tc"
