@@ -322,30 +322,53 @@ def main():
     assert out.shape == (BATCH, T, MELS)
 
     # ---- end to end through the public call with pinned host buffers --------------------------------------
+    # Three streams, double buffered: H2D of batch i+1 and D2H of batch i-1 overlap the kernel + NaN guard of
+    # batch i (the guard's host sync only waits for the compute stream).  Every step still moves its own
+    # 65.5 MB in and 32.5 MB out inside the timed region.
     h_in = [th.empty(BATCH, S, pin_memory=True).copy_(w) for w in wavs[:2]]
-    h_out = th.empty(BATCH, T, MELS, pin_memory=True)
-    d_in = th.empty(BATCH, S, device=dev)
+    h_out = [th.empty(BATCH, T, MELS, pin_memory=True) for _ in range(2)]
+    d_in = [th.empty(BATCH, S, device=dev) for _ in range(2)]
+    s_in, s_out = th.cuda.Stream(dev), th.cuda.Stream(dev)
+    ev_in = [th.cuda.Event() for _ in range(2)]
+    ev_used = [th.cuda.Event() for _ in range(2)]
+    ev_out = [th.cuda.Event() for _ in range(2)]
 
-    def e2e_step(i):
-        d_in.copy_(h_in[i % 2], non_blocking=True)
-        feats, nf = transform(d_in, lens)                # lengths on the host: no device sync for num_frames
-        h_out.copy_(feats, non_blocking=True)
+    def upload(i):
+        b = i % 2
+        with th.cuda.stream(s_in):
+            s_in.wait_event(ev_used[b])                  # the kernel that last read d_in[b] is done
+            d_in[b].copy_(h_in[b], non_blocking=True)
+            ev_in[b].record(s_in)
 
-    for i in range(3):
-        e2e_step(i)
+    def e2e_run(k):
+        for b in range(2):
+            ev_used[b].record(stream)
+            ev_out[b].record(s_out)
+        upload(0)
+        for i in range(k):
+            b = i % 2
+            if i + 1 < k:
+                upload(i + 1)
+            stream.wait_event(ev_in[b])
+            feats, nf = transform(d_in[b], lens)         # public call: kernel + check_valid (host sync on this stream)
+            ev_used[b].record(stream)
+            feats.record_stream(s_out)
+            with th.cuda.stream(s_out):
+                s_out.wait_event(ev_used[b])
+                h_out[b].copy_(feats, non_blocking=True)
+                ev_out[b].record(s_out)
+        s_out.synchronize()
+
+    e2e_run(3)
     th.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    k2 = max(5, min(args.steps, 20))
+    k2 = max(6, min(args.steps, 20))
     t0 = time.perf_counter()
-    f0, f1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for i in range(k2):
-        e2e_step(i)
-        launches += 1
-    f1.record(stream)
+    e2e_run(k2)
     th.cuda.synchronize(dev)
-    e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+    e2e_ms = 1e3 * (time.perf_counter() - t0)            # host wall clock brackets all three streams
+    launches += k2
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- aggregate over ranks: max time, sum frames -----------------------------------------------------------
@@ -380,7 +403,7 @@ def main():
         "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": BATCH * S * 4,
                 "d2h_bytes_per_step": BATCH * T * MELS * 4, "steps": k2,
-                "path": "AsrTransform.forward on a pinned-host batch: H2D -> fused kernel -> D2H, one stream"},
+                "path": "AsrTransform.forward on pinned-host batches: H2D | fused kernel + NaN guard | D2H on three streams, double buffered"},
         "gpu_launches": launches,
         "clocks": clocks,
     }
