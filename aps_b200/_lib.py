@@ -86,6 +86,8 @@ _SIGNATURES = {
     "aps_b200_linear_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(Epilogue),
                                     c_void_p, c_int64, c_void_p]),
     "aps_b200_tf32_split": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "aps_b200_im2col_tf32_split": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "aps_b200_linear_tc_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                        c_int64, POINTER(Epilogue), c_void_p, c_int64, c_void_p]),
     "aps_b200_conv2d_nhwc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,

@@ -406,7 +406,7 @@ class TransformerEncoder(nn.Module):
         x4 = x[:, None] if x.dim() == 3 else x                      # N x C x T x F
         nhwc = x4.permute(0, 2, 3, 1).contiguous()
         for (w, b, stride, padding), blk in zip(pk["convs"], self.proj.conv.enc_layers):
-            nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu")
+            nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu", cache=self._splits)
         N, T, Fq, C = nhwc.shape
         flat = nhwc.view(N * T, Fq * C)
         if "front_w" in pk:

@@ -28,6 +28,60 @@ int launch_gemm(const ALoader& a, const float* Wt, long long ldw, int M, int N, 
     return 0;
 }
 
+// Direct convolution for single-channel inputs (the first layer of the conv2d front, Cin = 1, K = KH*KW taps):
+// a GEMM with K = 9 would waste a 16-deep k-tile; this is a pure bandwidth kernel (one output row of Cout floats per
+// position).  Weights are staged tap-major in shared memory so channel reads are coalesced.
+struct Cin1Params {
+    const float* x;
+    const float* w;     // [Cout, KH*KW]
+    int H, W, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW, Cout;
+    long long M;
+    Epilogue e;
+};
+
+__global__ void __launch_bounds__(256) conv2d_cin1_kernel(const __grid_constant__ Cin1Params p) {
+    extern __shared__ float sw_[];                    // [K][Cout]
+    const int K = p.KH * p.KW;
+    for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
+        const int k = i / p.Cout, co = i - k * p.Cout;
+        sw_[i] = __ldg(p.w + (long long)co * K + k);
+    }
+    __syncthreads();
+    const int cgroups = (p.Cout + 3) / 4;
+    const long long total = p.M * cgroups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / cgroups;
+        const int co = (int)(i - m * cgroups) * 4;
+        const int ow = (int)(m % p.OW);
+        const long long t = m / p.OW;
+        const int oh = (int)(t % p.OH);
+        const long long nb = t / p.OH;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kh = 0; kh < p.KH; ++kh) {
+            const int ih = oh * p.sh - p.ph + kh * p.dh;
+            if (ih < 0 || ih >= p.H) continue;
+            for (int kw = 0; kw < p.KW; ++kw) {
+                const int iw = ow * p.sw - p.pw + kw * p.dw;
+                if (iw < 0 || iw >= p.W) continue;
+                const float xv = __ldg(p.x + (nb * p.H + ih) * p.W + iw);
+                const float* wr = sw_ + (kh * p.KW + kw) * p.Cout + co;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (co + j < p.Cout) acc[j] = fmaf(xv, wr[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = co + j;
+            if (n >= p.Cout) break;
+            float v = acc[j] + (p.e.bias ? __ldg(p.e.bias + n) : 0.f);
+            v = apply_act(v, p.e.act, p.e, n);
+            if (p.e.post_scale) v = fmaf(v, __ldg(p.e.post_scale + n), __ldg(p.e.post_shift + n));
+            p.e.out[m * p.e.ldo + n] = v * p.e.alpha;
+        }
+    }
+}
+
 static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* out, int64_t ldo) {
     APSB_CHECK_ARG(d && out, "null pointer argument");
     APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_GELU, "unknown activation %d", d->act);
@@ -80,6 +134,19 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
     Epilogue e{};
     const int ncols = (int)out_channels;
     if (int rc = fill_epilogue(e, epi, ncols, out, epi && epi->act == ACT_GLU ? ncols / 2 : ncols)) return rc;
+    if (in_channels == 1 && K <= 64 && epi->act != ACT_GLU && !epi->residual &&
+        (size_t)K * out_channels * 4 <= 48 * 1024) {
+        Cin1Params c{};
+        c.x = x; c.w = weight; c.H = (int)height; c.W = (int)width; c.KH = kernel_h; c.KW = kernel_w;
+        c.sh = stride_h; c.sw = stride_w; c.ph = pad_h; c.pw = pad_w; c.dh = dil_h; c.dw = dil_w;
+        c.OH = (int)OH; c.OW = (int)OW; c.Cout = ncols; c.M = M; c.e = e;
+        const long long total = M * ((ncols + 3) / 4);
+        const long long blocks = (total + 255) / 256;
+        const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+        conv2d_cin1_kernel<<<grid, 256, (size_t)K * ncols * 4, (cudaStream_t)stream>>>(c);
+        APSB_LAUNCH_CHECK();
+        return 0;
+    }
     ConvA a{};
     a.x = x; a.Nb = (int)batch; a.H = (int)height; a.W = (int)width; a.Cin = (int)in_channels;
     a.KH = kernel_h; a.KW = kernel_w; a.sh = stride_h; a.sw = stride_w; a.ph = pad_h; a.pw = pad_w;

@@ -283,6 +283,41 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict
     *reinterpret_cast<float4*>(lo + r * ldo + c) = l;
 }
 
+// im2col of an NHWC tensor fused with the TF32 split: patch[m, (kh*KW + kw)*Cin + c] -> hi / lo [M, K]
+struct Im2colParams {
+    const float* x;
+    int H, W, Cin, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW;
+    long long M;
+    int K;
+    float* hi;
+    float* lo;
+};
+
+__global__ void __launch_bounds__(256) im2col_split_kernel(const __grid_constant__ Im2colParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k4n = p.K >> 2;
+    if (i >= p.M * k4n) return;
+    const long long m = i / k4n;
+    const int k = (int)(i - m * k4n) * 4;
+    const int c = k % p.Cin, t = k / p.Cin;
+    const int kw = t % p.KW, kh = t / p.KW;
+    const int ow = (int)(m % p.OW);
+    const long long t2 = m / p.OW;
+    const int oh = (int)(t2 % p.OH);
+    const long long nb = t2 / p.OH;
+    const int ih = oh * p.sh - p.ph + kh * p.dh, iw = ow * p.sw - p.pw + kw * p.dw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+        v = __ldg(reinterpret_cast<const float4*>(p.x + ((nb * p.H + ih) * p.W + iw) * p.Cin + c));
+    float4 h, l;
+    h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
+    h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
+    h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
+    h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
+    *reinterpret_cast<float4*>(p.hi + m * p.K + k) = h;
+    *reinterpret_cast<float4*>(p.lo + m * p.K + k) = l;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -346,6 +381,30 @@ extern "C" int aps_b200_tf32_split(const float* x, int64_t rows, int64_t cols, i
     const long long total = rows * (cols >> 2);
     tf32_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, hi, lo, ld_out, rows,
                                                                                        (int)cols);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int aps_b200_im2col_tf32_split(const float* x, int64_t batch, int64_t height, int64_t width,
+                                          int64_t in_channels, int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                          int pad_h, int pad_w, int dil_h, int dil_w, float* hi, float* lo,
+                                          void* stream) {
+    APSB_CHECK_ARG(x && hi && lo, "null pointer argument");
+    APSB_CHECK_ARG(batch > 0 && height > 0 && width > 0 && in_channels > 0 && (in_channels & 3) == 0 &&
+                       ((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0,
+                   "im2col split needs Cin %% 4 == 0 and 16-byte aligned buffers");
+    Im2colParams p{};
+    p.x = x; p.H = (int)height; p.W = (int)width; p.Cin = (int)in_channels; p.KH = kernel_h; p.KW = kernel_w;
+    p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w; p.dh = dil_h; p.dw = dil_w;
+    p.OH = (int)((height + 2 * pad_h - dil_h * (kernel_h - 1) - 1) / stride_h + 1);
+    p.OW = (int)((width + 2 * pad_w - dil_w * (kernel_w - 1) - 1) / stride_w + 1);
+    APSB_CHECK_ARG(p.OH > 0 && p.OW > 0, "convolution output is empty");
+    p.M = batch * p.OH * p.OW;
+    p.K = kernel_h * kernel_w * (int)in_channels;
+    p.hi = hi; p.lo = lo;
+    const long long total = p.M * (p.K >> 2);
+    APSB_CHECK_ARG(total < (1LL << 31) * 256, "im2col too large");
+    im2col_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
     APSB_LAUNCH_CHECK();
     return 0;
 }

@@ -25,8 +25,9 @@ def _epilogue(bias=None, act="none", alpha=1.0, slope=None, leaky=0.0, residual=
 
 import os
 
-# GEMM engine of `linear`: "tc" = tcgen05 3xTF32 tensor-core kernel when the shape allows it, "simt" = exact fp32
-GEMM_ENGINE = os.environ.get("APS_B200_GEMM", "simt")
+# GEMM engine of `linear` / `conv2d_nhwc`: "tc" (default) = tcgen05 3xTF32 tensor-core kernel whenever the shape
+# allows it (K % 4 == 0, 16-byte aligned rows, M >= 64), "simt" = the exact-fp32 CUDA-core kernel everywhere
+GEMM_ENGINE = os.environ.get("APS_B200_GEMM", "tc")
 
 
 def tf32_split(x: th.Tensor):
@@ -93,7 +94,7 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
 
 
 def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
-                act: str = "none", slope=None, leaky: float = 0.0) -> th.Tensor:
+                act: str = "none", slope=None, leaky: float = 0.0, cache: Optional["SplitCache"] = None) -> th.Tensor:
     """x [B, H, W, Cin] contiguous, weight [Cout, KH, KW, Cin] contiguous -> [B, OH, OW, Cout]."""
     dev = _lib.require_cuda(x, "conv input")
     B, H, W, Cin = x.shape
@@ -104,6 +105,23 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
         raise RuntimeError(f"convolution output is empty for input {tuple(x.shape)}")
     out = th.empty((B, OH, OW, Cout // 2 if act == "glu" else Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, slope, leaky)
+    M, K = B * OH * OW, KH * KW * Cin
+    if (GEMM_ENGINE == "tc" and Cin % 4 == 0 and K >= 128 and M >= 128 and Cout >= 64 and act != "glu"
+            and x.data_ptr() % 16 == 0):
+        # tensor-core path: fused im2col + TF32 split, then the tcgen05 GEMM on the patch matrices
+        patches = th.empty((2, M, K), dtype=th.float32, device=dev)
+        w2 = weight.view(Cout, K)
+        w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
+        lib = _lib.load()
+        with th.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.aps_b200_im2col_tf32_split(x.data_ptr(), B, H, W, Cin, KH, KW, stride[0], stride[1], padding[0],
+                                                      padding[1], dilation[0], dilation[1], patches[0].data_ptr(),
+                                                      patches[1].data_ptr(), st))
+            _lib.check(lib.aps_b200_linear_tc_fwd(patches[0].data_ptr(), patches[1].data_ptr(), M, K, K, w_hi.data_ptr(),
+                                                  w_lo.data_ptr(), w_hi.stride(0), Cout, e, out.data_ptr(),
+                                                  out.shape[-1], st))
+        return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv2d_nhwc_fwd(x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW,
                                                         stride[0], stride[1], padding[0], padding[1], dilation[0],

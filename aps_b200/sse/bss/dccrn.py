@@ -180,10 +180,17 @@ class DCCRN(nn.Module):
                                bidirectional=rnn_bidir)
         self.num_spks, self.connection, self.share_decoder = num_spks, connection, share_decoder
         self._packs = None
-        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_packs", None))
+        self._splits = ops.SplitCache()
+        self.register_load_state_dict_post_hook(lambda m, k: m._reset())
+
+    def _reset(self):
+        self._packs = None
+        self._splits.clear()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
+        if hasattr(self, "_splits"):
+            self._splits.clear()
         return super()._apply(fn, *a, **k)
 
     def _build_packs(self):
@@ -203,7 +210,8 @@ class DCCRN(nn.Module):
         skips = []
         L = len(self.encoder.layers)
         for i, (blk, (w, b)) in enumerate(zip(self.encoder.layers, pk["enc"])):
-            x = ops.conv2d_nhwc(x, w, b, stride=blk.stride, padding=blk.padding, act="leaky_relu", leaky=0.01)
+            x = ops.conv2d_nhwc(x, w, b, stride=blk.stride, padding=blk.padding, act="leaky_relu", leaky=0.01,
+                                cache=self._splits)
             if i + 1 != L:
                 skips.append(x)
         # ---- complex LSTM bottleneck (cuDNN): features ordered (channel, frequency) like dccrn.py:41-50 ------

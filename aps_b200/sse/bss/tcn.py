@@ -110,11 +110,21 @@ class FreqConvTasNet(nn.Module):
         self.non_linear = non_linear
         self.num_spks, self.num_bins = num_spks, num_bins
         self._packs = None
-        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_packs", None))
+        self._splits = ops.SplitCache()
+        self.register_load_state_dict_post_hook(lambda m, k: m._reset())
+
+    def _reset(self):
+        self._packs = None
+        self._splits.clear()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
+        if hasattr(self, "_splits"):
+            self._splits.clear()
         return super()._apply(fn, *a, **k)
+
+    def _lin(self, x, w, b=None, **kw):
+        return ops.linear(x, w, b, cache=self._splits, **kw)
 
     def _build_packs(self):
         pk = {"blocks": [], "skip": []}
@@ -132,6 +142,8 @@ class FreqConvTasNet(nn.Module):
             pk["skip"] = [lin.packed() for lin in self.conv.skip_linear]
         C = self.mask[1].in_channels
         pk["ident"] = th.ones(1, C, device=self.mask[1].weight.device)
+        pk["proj_w"] = self.proj[1].weight.detach()[..., 0].contiguous()
+        pk["mask_w"] = self.mask[1].weight.detach()[..., 0].contiguous()
         return pk
 
     def _mask_rows(self, feats: th.Tensor) -> th.Tensor:
@@ -146,27 +158,27 @@ class FreqConvTasNet(nn.Module):
         pk = self._packs
         N, T, Fi = feats.shape
         rows = ops.rows2d(feats.detach().float())
-        x = ops.linear(rows, self.proj[1].weight.detach()[..., 0], self.proj[1].bias.detach())
+        x = self._lin(rows, pk["proj_w"], self.proj[1].bias.detach())
         outs, skip, bi = [x], 0, 0
         nrep, nblk = len(self.conv.repeat), len(self.conv.repeat[0])
         for r in range(nrep):
             if self.conv.skip_residual:
                 for i in range(r):                       # in-place accumulation semantics of tcn.py:203-224
                     w, b = pk["skip"][skip + i]
-                    x = ops.linear(outs[i], w, b, residual=x)
+                    x = self._lin(outs[i], w, b, residual=x)
                 outs[r] = x
                 skip += r
             for _ in range(nblk):
                 d = pk["blocks"][bi]
                 bi += 1
-                h = ops.linear(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=d["bn1"])
+                h = self._lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=d["bn1"])
                 h = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
                                  slope=d["a2"], post=d["bn2"])
-                x = ops.linear(h, d["w2"], d["b2"], residual=x)
+                x = self._lin(h, d["w2"], d["b2"], residual=x)
             outs.append(x)
         # mask head: PReLU then 1x1 conv then relu / sigmoid
         a = ops.dwconv1d(x, N, T, pk["ident"], None, act="prelu", slope=self.mask[0].weight.detach())
-        return ops.linear(a, self.mask[1].weight.detach()[..., 0], self.mask[1].bias.detach(), act=self.non_linear)
+        return self._lin(a, pk["mask_w"], self.mask[1].bias.detach(), act=self.non_linear)
 
     def _tf_mask(self, feats: th.Tensor, num_spks: int) -> List[th.Tensor]:
         """[N x F x T, ...] (views of one N x T x (F*spks) buffer) — tcn.py:403-414."""

@@ -213,6 +213,13 @@ int aps_b200_linear_fwd(const float* x, int64_t rows, int64_t in_features, int64
  * Same epilogue contract as aps_b200_linear_fwd.                                              */
 int aps_b200_tf32_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo,
                         int64_t ld_out, void* stream);
+/* im2col of x [B, H, W, Cin] (Cin % 4 == 0) fused with the TF32 split: hi / lo [B*OH*OW, KH*KW*Cin] patch
+ * matrices in the column order of a [Cout, KH, KW, Cin] filter, ready for aps_b200_linear_tc_fwd
+ * (the tensor-core path of aps_b200_conv2d_nhwc_fwd).                                          */
+int aps_b200_im2col_tf32_split(const float* x, int64_t batch, int64_t height, int64_t width,
+                               int64_t in_channels, int kernel_h, int kernel_w, int stride_h,
+                               int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float* hi,
+                               float* lo, void* stream);
 int aps_b200_linear_tc_fwd(const float* x_hi, const float* x_lo, int64_t rows, int64_t in_features,
                            int64_t ld_x, const float* weight_hi, const float* weight_lo, int64_t ld_w,
                            int64_t out_features, const aps_b200_epilogue* epi, float* out,

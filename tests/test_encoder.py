@@ -123,6 +123,22 @@ def test_tensor_core_gemm_vs_fp64():
 
 
 @pytest.mark.gpu
+def test_tensor_core_conv_path_vs_torch(monkeypatch):
+    """conv2d through fused im2col + TF32 split + tcgen05 GEMM (the path the conv2d front takes with engine tc)."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    th.manual_seed(3)
+    for (B, H, W, Ci, Co, k, s_, p_) in ((2, 33, 20, 16, 24, (3, 3), (2, 2), (1, 1)), (3, 40, 21, 32, 64, (3, 3), (2, 2), (1, 1)),
+                                         (1, 18, 9, 64, 32, (5, 2), (2, 1), (2, 0))):
+        x, w, b = th.randn(B, Ci, H, W), th.randn(Co, Ci, *k) * 0.1, th.randn(Co)
+        ref = F.relu(F.conv2d(x, w, b, stride=s_, padding=p_)).permute(0, 2, 3, 1)
+        got = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV),
+                              b.to(DEV), stride=s_, padding=p_, act="relu")
+        assert got.shape == ref.shape and rel_err(got, ref) < 1e-5
+
+
+@pytest.mark.gpu
 def test_dense_kernels_vs_torch():
     """GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the CPU."""
     import torch.nn.functional as F
@@ -173,10 +189,13 @@ def test_dense_kernels_vs_torch():
 
 
 @pytest.mark.gpu
-def test_c4_conformer_full_size_subset_vs_oracle():
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_c4_conformer_full_size_subset_vs_oracle(engine, monkeypatch):
     """BASELINE config[3]: conformer 12L d=256 h=4 rel-pos, conv2d x3 front, B=64 on 80-d fbank [64, 398, 80].
     Parity of sampled utterances against the CPU oracle + batch-shard invariance (bit identical rows)."""
+    from aps_b200 import ops
     from aps_b200.asr.transformer import TransformerEncoder
+    monkeypatch.setattr(ops, "GEMM_ENGINE", engine)
     cfg = dict(arch="cfmr", input_size=80, output_proj=-1, num_layers=12, proj="conv2d",
                proj_kwargs=dict(conv_channels=256, num_layers=3), pose="rel",
                pose_kwargs=dict(dropout=0.1, lradius=256, rradius=256),
