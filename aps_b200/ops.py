@@ -106,8 +106,8 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
     out = th.empty((B, OH, OW, Cout // 2 if act == "glu" else Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, slope, leaky)
     M, K = B * OH * OW, KH * KW * Cin
-    if (GEMM_ENGINE == "tc" and Cin % 4 == 0 and K >= 128 and M >= 128 and Cout >= 64 and act != "glu"
-            and x.data_ptr() % 16 == 0):
+    if (GEMM_ENGINE == "tc" and Cin % 4 == 0 and K >= 128 and M >= 128 and Cout >= 128 and act != "glu"
+            and x.data_ptr() % 16 == 0 and 8 * M * K <= (4 << 30)):      # patch matrices (hi + lo) capped at 4 GiB
         # tensor-core path: fused im2col + TF32 split, then the tcgen05 GEMM on the patch matrices
         patches = th.empty((2, M, K), dtype=th.float32, device=dev)
         w2 = weight.view(Cout, K)

@@ -139,10 +139,12 @@ def test_tensor_core_conv_path_vs_torch(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_dense_kernels_vs_torch():
-    """GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the CPU."""
+def test_dense_kernels_vs_torch(monkeypatch):
+    """Exact-fp32 (SIMT) GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the
+    CPU (the tensor-core engine has its own tests above)."""
     import torch.nn.functional as F
     from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "simt")
     th.manual_seed(1)
     for (M, K, N) in ((37, 257, 50), (300, 256, 512), (1000, 96, 64), (5, 8, 6), (129, 2304, 256)):
         x, w, b, r = th.randn(M, K), th.randn(N, K) / K**0.5, th.randn(N), th.randn(M, N)
