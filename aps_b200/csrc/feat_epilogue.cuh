@@ -31,22 +31,23 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 // sm_mel_i : [2*M + FI] band start / length, then per lane-slot i the max length over bands d = l + G*i (shared);  sm_mel_w: [M, mel_stride] weights in shared memory
 //            (used when p.mel_in_smem, else p.mel_w in global memory)
 // o        : output row of this frame (D floats) or nullptr to skip the store
-template <int G, int FI>
+// FULL: the caller guarantees D == G*FI, M == D and mel weights in shared memory (every guard folds away)
+template <int G, int FI, bool FULL = false>
 __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const float* __restrict__ mag,
                                                  const int* __restrict__ sm_mel_i,
                                                  const float* __restrict__ sm_mel_w, int l, unsigned mask,
                                                  float* __restrict__ o) {
     float feat[FI];
-    const int D = p.D;
+    const int D = FULL ? G * FI : p.D;
 #pragma unroll
     for (int i = 0; i < FI; ++i) {
         const int d = l + G * i;
         float acc = 0.f;
-        if (d < D) {
-            if (p.M > 0) {
+        if (FULL || d < D) {
+            if (FULL || p.M > 0) {
                 const int s0 = sm_mel_i[d], n = sm_mel_i[p.M + d];
                 const float* mg = mag + s0;
-                if (p.mel_in_smem) {   // keep the two address spaces apart: LDS, not generic LD
+                if (FULL || p.mel_in_smem) {   // keep the two address spaces apart: LDS, not generic LD
                     // uniform trip count for the whole group (weights are zero padded to mel_stride and the
                     // magnitude buffer has slack behind bin F-1), so there is no lane divergence
                     const float* wr = sm_mel_w + d * p.mel_stride;
@@ -60,12 +61,19 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
             } else {
                 acc = mag[d];
             }
-            // clamp mode: __logf (MUFU.LG2, abs err < 4e-7) — far inside the 1e-4 budget after CMVN;
-            // lower-bound mode keeps the fully accurate logf because log(lb + x) can sit next to 0
-            if (p.log_mode == 1) acc = __logf(acc < p.log_eps ? p.log_eps : acc);
-            else if (p.log_mode == 2) acc = logf(p.log_lb + acc);
         }
         feat[i] = acc;
+    }
+    // clamp mode: __logf (MUFU.LG2, abs err < 4e-7) — far inside the 1e-4 budget after CMVN;
+    // lower-bound mode keeps the fully accurate logf because log(lb + x) can sit next to 0
+    if (p.log_mode == 1) {
+        const float le = p.log_eps;
+#pragma unroll
+        for (int i = 0; i < FI; ++i) feat[i] = __logf(feat[i] < le ? le : feat[i]);   // NaN propagates like th.clamp
+    } else if (p.log_mode == 2) {
+        const float lb = p.log_lb;
+#pragma unroll
+        for (int i = 0; i < FI; ++i) feat[i] = logf(lb + feat[i]);
     }
     if (p.cmvn_mode == 1) {
         const float invD = 1.0f / (float)D;
@@ -107,16 +115,16 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
         }
     }
     if (o != nullptr) {
-        int bad = 0;
+        bool bad = false;   // any NaN among this lane's values (the host only tests the counter against 0)
 #pragma unroll
         for (int i = 0; i < FI; ++i) {
             const int d = l + G * i;
             if (d < D) {
                 o[d] = feat[i];
-                bad += (feat[i] != feat[i]) ? 1 : 0;
+                bad |= (feat[i] != feat[i]);
             }
         }
-        if (p.nan_count != nullptr && bad) atomicAdd(p.nan_count, bad);
+        if (bad && p.nan_count != nullptr) atomicAdd(p.nan_count, 1);
     }
 }
 

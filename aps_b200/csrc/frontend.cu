@@ -144,8 +144,9 @@ struct ChunkGeo {
 
 __device__ __forceinline__ ChunkGeo chunk_geo(const FrontendParams& p, long long chunk) {
     ChunkGeo g;
-    g.row = chunk / p.chunks_per_row;
-    const int c = (int)(chunk - g.row * p.chunks_per_row);
+    const unsigned r32 = (unsigned)chunk / (unsigned)p.chunks_per_row;   // total_chunks < 2^31 (host check)
+    g.row = r32;
+    const int c = (int)((unsigned)chunk - r32 * (unsigned)p.chunks_per_row);
     g.t0 = c * p.TC;
     g.nf = min(p.TC, p.T - g.t0);
     g.start = (long long)g.t0 * p.hop;
@@ -174,7 +175,8 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 
 // MODE 0: features, MODE 1: complex STFT.  FI = feature values per lane (MODE 0).
-template <int NC, int MODE, int FI>
+//          FULL (MODE 0): D == G*FI == num_mels with the mel weights in shared memory — no tail guards.
+template <int NC, int MODE, int FI, bool FULL = false>
 __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(const __grid_constant__ FrontendParams p) {
     using P = FFTPlan<NC>;
     constexpr int G = P::G;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(
                 __syncwarp(mask);
 
                 float* o = (f < nf) ? p.out + ((long long)row * p.T + (t0 + f)) * p.ld_out : nullptr;
-                feature_epilogue<G, FI>(p.ft, mag, sm_mel_i, sm_mel_w, l, mask, o);
+                feature_epilogue<G, FI, FULL>(p.ft, mag, sm_mel_i, sm_mel_w, l, mask, o);
                 __syncwarp(mask);  // mags consumed before the next frame reuses the buffer
             }
         }
@@ -445,9 +447,9 @@ static int log2i(int v) {
     return r;
 }
 
-template <int NC, int MODE, int FI>
+template <int NC, int MODE, int FI, bool FULL = false>
 static int launch_frontend(FrontendParams& p, cudaStream_t st) {
-    auto kern = frontend_kernel<NC, MODE, FI>;
+    auto kern = frontend_kernel<NC, MODE, FI, FULL>;
     constexpr int G = FFTPlan<NC>::G;
     constexpr int NGROUPS = kThreads / G;
     // frames per chunk: a multiple of the groups per CTA, sized so that >= 2 CTAs fit per SM
@@ -469,6 +471,7 @@ static int launch_frontend(FrontendParams& p, cudaStream_t st) {
     p.TC = TC;
     p.chunks_per_row = (p.T + TC - 1) / TC;
     p.total_chunks = p.rows * p.chunks_per_row;
+    APSB_CHECK_ARG(p.total_chunks < (1LL << 31), "frontend: too many chunks (%lld)", p.total_chunks);
     p.tma_ok = (((uintptr_t)p.wav & 15) == 0 && (p.ld & 3) == 0 && (((long long)TC * p.hop) & 3) == 0 &&
                 (p.pad & 3) == 0 && !g_disable_tma) ? 1 : 0;
     static int smem_set = -1, occ_smem = -1, occ_cached = 1;  // per instantiation; one GPU per process
@@ -499,6 +502,9 @@ static int dispatch_frontend(FrontendParams& p, cudaStream_t st) {
         if constexpr (MODE == 1) {                                                      \
             return launch_frontend<NC_, MODE, 1>(p, st);                                \
         } else {                                                                        \
+            if ((NC_ == 256 || NC_ == 128) && p.ft.M == 5 * (NC_ / 16) && p.ft.D == p.ft.M &&         \
+                p.ft.M * p.ft.mel_stride * 4 <= 24 * 1024)                              \
+                return launch_frontend<NC_, MODE, 5, true>(p, st);                      \
             if (fi <= 8) return launch_frontend<NC_, MODE, 8>(p, st);                   \
             return launch_frontend<NC_, MODE, 17>(p, st);                               \
         }
