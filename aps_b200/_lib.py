@@ -52,6 +52,17 @@ class AttnDesc(Structure):
                 ("padding_fill", c_float), ("attn_mask", c_void_p), ("scale", c_float)]
 
 
+class SignalList(Structure):
+    """mirror of `aps_b200_signal_list`"""
+    _fields_ = [("ptr", c_void_p * 4), ("ld", c_int64 * 4), ("count", c_int32)]
+
+
+class ObjfDesc(Structure):
+    """mirror of `aps_b200_objf_desc`"""
+    _fields_ = [("kind", c_int32), ("zero_mean", c_int32), ("non_negative", c_int32), ("eps", c_float),
+                ("snr_max", c_float)]
+
+
 ACT = {"none": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4, "prelu": 5, "glu": 6, "leaky_relu": 7, "gelu": 8}
 
 _SIGNATURES = {
@@ -104,6 +115,9 @@ _SIGNATURES = {
                                       c_void_p, c_int, c_int, c_int, POINTER(Epilogue), c_void_p, c_int64, c_void_p]),
     "aps_b200_mhsa_fwd": (c_int, [POINTER(AttnDesc), c_void_p, c_int64, c_void_p]),
     "aps_b200_cmvn_allband": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
+    "aps_b200_pair_objf_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
+    "aps_b200_pair_objf_fwd": (c_int, [POINTER(SignalList), POINTER(SignalList), c_int64, c_int64, POINTER(ObjfDesc),
+                                       c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

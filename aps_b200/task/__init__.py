@@ -1,0 +1,5 @@
+from .objf import pair_objf_matrix, sisnr_objf, snr_objf, permu_invarint_objf, multiple_objf, hybrid_permu_objf
+from .sse import SisnrTask, SnrTask
+
+__all__ = ["pair_objf_matrix", "sisnr_objf", "snr_objf", "permu_invarint_objf", "multiple_objf", "hybrid_permu_objf",
+           "SisnrTask", "SnrTask"]

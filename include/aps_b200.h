@@ -299,6 +299,33 @@ typedef struct aps_b200_attn_desc {
 } aps_b200_attn_desc;
 int aps_b200_mhsa_fwd(const aps_b200_attn_desc* desc, float* out, int64_t ld_out, void* stream);
 
+/* Time-domain separation objectives ----------------------------------------------------------
+ * Si-SNR / SNR between every estimate and every reference of an utterance in ONE pass over the
+ * waveforms (fp64 sums of x, s, x^2, s^2, x.s; closed-form objective).  out[n, e, r] is what
+ * sisnr_objf(est[e], ref[r]) / snr_objf(est[e], ref[r]) return for utterance n — the K x K
+ * matrix permu_invarint_objf needs — so PIT is a min over K! sums of K entries afterwards.
+ * Replaces aps/task/objf.py:133-163 (sisnr_objf), :166-198 (snr_objf) and the K!*K calls of
+ * :289-336 (permu_invarint_objf) made by aps/task/sse.py:83-139 (TimeDomainTask / SisnrTask).  */
+#define APS_B200_MAX_SIGNALS 4
+typedef struct aps_b200_signal_list {
+    const float* ptr[APS_B200_MAX_SIGNALS];  /* each [batch, num_samples], row stride ld[k] floats */
+    int64_t ld[APS_B200_MAX_SIGNALS];
+    int32_t count;
+} aps_b200_signal_list;
+typedef struct aps_b200_objf_desc {
+    int32_t kind;          /* 0: Si-SNR (objf.py:133), 1: SNR (objf.py:166)                        */
+    int32_t zero_mean;     /* Si-SNR: remove the per-utterance mean first (objf.py:151-153)        */
+    int32_t non_negative;  /* 10*log10(1 + snr^2) instead of 20*log10(eps + snr)                   */
+    float   eps;           /* EPSILON of the reference (float32 machine epsilon)                   */
+    float   snr_max;       /* SNR only: > 0 enables the thresholded form (objf.py:183-190)         */
+} aps_b200_objf_desc;
+/* Scratch for the per-CTA partial sums (bytes); 0 for an unsupported shape. */
+int64_t aps_b200_pair_objf_workspace_bytes(int64_t batch, int64_t num_samples, int num_signals);
+/* est->count == ref->count == K in [1, 4]; out: [batch, K, K] fp32. */
+int aps_b200_pair_objf_fwd(const aps_b200_signal_list* est, const aps_b200_signal_list* ref, int64_t batch,
+                           int64_t num_samples, const aps_b200_objf_desc* desc, void* workspace,
+                           int64_t workspace_bytes, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

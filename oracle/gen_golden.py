@@ -37,7 +37,41 @@ def wave(seed, *shape, kind="randn"):
     return th.rand(*shape, generator=g)
 
 
+def objf_cases():
+    """Si-SNR / SNR / PIT values of aps/task/objf.py on seeded estimate/reference pairs (row a25)."""
+    from aps.task.objf import hybrid_permu_objf, permu_invarint_objf, sisnr_objf, snr_objf
+    th.set_num_threads(4)
+    g = th.Generator().manual_seed(2500)
+    N, S = 6, 4000
+    refs = [0.1 * th.randn(N, S, generator=g) + 0.02 * k for k in range(3)]
+    # estimates: scaled references + noise at graded levels (about 40 dB ... -5 dB), speakers swapped for odd n
+    level = th.tensor([0.001, 0.003, 0.01, 0.03, 0.1, 0.2])[:, None]
+    ests = [(0.5 + 0.3 * k) * refs[k] + level * th.randn(N, S, generator=g) + 0.01 for k in range(3)]
+    swap = th.arange(N) % 2 == 1
+    e0, e1 = ests[0].clone(), ests[1].clone()
+    e0[swap], e1[swap] = ests[1][swap], ests[0][swap]
+    ests = [e0, e1, ests[2]]
+    arrays = {f"ref{k}": refs[k] for k in range(3)}
+    arrays.update({f"est{k}": ests[k] for k in range(3)})
+    for zm in (True, False):
+        for nn_ in (True, False):
+            arrays[f"sisnr_zm{int(zm)}_nn{int(nn_)}"] = sisnr_objf(ests[0], refs[0], zero_mean=zm, non_nagetive=nn_)
+    arrays["snr"] = snr_objf(ests[0], refs[0])
+    arrays["snr_nn"] = snr_objf(ests[0], refs[0], non_nagetive=True)
+    arrays["snr_max30"] = snr_objf(ests[0], refs[0], snr_max=30)
+    neg = lambda x, s: -sisnr_objf(x, s)
+    for K in (2, 3):
+        loss, index = permu_invarint_objf(ests[:K], refs[:K], neg, return_permutation=True)
+        arrays[f"pit{K}_loss"], arrays[f"pit{K}_index"] = loss, index
+    arrays["hybrid_3of2"] = hybrid_permu_objf(ests, refs, neg, permute=True, permu_num_spks=2)
+    arrays["hybrid_nopermute"] = hybrid_permu_objf(ests, refs, neg, weight=[0.5, 0.3, 0.2], permute=False)
+    save("objf_0", dict(N=N, S=S), **arrays)
+
+
 def main():
+    if "--only-objf" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return objf_cases()
     from aps.transform import AsrTransform, EnhTransform
     from aps.transform.utils import STFT, iSTFT
     th.set_num_threads(4)
@@ -209,6 +243,7 @@ def main():
         arrays = dict(mix=mix, wav=stack(wav), masks=stack(msk))
         arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})  # K: 2 MB each
         save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
+    objf_cases()
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)
