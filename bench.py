@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--workload", default="fbank", choices=["fbank", "encoder", "mvdr_tcn", "stft_istft"],
+    ap.add_argument("--workload", default="fbank", choices=["fbank", "encoder", "mvdr_tcn", "stft_istft", "dccrn"],
                     help="fbank = BASELINE configs[1] (the headline, default); the others are the remaining "
                          "single-GPU configs, reported with the same JSON schema (N = 1 only)")
     return ap.parse_args()
@@ -207,7 +207,8 @@ def run_extra(args):
         flops = 6.18e9 * B                                   # SURVEY.md §8d without the vocabulary projection
         ach = flops / (ms / args.steps * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "kernel": "gemm_kernel<..> (exact-fp32 SIMT GEMM; tensor pipe idle this round)",
+                "traffic": None, "kernel": "tc_gemm_kernel<BN> (tcgen05 3xTF32, fp32-equivalent FLOPs counted once) + "
+                                           "mhsa / layernorm / dwconv kernels, CUDA-graph replay",
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"}
         wl = "conformer encoder 12L d=256 h=4 rel-pos, conv2d x3 front, forward on [64, 398, 80] fbank (configs[3])"
     elif args.workload == "mvdr_tcn":
@@ -235,6 +236,40 @@ def run_extra(args):
                           "the TCN GEMMs (2.43 GFLOP/utt, fp32 SIMT) dominate the time",
                 "algorithmic_bytes_per_step": bytes_, "peak_source": peak_src}
         wl = "4-ch STFT + freq-TCN sigmoid mask + MVDR, B=64 x 4 s (configs[2]); value in 10 ms frames/s"
+    elif args.workload == "dccrn":
+        from aps_b200.sse.bss import DCCRN
+        from aps_b200.task import SisnrTask
+        from aps_b200.transform import EnhTransform
+        B = 128
+        enh = EnhTransform(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, center=True)
+        th.manual_seed(0)
+        net = DCCRN(enh_transform=enh, cplx=True, K="3,3;3,3;3,3;3,3;3,3;3,3;3,3", S="2,1;2,1;2,1;2,1;2,1;2,1;2,1",
+                    P="1,1,1,1,1,0,0", O="0,0,0,0,0,0,1", C="16,32,64,64,128,128,256", num_spks=2, rnn_resize=512,
+                    non_linear="sigmoid", connection="cat").to(dev).eval()       # tests/python/test_nnet_sse.py:216-228
+        task = SisnrTask(net, num_spks=2)
+        xs = [th.rand(B, S, device=dev, generator=gen) for _ in range(R)]
+        refs = [[0.5 * x, 0.5 * x.flip(-1)] for x in xs]
+        with th.no_grad():
+            ms = _time_steps(lambda i: task({"mix": xs[i % R], "ref": refs[i % R]})["loss"], args.steps, args.warmup, dev)
+        Tf = S // 256 + 1                                           # STFT frames (512/256, center)
+        # FLOPs of the complex (transposed) convolutions as the reference computes them (4 real convs each)
+        flops, Fq, Cs = 0.0, 257, [1, 16, 32, 64, 64, 128, 128, 256]
+        fqs = [Fq]
+        for i, pd in enumerate([1, 1, 1, 1, 1, 0, 0]):
+            Fq = (Fq + 2 * pd - 3) // 2 + 1
+            fqs.append(Fq)
+            flops += 2.0 * B * Fq * Tf * (2 * Cs[i + 1]) * (9 * 2 * Cs[i])
+        dec_c = [512, 256, 256, 128, 128, 64, 32]                 # "cat" inputs; outputs 128,128,64,64,32,16,num_spks
+        dec_o = [128, 128, 64, 64, 32, 16, 2]
+        for i in range(7):
+            flops += 2.0 * B * fqs[7 - i] * Tf * (2 * dec_c[i]) * (9 * 2 * dec_o[i])
+        frames, launches = B * (S // HOP), 1 + 7 + 7 + 2 * 2 + 2 + 6
+        ach = flops / (ms / args.steps * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": None, "kernel": "gemm_kernel<.., ConvA/ConvT> (exact-fp32 SIMT implicit GEMM on stacked re/im "
+                                           "channels) dominates; STFT, iSTFT x2, cmask, cuDNN LSTM bottleneck, fused Si-SNR",
+                "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"}
+        wl = ("DCCRN (C=16..256, cat, 2 spk) forward + PIT Si-SNR on B=128 x 4 s (configs[4]); value in 10 ms frames/s")
     else:
         from aps_b200.transform.utils import STFT, iSTFT
         B = 128
