@@ -115,6 +115,9 @@ _SIGNATURES = {
                                       c_void_p, c_int, c_int, c_int, POINTER(Epilogue), c_void_p, c_int64, c_void_p]),
     "aps_b200_mhsa_fwd": (c_int, [POINTER(AttnDesc), c_void_p, c_int64, c_void_p]),
     "aps_b200_cmvn_allband": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
+    "aps_b200_utt_norm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "aps_b200_utt_norm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
+                                      c_void_p, c_float, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "aps_b200_pair_objf_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "aps_b200_pair_objf_fwd": (c_int, [POINTER(SignalList), POINTER(SignalList), c_int64, c_int64, POINTER(ObjfDesc),
                                        c_void_p, c_int64, c_void_p, c_void_p]),

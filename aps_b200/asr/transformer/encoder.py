@@ -349,11 +349,12 @@ class TransformerEncoder(nn.Module):
         pk = {"dev": dev, "layers": []}
         if isinstance(self.proj, LinearProj):
             nrm = self.proj.norm.norm
-            if not isinstance(nrm, nn.BatchNorm1d):
-                raise RuntimeError("aps_b200: LinearProj(norm='LN') (a GroupNorm over time) is not implemented; "
-                                   "use norm='BN'")
-            w, b = self._fold_bn(self.proj.proj.weight, self.proj.proj.bias, nrm)
-            pk["lin_w"], pk["lin_b"] = w.contiguous(), b.contiguous()
+            if isinstance(nrm, nn.BatchNorm1d):
+                w, b = self._fold_bn(self.proj.proj.weight, self.proj.proj.bias, nrm)
+                pk["lin_w"], pk["lin_b"], pk["lin_ln"] = w.contiguous(), b.contiguous(), None
+            else:   # "LN" = GroupNorm(1, D) over (D, T) of every utterance (component.py:95-96): a separate pass
+                pk["lin_w"], pk["lin_b"] = self.proj.proj.weight.detach(), self.proj.proj.bias.detach()
+                pk["lin_ln"] = (nrm.weight.detach(), nrm.bias.detach(), nrm.eps)
         if isinstance(self.proj, Conv2dProj):
             convs = []
             for blk in self.proj.conv.enc_layers:
@@ -401,7 +402,12 @@ class TransformerEncoder(nn.Module):
             return x
         if isinstance(self.proj, LinearProj):
             N, T, Fi = x.shape
-            y = self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"], act="relu")
+            if pk["lin_ln"] is None:
+                y = self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"], act="relu")
+            else:
+                g, b, eps = pk["lin_ln"]
+                y = ops.utt_norm(self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"]), N, T, g, b, eps, relu=True,
+                                 inplace=True)
             return y.view(N, T, -1)
         x4 = x[:, None] if x.dim() == 3 else x                      # N x C x T x F
         nhwc = x4.permute(0, 2, 3, 1).contiguous()

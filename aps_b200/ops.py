@@ -173,6 +173,24 @@ def layernorm(x: th.Tensor, gamma, beta, eps: float = 1e-5, residual: Optional[t
     return out
 
 
+def utt_norm(x: th.Tensor, N: int, T: int, gamma=None, beta=None, eps: float = 1e-5, per_channel: bool = False,
+             relu: bool = False, stride_n: Optional[int] = None, stride_t: int = 1, inplace: bool = False) -> th.Tensor:
+    """Per-utterance normalisation over time of token rows [N*T, C] (row(n, t) = n*stride_n + t*stride_t):
+    GroupNorm(1, C) / gLN statistics over (C, T), or GroupNorm(C, C) statistics over T when `per_channel`."""
+    dev = _lib.require_cuda(x, "normalisation input")
+    C = x.shape[1]
+    lib = _lib.load()
+    nbytes = lib.aps_b200_utt_norm_workspace_bytes(N, T, C)
+    ws = th.empty(nbytes // 8, dtype=th.float64, device=dev)
+    out = x if inplace else th.empty_like(x)
+    with th.cuda.device(dev):
+        _lib.check(lib.aps_b200_utt_norm_fwd(x.data_ptr(), x.stride(0), N, T, C, T if stride_n is None else stride_n,
+                                             stride_t, int(per_channel), _lib.ptr(gamma), _lib.ptr(beta), float(eps),
+                                             int(relu), ws.data_ptr(), nbytes, out.data_ptr(), out.stride(0),
+                                             _lib.stream_ptr(dev)))
+    return out
+
+
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
              stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
              residual=None, post=None) -> th.Tensor:

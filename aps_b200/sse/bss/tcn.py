@@ -8,7 +8,9 @@ Module tree (names kept for strict checkpoint loading): `proj.1` (1x1 conv), `co
 Fused inference schedule on batch-major token rows [N*T, C] — three launches per block:
   GEMM(1x1 conv * scale + bias, PReLU, BatchNorm affine)  ->  depthwise dilated conv (+bias, PReLU,
   BatchNorm affine)  ->  GEMM(1x1 conv * scale + bias, + residual)
-Only `norm="BN"` (the default of the frequency-domain model) is implemented on this path.
+With `norm="BN"` (the default of the frequency-domain model) the eval-mode affine folds into the epilogues as
+above; "cLN" / "gLN" / "IN" need per-utterance statistics over time and add one `ops.utt_norm` (two small
+launches) after each PReLU.
 """
 from typing import List, Optional, Union
 
@@ -32,13 +34,46 @@ class ScaleLinear(nn.Conv1d):
         return w, b
 
 
+class GlobalChannelLayerNorm(nn.Module):
+    """tcn.py:33-72 (parameter container: `beta`, `gamma` of shape [C, 1])."""
+
+    def __init__(self, dim: int, eps: float = 1e-05, elementwise_affine: bool = True) -> None:
+        super().__init__()
+        self.eps, self.normalized_dim, self.elementwise_affine = eps, dim, elementwise_affine
+        if elementwise_affine:
+            self.beta = nn.Parameter(th.zeros(dim, 1))
+            self.gamma = nn.Parameter(th.ones(dim, 1))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def extra_repr(self) -> str:
+        return f"{self.normalized_dim}, eps={self.eps}, elementwise_affine={self.elementwise_affine}"
+
+
 def _norm_layer(norm: str, channels: int) -> nn.Module:
+    """tcn.py:75-88"""
     if norm not in ("cLN", "IN", "gLN", "BN"):
         raise RuntimeError(f"Unsupported normalize layer: {norm}")
-    if norm != "BN":
-        raise RuntimeError(f"aps_b200: normalisation '{norm}' needs per-utterance statistics over time and is not "
-                           "implemented on the fused path; use norm='BN'")
-    return nn.BatchNorm1d(channels)
+    if norm == "cLN":
+        return nn.GroupNorm(1, channels)
+    if norm == "IN":
+        return nn.GroupNorm(channels, channels)
+    if norm == "BN":
+        return nn.BatchNorm1d(channels)
+    return GlobalChannelLayerNorm(channels)
+
+
+def _norm_pack(m: nn.Module):
+    """-> ("bn", (scale, shift)) folded eval affine, or ("utt", dict(gamma, beta, eps, per_channel))."""
+    if isinstance(m, nn.BatchNorm1d):
+        return "bn", _bn_affine(m)
+    if isinstance(m, nn.GroupNorm):
+        return "utt", dict(gamma=m.weight.detach() if m.affine else None, beta=m.bias.detach() if m.affine else None,
+                           eps=m.eps, per_channel=m.num_groups != 1)
+    g = m.gamma.detach().reshape(-1).contiguous() if m.elementwise_affine else None
+    b = m.beta.detach().reshape(-1).contiguous() if m.elementwise_affine else None
+    return "utt", dict(gamma=g, beta=b, eps=m.eps, per_channel=False)
 
 
 class Conv1dBlock(nn.Module):
@@ -134,9 +169,9 @@ class FreqConvTasNet(nn.Module):
                 w2, b2 = blk.conv2.packed()
                 C = blk.dconv.weight.shape[0]
                 pk["blocks"].append(dict(
-                    w1=w1, b1=b1, a1=blk.norm1[0].weight.detach(), bn1=_bn_affine(blk.norm1[1]),
+                    w1=w1, b1=b1, a1=blk.norm1[0].weight.detach(), n1=_norm_pack(blk.norm1[1]),
                     wd=blk.dconv.weight.detach().view(C, -1).t().contiguous(), bd=blk.dconv.bias.detach(),
-                    a2=blk.norm2[0].weight.detach(), bn2=_bn_affine(blk.norm2[1]), w2=w2, b2=b2,
+                    a2=blk.norm2[0].weight.detach(), n2=_norm_pack(blk.norm2[1]), w2=w2, b2=b2,
                     dil=blk.dilation, lpad=blk.pad if blk.cau else blk.pad // 2))
         if self.conv.skip_linear is not None:
             pk["skip"] = [lin.packed() for lin in self.conv.skip_linear]
@@ -171,9 +206,14 @@ class FreqConvTasNet(nn.Module):
             for _ in range(nblk):
                 d = pk["blocks"][bi]
                 bi += 1
-                h = self._lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=d["bn1"])
+                (k1, n1), (k2, n2) = d["n1"], d["n2"]
+                h = self._lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=n1 if k1 == "bn" else None)
+                if k1 == "utt":
+                    h = ops.utt_norm(h, N, T, inplace=True, **n1)
                 h = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
-                                 slope=d["a2"], post=d["bn2"])
+                                 slope=d["a2"], post=n2 if k2 == "bn" else None)
+                if k2 == "utt":
+                    h = ops.utt_norm(h, N, T, inplace=True, **n2)
                 x = self._lin(h, d["w2"], d["b2"], residual=x)
             outs.append(x)
         # mask head: PReLU then 1x1 conv then relu / sigmoid

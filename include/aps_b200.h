@@ -299,6 +299,19 @@ typedef struct aps_b200_attn_desc {
 } aps_b200_attn_desc;
 int aps_b200_mhsa_fwd(const aps_b200_attn_desc* desc, float* out, int64_t ld_out, void* stream);
 
+/* Per-utterance normalisation over time of token rows, row(n, t) = n*stride_n + t*stride_t:
+ * per_channel = 0: statistics over (channels, frames) of each utterance — nn.GroupNorm(1, C), i.e. "cLN"
+ * (aps/sse/bss/tcn.py:81-82), Normalize1d("LN") (aps/asr/base/component.py:95-96, LinearProj default,
+ * aps/asr/transformer/proj.py:42) and GlobalChannelLayerNorm "gLN" (tcn.py:33-72);
+ * per_channel = 1: statistics over frames of each (utterance, channel) — nn.GroupNorm(C, C), "IN" (tcn.py:83-84).
+ * out = (x - mean) / sqrt(var + eps) * gamma[c] + beta[c] (biased variance; gamma/beta may be NULL), then
+ * ReLU when relu != 0 (proj.py:54).  In place (out == x) is allowed.                                    */
+int64_t aps_b200_utt_norm_workspace_bytes(int64_t batch, int64_t num_frames, int64_t channels);
+int aps_b200_utt_norm_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
+                          int64_t stride_n, int64_t stride_t, int per_channel, const float* gamma,
+                          const float* beta, float eps, int relu, void* workspace, int64_t workspace_bytes,
+                          float* out, int64_t ld_out, void* stream);
+
 /* Time-domain separation objectives ----------------------------------------------------------
  * Si-SNR / SNR between every estimate and every reference of an utterance in ONE pass over the
  * waveforms (fp64 sums of x, s, x^2, s^2, x.s; closed-form objective).  out[n, e, r] is what

@@ -68,7 +68,67 @@ def objf_cases():
     save("objf_0", dict(N=N, S=S), **arrays)
 
 
+def norm_cases():
+    """Per-utterance normalisations over time: TCN with cLN / gLN / IN (tcn.py:75-88) and the transformer
+    encoder behind LinearProj(norm="LN") (proj.py:30-56, component.py:86-114)."""
+    import copy
+    from aps.asr.transformer.encoder import TransformerEncoder
+    from aps.sse.bss.tcn import FreqConvTasNet
+    from aps.transform import EnhTransform
+    th.set_num_threads(4)
+    for i, norm in enumerate(["cLN", "gLN", "IN"]):
+        g = th.Generator().manual_seed(630 + i)
+        ekw = dict(feats="spectrogram-log-cmvn", frame_len=128, frame_hop=64)
+        nkw = dict(in_features=65, num_bins=65, B=2, N=2, K=3, conv_channels=24, proj_channels=16, norm=norm,
+                   num_spks=2 if i == 0 else 1, non_linear="sigmoid" if i else "relu")
+        net = FreqConvTasNet(enh_transform=EnhTransform(**ekw), **nkw).eval()
+        with th.no_grad():
+            for name, prm in net.named_parameters():
+                if not name.startswith("enh_transform") and (prm.dim() <= 1 or name.endswith(("gamma", "beta"))):
+                    prm.add_(0.1 * th.randn(prm.shape, generator=g))
+        mix = wave(630 + i, 3, 2500)
+        with th.no_grad():
+            stft, _ = net.enh_transform.encode(mix, None)
+            feats = net.enh_transform(stft)
+            masks = net.mask_predict(feats)
+            net.training_mode = "time"
+            wav = net(mix)
+        wav = th.stack(wav) if isinstance(wav, list) else wav
+        arrays = dict(mix=mix, feats=feats, masks=masks, wav=wav)
+        arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})
+        save(f"tcn_{3 + i}", dict(enh=ekw, net=nkw), **arrays)
+    for i, (arch, norm) in enumerate([("xfmr", "LN"), ("cfmr", "BN")]):
+        g = th.Generator().manual_seed(560 + i)
+        ak = dict(att_dim=64, nhead=2, feedforward_dim=96, att_dropout=0.1, ffn_dropout=0.1, pre_norm=bool(i))
+        if arch == "cfmr":
+            ak["kernel_size"] = 15
+        cfg = dict(arch=arch, input_size=40, output_proj=-1, num_layers=2, proj="linear", proj_kwargs=dict(norm=norm),
+                   pose="abs" if i == 0 else "rel", pose_kwargs=dict() if i == 0 else dict(lradius=30, rradius=30),
+                   arch_kwargs=ak)
+        net = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+        with th.no_grad():
+            for name, buf in net.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+                if name.endswith("running_var"):
+                    buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+            for name, prm in net.named_parameters():
+                if name.endswith("bias") or "norm" in name:
+                    prm.add_(0.1 * th.randn(prm.shape, generator=g))
+        T = 53
+        x = th.randn(3, T, 40, generator=g)
+        lens = th.tensor([T, T - 8, T - 23])
+        with th.no_grad():
+            y, yl = net(x, lens.clone())
+        arrays = dict(x=x, lens=lens, y=y, ylens=yl)
+        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        save(f"enc_{7 + i}", cfg, **arrays)
+
+
 def main():
+    if "--only-norms" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return norm_cases()
     if "--only-objf" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         return objf_cases()
@@ -244,6 +304,7 @@ def main():
         arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})  # K: 2 MB each
         save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
     objf_cases()
+    norm_cases()
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)

@@ -16,7 +16,7 @@ def _sd(g, strip_enh=False):
 
 def _oracle_masks(cfg, g):
     n = cfg["net"]
-    return OT.tf_mask(_sd(g, True), g["feats"], n["N"], n["B"], n["num_spks"], "BN", n["non_linear"],
+    return OT.tf_mask(_sd(g, True), g["feats"], n["N"], n["B"], n["num_spks"], n.get("norm", "BN"), n["non_linear"],
                       n.get("causal", False), n.get("skip_residual", False))
 
 
