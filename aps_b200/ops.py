@@ -63,6 +63,10 @@ def _tc_ok(x: th.Tensor, w: th.Tensor, M: int, K: int, N: int) -> bool:
             and w.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and w.stride(1) == 1)
 
 
+def _tc_conv_ok(x: th.Tensor, Cin: int, Cout: int, M: int) -> bool:
+    return GEMM_ENGINE == "tc" and Cin % 32 == 0 and M >= 128 and Cout >= 32 and x.data_ptr() % 16 == 0
+
+
 def rows2d(x: th.Tensor) -> th.Tensor:
     """View `x` as [rows, cols] with unit column stride (copies only if it has to)."""
     x = x.reshape(-1, x.shape[-1])
@@ -81,11 +85,11 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
         out = th.empty((M, ncol), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, alpha, slope, leaky, residual, beta, post)
     if _tc_ok(x, weight, M, K, N):
-        (x_hi, x_lo), (w_hi, w_lo) = tf32_split(x), (cache.get(weight) if cache is not None else tf32_split(weight))
+        w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
         with th.cuda.device(dev):
-            _lib.check(_lib.load().aps_b200_linear_tc_fwd(x_hi.data_ptr(), x_lo.data_ptr(), M, K, x_hi.stride(0),
-                                                          w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e,
-                                                          out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
+            _lib.check(_lib.load().aps_b200_linear_tc_fwd(x.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
+                                                          w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(),
+                                                          out.stride(0), _lib.stream_ptr(dev)))
         return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
@@ -106,21 +110,15 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
     out = th.empty((B, OH, OW, Cout // 2 if act == "glu" else Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, slope, leaky)
     M, K = B * OH * OW, KH * KW * Cin
-    if (GEMM_ENGINE == "tc" and Cin % 4 == 0 and K >= 128 and M >= 128 and Cout >= 128 and act != "glu"
-            and x.data_ptr() % 16 == 0 and 8 * M * K <= (4 << 30)):      # patch matrices (hi + lo) capped at 4 GiB
-        # tensor-core path: fused im2col + TF32 split, then the tcgen05 GEMM on the patch matrices
-        patches = th.empty((2, M, K), dtype=th.float32, device=dev)
+    if _tc_conv_ok(x, Cin, Cout, M):
+        # tensor-core path: implicit im2col + TF32 split by the kernel's producer warps
         w2 = weight.view(Cout, K)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
-        lib = _lib.load()
         with th.cuda.device(dev):
-            st = _lib.stream_ptr(dev)
-            _lib.check(lib.aps_b200_im2col_tf32_split(x.data_ptr(), B, H, W, Cin, KH, KW, stride[0], stride[1], padding[0],
-                                                      padding[1], dilation[0], dilation[1], patches[0].data_ptr(),
-                                                      patches[1].data_ptr(), st))
-            _lib.check(lib.aps_b200_linear_tc_fwd(patches[0].data_ptr(), patches[1].data_ptr(), M, K, K, w_hi.data_ptr(),
-                                                  w_lo.data_ptr(), w_hi.stride(0), Cout, e, out.data_ptr(),
-                                                  out.shape[-1], st))
+            _lib.check(_lib.load().aps_b200_conv2d_nhwc_tc_fwd(x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(),
+                                                               w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
+                                                               padding[0], padding[1], dilation[0], dilation[1], e,
+                                                               out.data_ptr(), _lib.stream_ptr(dev)))
         return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv2d_nhwc_fwd(x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW,
@@ -130,7 +128,8 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
 
 
 def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0),
-                          output_padding=(0, 0), act: str = "none", leaky: float = 0.0) -> th.Tensor:
+                          output_padding=(0, 0), act: str = "none", leaky: float = 0.0,
+                          cache: Optional["SplitCache"] = None) -> th.Tensor:
     """x [B, H, W, Cin], weight [Cout, KH, KW, Cin] -> [B, OH, OW, Cout] (transposed convolution)."""
     dev = _lib.require_cuda(x, "conv input")
     B, H, W, Cin = x.shape
@@ -139,6 +138,14 @@ def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1,
     OW = (W - 1) * stride[1] - 2 * padding[1] + KW + output_padding[1]
     out = th.empty((B, OH, OW, Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, None, leaky)
+    if _tc_conv_ok(x, Cin, Cout, B * OH * OW):
+        w2 = weight.view(Cout, KH * KW * Cin)
+        w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
+        with th.cuda.device(dev):
+            _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_tc_fwd(
+                x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
+                padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
+        return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_fwd(
             x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW, stride[0], stride[1], padding[0], padding[1],

@@ -231,7 +231,7 @@ class DCCRN(nn.Module):
                 x = x + skips[i - 1] if self.connection == "sum" else _cat_complex(x, skips[i - 1])
             x = ops.conv_transpose2d_nhwc(x.contiguous(), w, b, stride=blk.stride, padding=blk.padding,
                                           output_padding=blk.output_padding,
-                                          act="none" if blk.last else "leaky_relu", leaky=0.01)
+                                          act="none" if blk.last else "leaky_relu", leaky=0.01, cache=self._splits)
         return x
 
     def _infer(self, mix: th.Tensor, mode: str):

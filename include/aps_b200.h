@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define APS_B200_ABI_VERSION 1
+#define APS_B200_ABI_VERSION 2
 
 /* library / device ------------------------------------------------------------------------ */
 int aps_b200_abi_version(void);
@@ -206,24 +206,33 @@ int aps_b200_linear_fwd(const float* x, int64_t rows, int64_t in_features, int64
                         const float* weight, int64_t ld_w, int64_t out_features,
                         const aps_b200_epilogue* epi, float* out, int64_t ld_out, void* stream);
 
-/* Tensor-core variant of aps_b200_linear_fwd (tcgen05.mma kind::tf32, accumulators in TMEM, operands
- * by TMA) with a 3xTF32 split: both operands are given as hi = rn_tf32(v) and lo = rn_tf32(v - hi)
- * (aps_b200_tf32_split; weights once, activations per call) and hi*hi + hi*lo + lo*hi is accumulated
- * in fp32.  Needs in_features % 4 == 0 and 16-byte aligned rows; hi and lo share the row stride.
- * Same epilogue contract as aps_b200_linear_fwd.                                              */
+/* Tensor-core engine (tcgen05.mma kind::tf32, double-buffered accumulators in TMEM, persistent 128 x BN
+ * tiles) with a 3xTF32 split: hi = rn_tf32(v), lo = rn_tf32(v - hi) and hi*hi + hi*lo + lo*hi accumulated in
+ * fp32.  WEIGHTS are passed pre-split (aps_b200_tf32_split, once per module; TMA loads them); ACTIVATIONS are
+ * passed as plain fp32 and are gathered + split inside the kernel by producer warps, so neither a hi/lo copy
+ * nor an im2col matrix of an activation is written to memory.  Same epilogue contract as aps_b200_linear_fwd.
+ * Needs in_features % 4 == 0 and 16-byte aligned rows (linear), Cin % 32 == 0 (convolutions).           */
 int aps_b200_tf32_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo,
                         int64_t ld_out, void* stream);
-/* im2col of x [B, H, W, Cin] (Cin % 4 == 0) fused with the TF32 split: hi / lo [B*OH*OW, KH*KW*Cin] patch
- * matrices in the column order of a [Cout, KH, KW, Cin] filter, ready for aps_b200_linear_tc_fwd
- * (the tensor-core path of aps_b200_conv2d_nhwc_fwd).                                          */
-int aps_b200_im2col_tf32_split(const float* x, int64_t batch, int64_t height, int64_t width,
-                               int64_t in_channels, int kernel_h, int kernel_w, int stride_h,
-                               int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float* hi,
-                               float* lo, void* stream);
-int aps_b200_linear_tc_fwd(const float* x_hi, const float* x_lo, int64_t rows, int64_t in_features,
-                           int64_t ld_x, const float* weight_hi, const float* weight_lo, int64_t ld_w,
+/* F.linear: aps/asr/transformer/impl.py:62-83, :388-393, :454-475; 1x1 convs of aps/sse/bss/tcn.py:112-159 */
+int aps_b200_linear_tc_fwd(const float* x, int64_t rows, int64_t in_features, int64_t ld_x,
+                           const float* weight_hi, const float* weight_lo, int64_t ld_w,
                            int64_t out_features, const aps_b200_epilogue* epi, float* out,
                            int64_t ld_out, void* stream);
+/* Conv2d as an implicit GEMM (same geometry / layouts as aps_b200_conv2d_nhwc_fwd; weight_hi / weight_lo are
+ * the split [Cout, KH*KW*Cin] filter): aps/asr/base/component.py:251-307, aps/sse/enh/dcunet.py:24-45      */
+int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                int64_t in_channels, const float* weight_hi, const float* weight_lo,
+                                int64_t out_channels, int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                int pad_h, int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
+                                float* out, void* stream);
+/* ConvTranspose2d as an implicit gather GEMM (as aps_b200_conv_transpose2d_nhwc_fwd): dcunet.py:48-70       */
+int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                          int64_t in_channels, const float* weight_hi,
+                                          const float* weight_lo, int64_t out_channels, int kernel_h,
+                                          int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                                          int out_pad_h, int out_pad_w, const aps_b200_epilogue* epi,
+                                          float* out, void* stream);
 
 /* Implicit-GEMM convolution on channels-last data: x [B, H, W, Cin], weight [Cout, KH, KW, Cin],
  * out [B, OH, OW, Cout] with OH = (H + 2 pad - dil (K-1) - 1) / stride + 1.  Replaces the
