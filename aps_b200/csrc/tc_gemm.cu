@@ -13,12 +13,12 @@
 // of an activation is ever written to HBM.
 //
 // One persistent CTA per SM (320 threads) walks 128 x BN output tiles; roles:
-//   warp 0    : TMA producer for W_hi / W_lo tiles (BN rows x 32 floats, 128-byte swizzle), mbarrier tx
-//   warp 1    : allocates TMEM (2 x BN columns: double-buffered accumulator) and issues the UMMAs
-//   warps 2-5 : epilogue — tcgen05.ld of the finished accumulator while the NEXT tile's MMAs run into the other
+//   warp 8    : TMA producer for W_hi / W_lo tiles (BN rows x BK floats, swizzled), mbarrier tx
+//   warp 9    : allocates TMEM (2 x BN columns: double-buffered accumulator) and issues the UMMAs
+//   warps 4-7 : epilogue — tcgen05.ld of the finished accumulator while the NEXT tile's MMAs run into the other
 //               buffer; 32x32 transposes through shared memory, bias / activation / GLU / affine / residual, coalesced
 //               128-byte row stores
-//   warps 6-9 : A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
+//   warps 0-3 : A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
 //               taps), hi/lo split in registers, st.shared into the same 128-byte-swizzled K-major layout TMA would
 //               write, fence.proxy.async, mbarrier arrive
 // Replaces the cuBLAS / cuDNN calls behind F.linear, 1x1 convolutions and Conv2d / ConvTranspose2d of the reference
@@ -36,10 +36,10 @@
 
 namespace apsb {
 
-constexpr int TC_BM = 128, TC_BK = 32;
+constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 320;
-constexpr int TC_PRODUCERS = 128;          // warps 6..9
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;
+constexpr int TC_PRODUCERS = 128;          // warps 0..3
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -52,9 +52,19 @@ __device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
 }
-// bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+// Wait for the phase with the given parity.  Fast path: one non-blocking test_wait — on B200 a try_wait costs ~300
+// cycles even when the phase is already complete (scripts/ubench/umma_rate.cu), which starves the tensor pipe when the
+// single MMA-issuing thread pays it twice per k-block.  Slow path: bounded try_wait spin; a protocol bug traps (CUDA
+// error) instead of hanging the GPU.
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -79,14 +89,16 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar))
                  : "memory");
 }
-// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart
+// shared-memory matrix descriptor: K-major operand whose rows are one swizzle span (SWZ = 128 or 64 bytes) wide,
+// 8-row groups 8*SWZ bytes apart (canonical layouts Swizzle<3,4,3> / Swizzle<2,4,3>)
+template <int SWZ>
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0, 14)
-    d |= (uint64_t)0 << 16;                           // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset [32, 46)
+    d |= (uint64_t)(SWZ == 128 ? 0 : 1) << 16;        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * SWZ) >> 4) << 32;            // stride byte offset [32, 46)
     d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+    d |= (uint64_t)(SWZ == 128 ? 2 : 4) << 61;        // layout type: SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -105,28 +117,166 @@ __device__ __forceinline__ float rn_tf32(float v) {
     return __uint_as_float(u);
 }
 
+// Activation resolved at compile time (a run-time switch inside the unrolled element loops would replicate tanhf / erff
+// dozens of times: the epilogue is instruction-issue bound, one warp per scheduler).
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v, float slope) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_SWISH) return __fdividef(v, 1.f + __expf(-v));
+    if (ACT == ACT_TANH) return tanhf(v);
+    if (ACT == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
+    if (ACT == ACT_PRELU || ACT == ACT_LEAKY) return v >= 0.f ? v : v * slope;
+    if (ACT == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    return v;
+}
+
+// 32 accumulator columns of one row (lane = row, the native TMEM layout): everything is 16-byte vector traffic on the
+// lane's own row — 8 LDG.128 of the residual (prefetched by the caller), 8 broadcast LDG.128 per per-column vector,
+// 8 STG.128 — about 250 instructions per 32 x 32 block instead of ~1500 for the transposed scalar form.
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue_vec(const uint32_t (&r)[32], const float4 (&res)[8], const Epilogue& e,
+                                                int n0, int N, bool row_ok, float* __restrict__ orow) {
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+        const int n = n0 + 4 * q4;
+        if (n < N) {                                  // N % 4 == 0 on this path
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = b4;
+            float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
+            if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            if (e.post_scale) {
+                ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+            }
+            if (ACT == ACT_PRELU) {
+                if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+            }
+            float4 o;
+            o.x = fmaf(e.beta, res[q4].x, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 0]) + b4.x, sl4.x), ps4.x, pt4.x) * e.alpha);
+            o.y = fmaf(e.beta, res[q4].y, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 1]) + b4.y, sl4.y), ps4.y, pt4.y) * e.alpha);
+            o.z = fmaf(e.beta, res[q4].z, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 2]) + b4.z, sl4.z), ps4.z, pt4.z) * e.alpha);
+            o.w = fmaf(e.beta, res[q4].w, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 3]) + b4.w, sl4.w), ps4.w, pt4.w) * e.alpha);
+            if (row_ok) *reinterpret_cast<float4*>(orow + 4 * q4) = o;
+        }
+    }
+}
+
 // How the A operand is gathered (host-filled; see aps_b200_gemm_a_desc)
 struct AGather {
     int mode;                 // 0 linear rows, 1 conv2d NHWC, 2 conv_transpose2d NHWC
     const float* x;
     long long ld;             // linear: floats between rows
     int H, W, Cin, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW;
+    // Transposed convolution with stride sh > 1 along H: output row oh only sees the taps kh with (oh + ph - kh) % sh == 0.
+    // The GEMM rows are therefore enumerated CLASS-MAJOR (all rows with oh % sh == 0 first, then oh % sh == 1, ...), so
+    // that a 128-row tile lies in one class and every role skips the k-blocks of the taps that are all-zero for it:
+    // the zero-insertion work of the reference's conv_transpose2d (half of it at stride 2) is never done.
+    int classes;              // sh (1 = plain row order)
+    long long class_start[4]; // first GEMM row of each class
+    int class_rows[4];        // output rows per image in each class
 };
+
+struct RowPos {
+    int nb, oh, ow;
+};
+
+// GEMM row m -> (image, output row, output column) for the convolution modes.  M < 2^31 (host check), so all of this
+// is 32-bit arithmetic: 64-bit integer divisions are emulated and would cost thousands of cycles per tile.
+__device__ __forceinline__ RowPos tc_decode_row(const AGather& a, unsigned m) {
+    RowPos r;
+    if (a.mode == 2 && a.classes > 1) {
+        int cls = 0;
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+            if (c < a.classes && m >= (unsigned)a.class_start[c]) cls = c;
+        const unsigned mm = m - (unsigned)a.class_start[cls];
+        const unsigned t = mm / (unsigned)a.OW;
+        r.ow = (int)(mm - t * (unsigned)a.OW);
+        const unsigned nb = t / (unsigned)a.class_rows[cls];
+        r.oh = (int)(t - nb * (unsigned)a.class_rows[cls]) * a.sh + cls;
+        r.nb = (int)nb;
+    } else {
+        const unsigned t = m / (unsigned)a.OW;
+        r.ow = (int)(m - t * (unsigned)a.OW);
+        const unsigned nb = t / (unsigned)a.OH;
+        r.oh = (int)(t - nb * (unsigned)a.OH);
+        r.nb = (int)nb;
+    }
+    return r;
+}
+// class of a tile (rows m_first .. m_last), -1 if it straddles two classes or classes are off
+__device__ __forceinline__ int tc_tile_class(const AGather& a, unsigned m_first, unsigned m_last) {
+    if (a.mode != 2 || a.classes <= 1) return -1;
+    int c0 = 0, c1 = 0;
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+        if (c < a.classes) {
+            if (m_first >= (unsigned)a.class_start[c]) c0 = c;
+            if (m_last >= (unsigned)a.class_start[c]) c1 = c;
+        }
+    return c0 == c1 ? c0 : -1;
+}
+// does tap (kh, kw) contribute to the rows of class `cls`?
+__device__ __forceinline__ bool tc_tap_valid(const AGather& a, int cls, int tap) {
+    if (cls < 0) return true;
+    const int kh = tap / a.KW;
+    return ((cls + a.ph - kh) % a.sh) == 0;
+}
+// output row index (in units of rows of the [.., Cout] output) of GEMM row m
+__device__ __forceinline__ long long tc_out_row(const AGather& a, unsigned m) {
+    if (a.mode == 2 && a.classes > 1) {
+        const RowPos r = tc_decode_row(a, m);
+        return ((long long)r.nb * a.OH + r.oh) * a.OW + r.ow;
+    }
+    return m;
+}
 
 struct TcParams {
     int M, N, K;
     int tiles_n;
-    long long tiles;
+    unsigned tiles;
     AGather a;
     Epilogue e;
+    int epi_vec;                 // output / residual rows are 16-byte aligned and N % 4 == 0 (N % 8 for GLU)
+    int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
+    unsigned long long* trace;   // debug builds (-DAPSB_TC_TRACE): [0] = event counter, then (event << 48 | clock) words
 };
 
+// Pipeline timeline of CTA 0 for tuning (compiled out unless APSB_TC_TRACE is defined).
+#ifdef APSB_TC_TRACE
+static unsigned long long* g_tc_trace = nullptr;
+static int g_tc_trace_cap = 0;
+#define TC_TRACE_WORDS 1024
+#define TC_TR(ev)                                                                                        \
+    do {                                                                                                 \
+        if (p.trace && blockIdx.x == 0 && (!(p.dbg & 16) || (ev) == 3 || (ev) == 9 || (ev) == 4 || (ev) == 6)) {                   \
+            const unsigned i_ = atomicAdd(reinterpret_cast<unsigned*>(tr_smem), 1u);                     \
+            if (i_ + 1 < TC_TRACE_WORDS)                                                                 \
+                tr_smem[1 + i_] = ((unsigned long long)(ev) << 48) | (clock64() & 0xFFFFFFFFFFFFull);    \
+        }                                                                                                \
+    } while (0)
+#else
+#define TC_TR(ev) do { } while (0)
+#endif
+
+// BN = 256 uses 16-float k-blocks (64-byte swizzle) so that FOUR 48 KB stages fit: with 32-float blocks only two
+// 96 KB stages fit and neither the TMA weight loads nor the A gathers can run far enough ahead of the MMAs.
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr int B_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int BK = BN == 256 ? 16 : 32;
+    static constexpr int SWZ = BK * 4;                                          // bytes per operand row = swizzle span
+    static constexpr int STAGES = BN == 128 ? 3 : 4;
+    static constexpr int A_BYTES = TC_BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;   // + barriers + alignment slack
+#ifdef APSB_TC_TRACE
+    static constexpr int TRACE_BYTES = 8 * 1024;
+    static constexpr int EPI_ALLOC = 0;                                        // trace builds alias the epilogue tiles
+#else
+    static constexpr int TRACE_BYTES = 0;
+    static constexpr int EPI_ALLOC = EPI_BYTES;
+#endif
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_ALLOC + 256 + 1024 + TRACE_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -135,28 +285,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ TcParams p) {
     using C = TcCfg<BN>;
-    constexpr int S = C::STAGES;
+    constexpr int S = C::STAGES, BK = C::BK, SWZ = C::SWZ, A_BYTES = C::A_BYTES;
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
-    float* epi_tiles = reinterpret_cast<float*>(base + S * C::STAGE_BYTES);
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(base + S * C::STAGE_BYTES + C::EPI_BYTES);
+    uint8_t* after_stages = base + S * C::STAGE_BYTES;
+#ifdef APSB_TC_TRACE
+    float* epi_tiles = reinterpret_cast<float*>(base);   // trace builds: fallback epilogue not supported (aliases stage 0)
+#else
+    float* epi_tiles = reinterpret_cast<float*>(after_stages);
+#endif
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(after_stages + C::EPI_ALLOC);
     uint64_t* full_b = full_a + S;
     uint64_t* empty = full_b + S;
     uint64_t* tmem_full = empty + S;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+#ifdef APSB_TC_TRACE
+    unsigned long long* tr_smem = reinterpret_cast<unsigned long long*>(after_stages + C::EPI_ALLOC + 256);
+    if (threadIdx.x == 0) tr_smem[0] = 0;
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    // k-blocks are walked tap by tap (convolutions: a k-block never crosses a (kh, kw) tap since Cin % 32 == 0) so that
+    // a transposed-convolution tile can skip the taps that are zero for its row class; a linear layer is one "tap"
+    const int num_taps = p.a.mode == 0 ? 1 : p.a.KH * p.a.KW;
+    const int kb_per_tap = p.a.mode == 0 ? (p.K + BK - 1) / BK : p.a.Cin / BK;
+    auto tile_class = [&](unsigned tile) {
+        const unsigned m_first = (tile / (unsigned)p.tiles_n) * TC_BM;
+        const unsigned m_last = m_first + TC_BM - 1 < (unsigned)p.M ? m_first + TC_BM - 1 : (unsigned)p.M - 1;
+        return tc_tile_class(p.a, m_first, m_last);
+    };
 
-    if (warp == 0 && lane == 0) {
+    // Role -> warp assignment: the SM's schedulers prefer the HIGHEST warp id among eligible warps of a sub-partition
+    // (warp % 4), so the two single-thread, latency-critical roles get the top ids: warp 9 issues the MMAs, warp 8 the
+    // TMA loads; warps 4-7 are the epilogue (TMEM lane quarter = warp % 4), warps 0-3 the A producers.
+    if (warp == WARP_TMA && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
     }
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                tc_mbar_init(full_a + s, TC_PRODUCERS);
+                tc_mbar_init(full_a + s, TC_PRODUCERS / 32);
                 tc_mbar_init(full_b + s, 1);
                 tc_mbar_init(empty + s, 1);
             }
@@ -176,80 +346,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TR(9);
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const int n_blk = (int)(tile % p.tiles_n);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    tc_mbar_wait(empty + s, ph ^ 1);
-                    uint8_t* st = base + s * C::STAGE_BYTES + 2 * TC_A_BYTES;
-                    tc_mbar_expect_tx(full_b + s, 2 * C::B_BYTES);
-                    tc_tma_load_2d(&tmB, full_b + s, st, kb * TC_BK, n_blk * BN);
-                    tc_tma_load_2d(&tmBlo, full_b + s, st + C::B_BYTES, kb * TC_BK, n_blk * BN);
+            for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int n_blk = (int)(tile % (unsigned)p.tiles_n);
+                const int cls = tile_class(tile);
+                for (int tap = 0; tap < num_taps; ++tap) {
+                    if (!tc_tap_valid(p.a, cls, tap)) continue;
+                    for (int cb = 0; cb < kb_per_tap; ++cb, ++it) {
+                        const int kb = tap * kb_per_tap + cb;
+                        const int s = it % S;
+                        const uint32_t ph = (it / S) & 1;
+                        tc_mbar_wait(empty + s, ph ^ 1);
+                        uint8_t* st = base + s * C::STAGE_BYTES + 2 * A_BYTES;
+#ifdef APSB_TC_TRACE
+                        if (p.dbg & 2) {
+                            tc_mbar_arrive(full_b + s);
+                            continue;
+                        }
+#endif
+                        tc_mbar_expect_tx(full_b + s, 2 * C::B_BYTES);
+                        tc_tma_load_2d(&tmB, full_b + s, st, kb * BK, n_blk * BN);
+                        tc_tma_load_2d(&tmBlo, full_b + s, st + C::B_BYTES, kb * BK, n_blk * BN);
+                        TC_TR(1);
+                    }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, tcount = 0;
-            for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
+            for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1;
                 tc_mbar_wait(tmem_empty + buf, ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int cls = tile_class(tile);
+                uint32_t first = 1;
+                for (int tap = 0; tap < num_taps; ++tap) {
+                  if (!tc_tap_valid(p.a, cls, tap)) continue;
+                  for (int cb = 0; cb < kb_per_tap; ++cb, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     tc_mbar_wait(full_a + s, ph);
+                    TC_TR(11);
                     tc_mbar_wait(full_b + s, ph);
                     tc_fence_after();
+                    TC_TR(2);
                     const uint32_t sa = s_u32(base + s * C::STAGE_BYTES);
-                    const uint32_t sal = sa + TC_A_BYTES, sb = sa + 2 * TC_A_BYTES, sbl = sb + C::B_BYTES;
+                    const uint32_t sal = sa + A_BYTES, sb = sa + 2 * A_BYTES, sbl = sb + C::B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t da = tc_smem_desc(sa + k * 32), dal = tc_smem_desc(sal + k * 32);
-                        const uint64_t db = tc_smem_desc(sb + k * 32), dbl = tc_smem_desc(sbl + k * 32);
-                        tc_mma_tf32(d_tmem, da, db, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t da = tc_smem_desc<SWZ>(sa + k * 32), dal = tc_smem_desc<SWZ>(sal + k * 32);
+                        const uint64_t db = tc_smem_desc<SWZ>(sb + k * 32), dbl = tc_smem_desc<SWZ>(sbl + k * 32);
+                        tc_mma_tf32(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
                         tc_mma_tf32(d_tmem, da, dbl, idesc, 1);
                         tc_mma_tf32(d_tmem, dal, db, idesc, 1);
                     }
+                    first = 0;
                     tc_commit(empty + s);          // frees the stage once the MMAs above have read it
+                  }
                 }
                 tc_commit(tmem_full + buf);        // accumulator complete
+                TC_TR(3);
             }
         }
-    } else if (warp < 6) {
-        // ================= epilogue warps 2..5: TMEM lane quarter = warp % 4 =================
-        // A 32x32 block comes out of TMEM with lane = row; it is transposed through a padded shared tile so that
-        // lane = COLUMN afterwards: bias / residual loads and the output stores are full 128-byte rows.
+    } else if (warp >= 4) {
+        // ================= epilogue warps 4..7: TMEM lane quarter = warp % 4 =================
+        // Fast path (p.epi_vec: 16-byte aligned output / residual rows, N % 4 == 0): lane = row straight out of TMEM,
+        // vector loads / stores on the lane's own row.  Fallback (e.g. N = 257 mask rows): the 32x32 block is transposed
+        // through a padded shared tile so that lane = column and the scalar accesses are still 128-byte rows.
         const int q = warp & 3;
-        float* tile_s = epi_tiles + (warp - 2) * (32 * 33);
+        float* tile_s = epi_tiles + (warp - 4) * (32 * 33);
         const Epilogue& e = p.e;
+        const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
-        for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
-            const int n_blk = (int)(tile % p.tiles_n);
-            const long long m_blk = tile / p.tiles_n;
+        for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
+            const int n_blk = (int)(tile % (unsigned)p.tiles_n);
+            const unsigned m_blk = tile / (unsigned)p.tiles_n;
             const uint32_t buf = tcount & 1;
-            tc_mbar_wait(tmem_full + buf, (tcount >> 1) & 1);
+            if (lane == 0) tc_mbar_wait(tmem_full + buf, (tcount >> 1) & 1);
+            __syncwarp();
             tc_fence_after();
-            const long long m0 = m_blk * TC_BM + q * 32;
+            if (threadIdx.x == 128) TC_TR(4);
+            const long long m0 = (long long)m_blk * TC_BM + q * 32;
             const int ncols = min(BN, p.N - n_blk * BN);
             const int nchunks = (ncols + 31) >> 5;
             const long long rows_ll = (long long)p.M - m0;
             const int rows = rows_ll >= 32 ? 32 : (rows_ll > 0 ? (int)rows_ll : 0);
+            const bool row_ok = lane < rows;
+            const long long mrow = row_ok ? tc_out_row(p.a, (unsigned)(m0 + lane)) : 0;   // row of the output / residual matrices
+            // residual of the lane's row, one chunk ahead (vector path)
+            float4 res_nxt[8];
+            auto fetch_res = [&](int ch, float4 (&dst)[8]) {
+                const int n0 = n_blk * BN + ch * 32;
+                const bool ok = p.epi_vec && e.res != nullptr && !glu && row_ok;
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4)
+                    dst[q4] = (ok && n0 + 4 * q4 < p.N) ? __ldg(reinterpret_cast<const float4*>(e.res + mrow * e.ldres + n0) + q4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            fetch_res(0, res_nxt);
 #pragma unroll 1
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int c0 = ch * 32;
+                const int n0 = n_blk * BN + c0;
                 uint32_t r[32];
+                float4 res_cur[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) res_cur[j] = res_nxt[j];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -262,48 +475,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                       "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr)
                     : "memory");
+                if (ch + 1 < nchunks) fetch_res(ch + 1, res_nxt);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ch == nchunks - 1) {           // last read of this accumulator buffer: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
+                    if (threadIdx.x == 128) TC_TR(5);
                 }
-                __syncwarp();
+                if (p.epi_vec) {
+                    if (glu) {
+                        // columns (2j, 2j+1) of the lane's row -> output column j; 16 outputs = 4 vector stores
+                        float* orow = e.out + mrow * e.ldo + (n0 >> 1);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                const int n = n_blk * BN + c0 + lane;             // this lane's column from here on
-                const bool nok = n < p.N;
-                const float bias = (e.bias && nok) ? __ldg(e.bias + n) : 0.f;
-                if (e.act == ACT_GLU) {
-                    const int no = n >> 1;
-                    for (int rr = 0; rr < rows; ++rr) {
-                        const float v = tile_s[rr * 33 + lane] + bias;
-                        const float g = __shfl_down_sync(0xffffffffu, v, 1);
-                        if (!(lane & 1) && n + 1 < p.N) {
-                            const long long m = m0 + rr;
-                            float o = e.alpha * (v * (1.f / (1.f + __expf(-g))));
-                            if (e.res) o = fmaf(e.beta, __ldg(e.res + m * e.ldres + no), o);
-                            e.out[m * e.ldo + no] = o;
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int n = n0 + 8 * q4;
+                            if (n < p.N) {         // N % 8 == 0 on this path
+                                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+                                if (e.bias) {
+                                    ba = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                                    bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + 4));
+                                }
+                                auto gl = [&](uint32_t v, float bv, uint32_t g, float bg) {
+                                    return e.alpha * ((__uint_as_float(v) + bv) * (1.f / (1.f + __expf(-(__uint_as_float(g) + bg)))));
+                                };
+                                float4 o;
+                                o.x = gl(r[8 * q4 + 0], ba.x, r[8 * q4 + 1], ba.y);
+                                o.y = gl(r[8 * q4 + 2], ba.z, r[8 * q4 + 3], ba.w);
+                                o.z = gl(r[8 * q4 + 4], bb.x, r[8 * q4 + 5], bb.y);
+                                o.w = gl(r[8 * q4 + 6], bb.z, r[8 * q4 + 7], bb.w);
+                                if (row_ok) {
+                                    if (e.res) {
+                                        const float4 rv = __ldg(reinterpret_cast<const float4*>(e.res + mrow * e.ldres + (n0 >> 1)) + q4);
+                                        o.x = fmaf(e.beta, rv.x, o.x); o.y = fmaf(e.beta, rv.y, o.y);
+                                        o.z = fmaf(e.beta, rv.z, o.z); o.w = fmaf(e.beta, rv.w, o.w);
+                                    }
+                                    *reinterpret_cast<float4*>(orow + 4 * q4) = o;
+                                }
+                            }
                         }
+                    } else {
+                        float* orow = e.out + mrow * e.ldo + n0;
+#define TC_EPI_CASE(A) \
+    case A: tc_epilogue_vec<A>(r, res_cur, e, n0, p.N, row_ok, orow); break;
+                        switch (e.act) {
+                            TC_EPI_CASE(ACT_RELU)
+                            TC_EPI_CASE(ACT_SWISH)
+                            TC_EPI_CASE(ACT_TANH)
+                            TC_EPI_CASE(ACT_SIGMOID)
+                            TC_EPI_CASE(ACT_PRELU)
+                            TC_EPI_CASE(ACT_LEAKY)
+                            TC_EPI_CASE(ACT_GELU)
+                            default: tc_epilogue_vec<ACT_NONE>(r, res_cur, e, n0, p.N, row_ok, orow);
+                        }
+#undef TC_EPI_CASE
                     }
                 } else {
-                    const float ps = (e.post_scale && nok) ? __ldg(e.post_scale + n) : 1.f;
-                    const float pt = (e.post_scale && nok) ? __ldg(e.post_shift + n) : 0.f;
-                    const float slope =
-                        (e.act == ACT_PRELU && nok) ? __ldg(e.slope + (long long)n * e.slope_stride) : e.leak;
-                    // rows in batches of 8: the eight residual loads are in flight together
-                    for (int r0 = 0; r0 < rows; r0 += 8) {
-                        float v8[8], res8[8];
+                    // ---- transposed scalar fallback (unaligned rows) ----
+                    __syncwarp();
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int rr = r0 + u;
-                            v8[u] = tile_s[min(rr, 31) * 33 + lane] + bias;
-                            res8[u] = (e.res && nok && rr < rows) ? __ldg(e.res + (m0 + rr) * e.ldres + n) : 0.f;
+                    for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int n = n0 + lane;                          // this lane's column from here on
+                    const bool nok = n < p.N;
+                    const float bias = (e.bias && nok) ? __ldg(e.bias + n) : 0.f;
+                    if (glu) {
+                        const int no = n >> 1;
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const float v = tile_s[rr * 33 + lane] + bias;
+                            const float g = __shfl_down_sync(0xffffffffu, v, 1);
+                            if (!(lane & 1) && n + 1 < p.N) {
+                                const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
+                                float o = e.alpha * (v * (1.f / (1.f + __expf(-g))));
+                                if (e.res) o = fmaf(e.beta, __ldg(e.res + m * e.ldres + no), o);
+                                e.out[m * e.ldo + no] = o;
+                            }
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            float v = v8[u];
+                    } else {
+                        const float ps = (e.post_scale && nok) ? __ldg(e.post_scale + n) : 1.f;
+                        const float pt = (e.post_scale && nok) ? __ldg(e.post_shift + n) : 0.f;
+                        const float slope =
+                            (e.act == ACT_PRELU && nok) ? __ldg(e.slope + (long long)n * e.slope_stride) : e.leak;
+#pragma unroll 4
+                        for (int rr = 0; rr < rows; ++rr) {
+                            float v = tile_s[rr * 33 + lane] + bias;
                             switch (e.act) {
                                 case ACT_RELU: v = fmaxf(v, 0.f); break;
                                 case ACT_SWISH: v = __fdividef(v, 1.f + __expf(-v)); break;
@@ -315,99 +570,195 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                 default: break;
                             }
                             v = fmaf(v, ps, pt) * e.alpha;
-                            v = fmaf(e.beta, res8[u], v);
-                            if (nok && r0 + u < rows) e.out[(m0 + r0 + u) * e.ldo + n] = v;
+                            if (nok) {
+                                const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
+                                if (e.res) v = fmaf(e.beta, __ldg(e.res + m * e.ldres + n), v);
+                                e.out[m * e.ldo + n] = v;
+                            }
                         }
                     }
+                    __syncwarp();                  // tile_s is reused by the next chunk
                 }
-                __syncwarp();                      // tile_s is reused by the next chunk
             }
+            if (threadIdx.x == 128) TC_TR(6);
         }
     } else {
-        // ================= A producers (warps 6..9) =================
-        // thread -> 16-byte chunk c of rows rg, rg + 16, ..., rg + 112: a warp instruction reads 4 full 128-byte rows
-        const int pt = threadIdx.x - 192;
-        const int c = pt & 7, rg = pt >> 3;
+        // ================= A producers (warps 0..3) =================
+        // thread -> 16-byte chunk c of rows rg, rg + RSTEP, ...: a warp instruction reads whole SWZ-byte row segments.
+        // The gather for k-block i+1 is issued BEFORE block i is split and stored, so the L2 round trip is hidden.
+        constexpr int CPR = BK / 4;                 // 16-byte chunks per operand row
+        constexpr int RSTEP = TC_PRODUCERS / CPR;   // rows covered by one pass of the 128 producer threads
+        constexpr int RPT = TC_BM / RSTEP;          // rows per thread (= CPR)
+        const int pt = threadIdx.x;
+        const int c = pt % CPR, rg = pt / CPR;
         const AGather& a = p.a;
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            const long long m_blk = tile / p.tiles_n;
-            // per-row bases for this tile
-            const float* rowp[8];      // linear: row pointer; conv: image base of the row's batch index
-            int r_a[8], r_b[8];        // conv: ih0 / iw0;  tconv: oh + ph / ow + pw
+        const float* rowp[RPT];     // linear: row pointer; conv: image base of the row's batch index; null: row >= M
+        int r_a[RPT], r_b[RPT];     // conv: ih0 / iw0;  tconv: oh + ph / ow + pw
+        auto set_tile = [&](unsigned tile) {
+            const unsigned m_blk = tile / (unsigned)p.tiles_n;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const long long m = m_blk * TC_BM + rg + 16 * i;
-                if (m >= p.M) {
-                    rowp[i] = nullptr; r_a[i] = 0; r_b[i] = 0;
+            for (int i = 0; i < RPT; ++i) {
+                const unsigned m = m_blk * TC_BM + rg + RSTEP * i;
+                r_a[i] = 0; r_b[i] = 0;
+                if (m >= (unsigned)p.M) {
+                    rowp[i] = nullptr;
                 } else if (a.mode == 0) {
-                    rowp[i] = a.x + m * a.ld; r_a[i] = 0; r_b[i] = 0;
+                    rowp[i] = a.x + (long long)m * a.ld;
                 } else {
-                    const int ow = (int)(m % a.OW);
-                    const long long t = m / a.OW;
-                    const int oh = (int)(t % a.OH);
-                    const long long nb = t / a.OH;
-                    rowp[i] = a.x + nb * a.H * a.W * a.Cin;
-                    if (a.mode == 1) { r_a[i] = oh * a.sh - a.ph; r_b[i] = ow * a.sw - a.pw; }
-                    else             { r_a[i] = oh + a.ph;        r_b[i] = ow + a.pw; }
+                    const RowPos rp = tc_decode_row(a, m);
+                    rowp[i] = a.x + (long long)rp.nb * a.H * a.W * a.Cin;
+                    if (a.mode == 1) { r_a[i] = rp.oh * a.sh - a.ph; r_b[i] = rp.ow * a.sw - a.pw; }
+                    else             { r_a[i] = rp.oh + a.ph;        r_b[i] = rp.ow + a.pw; }
                 }
             }
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                const int k = kb * TC_BK + c * 4;
-                float4 v[8];
-                if (a.mode == 0) {
+        };
+        // Gather of one k-block into registers.  Plain (L1-allocating) loads on purpose: L1 merges a warp's 16-byte lane
+        // requests into 128-byte line requests and serves the kw-overlap of neighbouring taps; both L1-bypassing forms
+        // that were tried (ld.global.nc.L1::no_allocate, cp.async.cg into a shared-memory ring) were 15-50 % slower.
+        auto gather = [&](int kb, float4 (&v)[RPT]) {
+            const int k = kb * BK + c * 4;
+            if (a.mode == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[i] = (rowp[i] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + k))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    // Cin % 32 == 0: the whole k-block lies inside one (kh, kw) tap
-                    const int k0 = kb * TC_BK;
-                    const int tap = k0 / a.Cin, cc = k0 - tap * a.Cin + c * 4;
-                    const int kw = tap % a.KW, kh = tap / a.KW;
+                for (int i = 0; i < RPT; ++i)
+                    v[i] = (rowp[i] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                // Cin % 32 == 0: the whole k-block lies inside one (kh, kw) tap
+                const int k0 = kb * BK;
+                const int tap = k0 / a.Cin, cc = k0 - tap * a.Cin + c * 4;
+                const int kw = tap % a.KW, kh = tap / a.KW;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int ih, iw;
-                        bool ok = rowp[i] != nullptr && k < p.K;
-                        if (a.mode == 1) {
-                            ih = r_a[i] + kh * a.dh;
-                            iw = r_b[i] + kw * a.dw;
-                            ok = ok && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-                        } else {
-                            const int nh = r_a[i] - kh, nw = r_b[i] - kw;
-                            ok = ok && nh >= 0 && nw >= 0 && (nh % a.sh) == 0 && (nw % a.sw) == 0;
-                            ih = nh / a.sh;
-                            iw = nw / a.sw;
-                            ok = ok && ih < a.H && iw < a.W;
-                        }
-                        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(rowp[i] + ((long long)ih * a.W + iw) * a.Cin + cc))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < RPT; ++i) {
+                    int ih, iw;
+                    bool ok = rowp[i] != nullptr && k < p.K;
+                    if (a.mode == 1) {
+                        ih = r_a[i] + kh * a.dh;
+                        iw = r_b[i] + kw * a.dw;
+                        ok = ok && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+                    } else {
+                        const int nh = r_a[i] - kh, nw = r_b[i] - kw;
+                        ok = ok && nh >= 0 && nw >= 0;
+                        // strides 1 and 2 (every reference model) without integer divisions
+                        if (a.sh == 1) ih = nh;
+                        else if (a.sh == 2) { ok = ok && !(nh & 1); ih = nh >> 1; }
+                        else { ok = ok && (nh % a.sh) == 0; ih = nh / a.sh; }
+                        if (a.sw == 1) iw = nw;
+                        else if (a.sw == 2) { ok = ok && !(nw & 1); iw = nw >> 1; }
+                        else { ok = ok && (nw % a.sw) == 0; iw = nw / a.sw; }
+                        ok = ok && ih < a.H && iw < a.W;
                     }
+                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(rowp[i] + ((long long)ih * a.W + iw) * a.Cin + cc))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                tc_mbar_wait(empty + s, ph ^ 1);   // loads above are already in flight
-                uint8_t* st = base + s * C::STAGE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rg + 16 * i;
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                    float4 h, l;
-                    h.x = rn_tf32(v[i].x); l.x = rn_tf32(v[i].x - h.x);
-                    h.y = rn_tf32(v[i].y); l.y = rn_tf32(v[i].y - h.y);
-                    h.z = rn_tf32(v[i].z); l.z = rn_tf32(v[i].z - h.z);
-                    h.w = rn_tf32(v[i].w); l.w = rn_tf32(v[i].w - h.w);
-                    *reinterpret_cast<float4*>(st + off) = h;
-                    *reinterpret_cast<float4*>(st + TC_A_BYTES + off) = l;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
-                tc_mbar_arrive(full_a + s);
             }
+        };
+        constexpr int D = BK == 16 ? 3 : 2;     // k-blocks of gathers in flight (registers)
+        // iterator over the (tile, tap, k-block) sequence of this CTA, skipping taps that are zero for the tile's class
+        unsigned ltile = blockIdx.x;
+        int ltap = 0, lcb = 0, lcls = -1;
+        bool lfresh = true;                     // the tile's rows have not been decoded yet
+        auto seek = [&]() {                     // move (ltile, ltap) to the next valid tap; false at the end
+            while (ltile < p.tiles) {
+                if (lfresh) lcls = tile_class(ltile);
+                while (ltap < num_taps && !tc_tap_valid(a, lcls, ltap)) ++ltap;
+                if (ltap < num_taps) return true;
+                ltile += gridDim.x;
+                ltap = 0;
+                lcb = 0;
+                lfresh = true;
+            }
+            return false;
+        };
+        float4 ring[D][RPT];
+        auto gather_next = [&](float4 (&dst)[RPT]) {
+            if (!seek()) return false;
+            if (lfresh) {
+                set_tile(ltile);
+                lfresh = false;
+            }
+            gather(ltap * kb_per_tap + lcb, dst);
+            if (++lcb == kb_per_tap) {
+                lcb = 0;
+                ++ltap;
+            }
+            return true;
+        };
+        bool live[D];
+#ifdef APSB_TC_TRACE
+        long long acc_wait = 0, acc_store = 0, acc_gather = 0;
+#endif
+#pragma unroll
+        for (int d = 0; d < D; ++d) live[d] = gather_next(ring[d]);
+        for (long long it0 = 0;; it0 += D) {
+            bool any = false;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const long long it = it0 + d;
+                if (live[d]) {
+                    any = true;
+                    const int s = (int)(it % S);
+                    const uint32_t ph = (uint32_t)(it / S) & 1;
+#ifdef APSB_TC_TRACE
+                    const long long c0_ = clock64();
+#endif
+                    if (lane == 0) tc_mbar_wait(empty + s, ph ^ 1);   // one poller per warp
+                    __syncwarp();
+                    if (pt == 0) TC_TR(8);
+#ifdef APSB_TC_TRACE
+                    const long long c1_ = clock64();
+#endif
+                    uint8_t* st = base + s * C::STAGE_BYTES;
+#ifdef APSB_TC_TRACE
+                    if (!(p.dbg & 1))
+#endif
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        const int r = rg + RSTEP * i;
+                        const int sw = SWZ == 128 ? (r & 7) : ((r >> 1) & 3);
+                        const uint32_t off = (uint32_t)r * (uint32_t)SWZ + (uint32_t)((c ^ sw) << 4);
+                        const float4 v = ring[d][i];
+                        // lo = v - hi is exact; the tensor core drops its low mantissa bits itself (tf32 operand)
+                        float4 h, l;
+                        h.x = rn_tf32(v.x); l.x = v.x - h.x;
+                        h.y = rn_tf32(v.y); l.y = v.y - h.y;
+                        h.z = rn_tf32(v.z); l.z = v.z - h.z;
+                        h.w = rn_tf32(v.w); l.w = v.w - h.w;
+                        *reinterpret_cast<float4*>(st + off) = h;
+                        *reinterpret_cast<float4*>(st + A_BYTES + off) = l;
+                    }
+#ifdef APSB_TC_TRACE
+                    if (!(p.dbg & 4))
+#endif
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive(full_a + s);      // one arrival per producer warp
+                    if (pt == 0) TC_TR(7);
+#ifdef APSB_TC_TRACE
+                    const long long c2_ = clock64();
+                    acc_wait += c1_ - c0_;
+                    acc_store += c2_ - c1_;
+                    if (p.dbg & 8) { live[d] = seek(); if (live[d]) { if (++lcb == kb_per_tap) { lcb = 0; ++ltap; } } } else
+#endif
+                    live[d] = gather_next(ring[d]);
+#ifdef APSB_TC_TRACE
+                    acc_gather += clock64() - c2_;
+#endif
+                }
+            }
+            if (!any) break;
         }
+#ifdef APSB_TC_TRACE
+        if (pt == 0 && p.trace && blockIdx.x == 0) {
+            tr_smem[1020] = acc_wait; tr_smem[1021] = acc_store; tr_smem[1022] = acc_gather;
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+#ifdef APSB_TC_TRACE
+    if (p.trace && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < TC_TRACE_WORDS; i += TC_THREADS) p.trace[i] = tr_smem[i];
+#endif
+    if (warp == WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS)
                      : "memory");
@@ -452,24 +803,26 @@ static EncodeTiledFn encode_fn() {
 struct MapKey {
     const void* ptr;
     long long rows, cols, ld;
-    int box_rows;
+    int box_rows, box_cols;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         h = h * 1000003u ^ std::hash<long long>()(k.rows * 131 + k.cols);
-        h = h * 1000003u ^ std::hash<long long>()(k.ld * 7 + k.box_rows);
+        h = h * 1000003u ^ std::hash<long long>()(k.ld * 7 + k.box_rows + 1024 * k.box_cols);
         return h;
     }
 };
 
-static int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_rows,
+                    int box_cols) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, rows, cols, ld, box_rows};
+    const MapKey key{ptr, rows, cols, ld, box_rows, box_cols};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -482,10 +835,11 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
     APSB_CHECK_ARG(fn, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     APSB_CHECK_ARG(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
     std::lock_guard<std::mutex> g(mu);
@@ -499,8 +853,8 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
                      const Epilogue& e, cudaStream_t st) {
     using C = TcCfg<BN>;
     CUtensorMap tB, tBl;
-    if (int rc = make_map(&tB, W, N, K, ldw, BN)) return rc;
-    if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN)) return rc;
+    if (int rc = make_map(&tB, W, N, K, ldw, BN, C::BK)) return rc;
+    if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN, C::BK)) return rc;
     static bool attr = false;
     if (!attr) {
         APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -509,28 +863,52 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     TcParams p{};
     p.M = M; p.N = N; p.K = K;
     p.tiles_n = (N + BN - 1) / BN;
-    p.tiles = (long long)((M + TC_BM - 1) / TC_BM) * p.tiles_n;
+    const long long tiles = (long long)((M + TC_BM - 1) / TC_BM) * p.tiles_n;
+    APSB_CHECK_ARG(tiles < (1LL << 31) - 1024, "too many output tiles (%lld)", tiles);
+    p.tiles = (unsigned)tiles;
     p.a = a; p.e = e;
-    const long long grid = p.tiles < num_sms() ? p.tiles : num_sms();
+    {
+        const bool glu = e.act == ACT_GLU;
+        bool v = ((uintptr_t)e.out & 15) == 0 && (e.ldo & 3) == 0 && (N % (glu ? 8 : 4)) == 0;
+        if (e.res) v = v && ((uintptr_t)e.res & 15) == 0 && (e.ldres & 3) == 0;
+        if (e.bias) v = v && ((uintptr_t)e.bias & 15) == 0;
+        if (e.post_scale) v = v && ((uintptr_t)e.post_scale & 15) == 0 && ((uintptr_t)e.post_shift & 15) == 0;
+        if (e.act == ACT_PRELU && e.slope_stride) v = v && ((uintptr_t)e.slope & 15) == 0;
+        p.epi_vec = v ? 1 : 0;
+    }
+#ifdef APSB_TC_TRACE
+    p.trace = g_tc_trace;
+    p.dbg = getenv("APS_B200_TC_DBG") ? atoi(getenv("APS_B200_TC_DBG")) : 0;
+#endif
+    const long long grid = tiles < num_sms() ? tiles : num_sms();
     tc_gemm_kernel<BN><<<(unsigned)grid, TC_THREADS, C::SMEM, st>>>(tB, tBl, p);
     APSB_LAUNCH_CHECK();
     return 0;
 }
 
-// Tile width: 256 columns halve the A re-reads and the shared-memory traffic per MMA, but need enough tiles to fill
-// the machine; narrow outputs take 128 / 64 so that more CTAs share the work.
+// Tile width from a small cost model fitted to B200 measurements (profiles/r01_tc_gemm_v2_microbench.txt, cycles):
+// a k-step of 1 costs ~87 (BN 256), ~64 (BN 128), ~53 (BN 64) cycles per tile in the main loop (+ ~5000 per tile for the
+// pipeline refill), the epilogue ~4000 cycles per 32 columns and overlaps the next tile's main loop; tiles run in
+// waves of one per SM.
 static int run_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, long long M, long long N,
                   long long K, const Epilogue& e, cudaStream_t st) {
     const long long tm = (M + TC_BM - 1) / TC_BM;
     const int sms = num_sms();
     const char* fe = getenv("APS_B200_TC_BN");                    // tuning / test aid: force the tile width
-    const int force = fe ? atoi(fe) : 0;
-    int bn;
-    if (force == 64 || force == 128 || force == 256) bn = force;
-    else if (N >= 256 && tm * ((N + 255) / 256) >= sms) bn = 256;
-    else if (N >= 128 && tm * ((N + 127) / 128) >= sms) bn = 128;
-    else if (N > 128 && tm * ((N + 127) / 128) * 2 >= sms) bn = 128;
-    else bn = 64;
+    int bn = fe ? atoi(fe) : 0;
+    if (bn != 64 && bn != 128 && bn != 256) {
+        const int cand[3] = {256, 128, 64};
+        const double per_k[3] = {87.0, 64.0, 53.0};
+        double best = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            if (cand[i] > 64 && N <= cand[i] / 2) continue;       // more than half of the tile would be padding
+            const long long tiles = tm * ((N + cand[i] - 1) / cand[i]);
+            const double waves = (double)((tiles + sms - 1) / sms);
+            const double main_c = (double)K * per_k[i] + 5000.0, epi_c = 4000.0 * (cand[i] / 32);
+            const double t = main_c + (waves - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
+            if (bn == 0 || t < best) { best = t; bn = cand[i]; }
+        }
+    }
     if (bn == 256) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
     if (bn == 128) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
     return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
@@ -564,6 +942,14 @@ static int check_weights(const float* w_hi, const float* w_lo, long long ld_w, l
 }  // namespace apsb
 
 using namespace apsb;
+
+#ifdef APSB_TC_TRACE
+extern "C" int aps_b200_tc_trace(unsigned long long* device_buffer, int capacity_words) {
+    g_tc_trace = device_buffer;
+    g_tc_trace_cap = capacity_words;
+    return 0;
+}
+#endif
 
 extern "C" int aps_b200_tf32_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo,
                                    int64_t ld_out, void* stream) {
@@ -601,7 +987,7 @@ static int conv_geometry(AGather& a, const float* x, int64_t batch, int64_t heig
     APSB_CHECK_ARG(batch > 0 && height > 0 && width > 0 && in_channels > 0, "bad shape");
     APSB_CHECK_ARG(kernel_h > 0 && kernel_w > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0,
                    "bad convolution geometry");
-    APSB_CHECK_ARG(in_channels % TC_BK == 0 && ((uintptr_t)x & 15) == 0,
+    APSB_CHECK_ARG(in_channels % 32 == 0 && ((uintptr_t)x & 15) == 0,
                    "the tensor-core convolution needs Cin %% 32 == 0 and a 16-byte aligned input (Cin = %lld)",
                    (long long)in_channels);
     APSB_CHECK_ARG(height < (1 << 20) && width < (1 << 20) && in_channels < (1 << 20), "shape too large");
@@ -650,6 +1036,26 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t bat
     const int64_t OW = (width - 1) * stride_w - 2 * pad_w + kernel_w + out_pad_w;
     APSB_CHECK_ARG(OH > 0 && OW > 0, "transposed convolution output is empty");
     a.OH = (int)OH; a.OW = (int)OW;
+    // row classes (oh % stride_h): usable when every class owns at least one tap, else plain row order
+    a.classes = 1;
+    if (stride_h >= 2 && stride_h <= 4 && !getenv("APS_B200_TC_NO_CLASSES")) {
+        bool ok = true;
+        for (int r = 0; r < stride_h && ok; ++r) {
+            bool any = false;
+            for (int kh = 0; kh < kernel_h; ++kh) any = any || ((r + pad_h - kh) % stride_h) == 0;
+            ok = any;
+        }
+        if (ok) {
+            a.classes = stride_h;
+            long long start = 0;
+            for (int r = 0; r < stride_h; ++r) {
+                a.class_start[r] = start;
+                a.class_rows[r] = OH > r ? (int)((OH - r + stride_h - 1) / stride_h) : 0;
+                start += batch * a.class_rows[r] * OW;
+            }
+            for (int r = stride_h; r < 4; ++r) { a.class_start[r] = start; a.class_rows[r] = 0; }
+        }
+    }
     const int64_t M = batch * OH * OW, K = (int64_t)kernel_h * kernel_w * in_channels;
     APSB_CHECK_ARG(M < (1LL << 31) && K < (1LL << 31) && out_channels < (1LL << 31), "shape too large");
     if (int rc = check_weights(weight_hi, weight_lo, K, K)) return rc;

@@ -22,7 +22,7 @@ def relerr(a, b):
 # ---- correctness: linear, all tile widths, ragged shapes, more tiles than SMs -------------------------------
 for bn in ("64", "128", "256", ""):
     os.environ["APS_B200_TC_BN"] = bn
-    for (M, K, N) in ((128, 32, 64), (333, 96, 200), (3200, 256, 768), (700, 2304, 256), (40000, 64, 320)):
+    for (M, K, N) in ((128, 32, 64), (333, 96, 200), (300, 64, 257), (3200, 256, 768), (700, 2304, 256), (40000, 64, 320)):
         x = th.randn(M, K, device=dev)
         w = th.randn(N, K, device=dev) / K**0.5
         b = th.randn(N, device=dev)
@@ -38,6 +38,14 @@ for bn in ("64", "128", "256", ""):
     wi = th.stack([w[:256], w[256:]], 1).reshape(512, 256).contiguous()
     bi = th.stack([b[:256], b[256:]], 1).reshape(512).contiguous()
     print(f"BN={bn or 'auto':>4} glu err {relerr(ops.linear(x, wi, bi, act='glu'), F.glu(ref, -1)):.2e}", flush=True)
+    ref = F.linear(x.double(), w[:258].double(), b[:258].double())
+    wi = th.stack([w[:129], w[129:258]], 1).reshape(258, 256).contiguous()
+    bi = th.stack([b[:129], b[129:258]], 1).reshape(258).contiguous()
+    print(f"BN={bn or 'auto':>4} glu(unaligned) err {relerr(ops.linear(x, wi, bi, act='glu'), F.glu(ref, -1)):.2e}", flush=True)
+    sl, ps, pt = th.rand(512, device=dev), th.rand(512, device=dev) + 0.5, th.randn(512, device=dev)
+    ref = F.linear(x.double(), w.double(), b.double())
+    refp = th.where(ref >= 0, ref, ref * sl.double()) * ps.double() + pt.double()
+    print(f"BN={bn or 'auto':>4} prelu+affine err {relerr(ops.linear(x, w, b, act='prelu', slope=sl, post=(ps, pt)), refp):.2e}", flush=True)
     # implicit conv / transposed conv vs torch (fp64 on the CPU)
     for (B, H, W, Ci, Co, k, s_, p_, d_) in ((3, 40, 21, 32, 64, (3, 3), (2, 2), (1, 1), (1, 1)),
                                              (1, 18, 9, 64, 32, (5, 2), (2, 1), (2, 0), (1, 1)),
@@ -50,7 +58,11 @@ for bn in ("64", "128", "256", ""):
         print(f"BN={bn or 'auto':>4} conv {B}x{H}x{W}x{Ci}->{Co} k{k} s{s_}: err {relerr(got.cpu(), ref):.2e}", flush=True)
     for (B, H, W, Ci, Co, k, s_, p_, op_) in ((2, 9, 30, 64, 32, (3, 3), (2, 1), (1, 1), (0, 0)),
                                               (2, 4, 25, 256, 128, (3, 3), (2, 1), (0, 1), (1, 0)),
-                                              (1, 17, 11, 32, 64, (3, 3), (2, 2), (1, 1), (1, 1))):
+                                              (1, 17, 11, 32, 64, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                              (3, 17, 30, 64, 4, (3, 3), (2, 1), (1, 1), (0, 0)),
+                                              (2, 7, 13, 32, 36, (3, 3), (1, 1), (1, 1), (0, 0)),
+                                              (2, 6, 9, 32, 40, (5, 3), (3, 1), (2, 1), (2, 0)),
+                                              (5, 40, 60, 32, 32, (3, 3), (2, 1), (0, 1), (1, 0))):
         x, w, b = th.randn(B, Ci, H, W), th.randn(Ci, Co, *k) * 0.1, th.randn(Co)
         ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=s_, padding=p_, output_padding=op_).permute(0, 2, 3, 1)
         got = ops.conv_transpose2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(dev),

@@ -105,37 +105,92 @@ def test_encoder_tensor_core_engine_and_graph_replay(name, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_tensor_core_gemm_vs_fp64():
-    """tcgen05 3xTF32 GEMM: error against fp64 must stay at the fp32 level (well below TF32's 1e-3)."""
+@pytest.mark.parametrize("bn", ["", "64", "128", "256"])
+def test_tensor_core_gemm_vs_fp64(monkeypatch, bn):
+    """tcgen05 3xTF32 GEMM (every tile width): error against fp64 must stay at the fp32 level (well below TF32's 1e-3);
+    ragged M / N, more tiles than SMs, unaligned rows (N = 257 takes the transposed scalar epilogue)."""
     from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    monkeypatch.setenv("APS_B200_TC_BN", bn)
     th.manual_seed(2)
-    for (M, K, N) in ((128, 32, 64), (3200, 256, 2048), (3200, 2048, 256), (333, 96, 200), (700, 2304, 256)):
+    for (M, K, N) in ((128, 32, 64), (3200, 256, 2048), (3200, 2048, 256), (333, 96, 200), (700, 2304, 256), (300, 64, 257),
+                      (40000, 64, 320)):
         x, w, b = th.randn(M, K, device=DEV), th.randn(N, K, device=DEV) / K**0.5, th.randn(N, device=DEV)
+        r = th.randn(M, N, device=DEV)
         ref = x.double() @ w.double().t() + b.double()
-        old = ops.GEMM_ENGINE
-        try:
-            ops.GEMM_ENGINE = "tc"
-            y = ops.linear(x, w, b)
-        finally:
-            ops.GEMM_ENGINE = old
+        y = ops.linear(x, w, b)
         # the TMEM accumulator rounds toward zero: the error grows ~K/8 * 2^-24 (1.2e-5 at K = 2048), far below TF32's 1e-3
         assert float((y.double() - ref).abs().max() / ref.abs().max()) < 3e-5, (M, K, N)
+        y2 = ops.linear(x, w, b, act="swish", alpha=0.5, residual=r)
+        ref2 = 0.5 * ref * th.sigmoid(ref) + r.double()
+        assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) < 3e-5, (M, K, N)
+
+
+@pytest.mark.gpu
+def test_tensor_core_epilogues(monkeypatch):
+    """GLU (aligned and unaligned output rows), PReLU + post affine, strided input rows on the tensor-core engine."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    th.manual_seed(4)
+    x, w, b = th.randn(300, 256, device=DEV), th.randn(512, 256, device=DEV) / 16, th.randn(512, device=DEV)
+    ref = F.linear(x.double(), w.double(), b.double())
+    for half in (256, 129):
+        n = 2 * half
+        wi = th.stack([w[:half], w[half:n]], 1).reshape(n, 256).contiguous()
+        bi = th.stack([b[:half], b[half:n]], 1).reshape(n).contiguous()
+        assert rel_err(ops.linear(x, wi, bi, act="glu"), F.glu(ref[:, :n], -1)) < 1e-5
+    sl, ps, pt = th.rand(512, device=DEV), th.rand(512, device=DEV) + 0.5, th.randn(512, device=DEV)
+    refp = th.where(ref >= 0, ref, ref * sl.double()) * ps.double() + pt.double()
+    assert rel_err(ops.linear(x, w, b, act="prelu", slope=sl, post=(ps, pt)), refp) < 1e-5
+    for act, fn in (("relu", F.relu), ("tanh", th.tanh), ("sigmoid", th.sigmoid), ("gelu", F.gelu)):
+        assert rel_err(ops.linear(x, w, b, act=act), fn(ref)) < 1e-5
+    big = th.randn(640, 300, device=DEV)
+    assert rel_err(ops.linear(big[:, 20:148], w[:, :128].contiguous()), F.linear(big[:, 20:148].double(), w[:, :128].double())) < 1e-5
 
 
 @pytest.mark.gpu
 def test_tensor_core_conv_path_vs_torch(monkeypatch):
-    """conv2d through fused im2col + TF32 split + tcgen05 GEMM (the path the conv2d front takes with engine tc)."""
+    """conv2d as an implicit GEMM on the tensor-core engine (in-kernel im2col gather + TF32 split)."""
     import torch.nn.functional as F
     from aps_b200 import ops
     monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
     th.manual_seed(3)
-    for (B, H, W, Ci, Co, k, s_, p_) in ((2, 33, 20, 16, 24, (3, 3), (2, 2), (1, 1)), (3, 40, 21, 32, 64, (3, 3), (2, 2), (1, 1)),
-                                         (1, 18, 9, 64, 32, (5, 2), (2, 1), (2, 0))):
+    for (B, H, W, Ci, Co, k, s_, p_, d_) in ((3, 40, 21, 32, 64, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                             (1, 18, 9, 64, 32, (5, 2), (2, 1), (2, 0), (1, 1)),
+                                             (2, 31, 17, 32, 288, (3, 3), (2, 1), (0, 1), (1, 2)),
+                                             (4, 100, 20, 256, 256, (3, 3), (2, 2), (1, 1), (1, 1))):
         x, w, b = th.randn(B, Ci, H, W), th.randn(Co, Ci, *k) * 0.1, th.randn(Co)
-        ref = F.relu(F.conv2d(x, w, b, stride=s_, padding=p_)).permute(0, 2, 3, 1)
+        ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=s_, padding=p_, dilation=d_)).permute(0, 2, 3, 1)
         got = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV),
-                              b.to(DEV), stride=s_, padding=p_, act="relu")
-        assert got.shape == ref.shape and rel_err(got, ref) < 1e-5
+                              b.to(DEV), stride=s_, padding=p_, dilation=d_, act="relu")
+        assert got.shape == ref.shape and rel_err(got, ref) < 3e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("classes", [True, False])
+def test_tensor_core_conv_transpose_vs_torch(monkeypatch, classes):
+    """conv_transpose2d as an implicit gather GEMM; with stride_h > 1 the rows are walked class-major (oh % stride_h)
+    and the all-zero taps of a tile are skipped — both orders must give the reference result."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    if not classes:
+        monkeypatch.setenv("APS_B200_TC_NO_CLASSES", "1")
+    th.manual_seed(5)
+    for (B, H, W, Ci, Co, k, s_, p_, op_) in ((2, 9, 30, 64, 32, (3, 3), (2, 1), (1, 1), (0, 0)),
+                                              (2, 4, 25, 256, 128, (3, 3), (2, 1), (0, 1), (1, 0)),
+                                              (1, 17, 11, 32, 64, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                              (3, 17, 30, 64, 4, (3, 3), (2, 1), (1, 1), (0, 0)),
+                                              (2, 7, 13, 32, 36, (3, 3), (1, 1), (1, 1), (0, 0)),
+                                              (2, 6, 9, 32, 40, (5, 3), (3, 1), (2, 1), (2, 0)),
+                                              (5, 40, 60, 32, 32, (3, 3), (2, 1), (0, 1), (1, 0))):
+        x, w, b = th.randn(B, Ci, H, W), th.randn(Ci, Co, *k) * 0.1, th.randn(Co)
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=s_, padding=p_, output_padding=op_).permute(0, 2, 3, 1)
+        got = ops.conv_transpose2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV),
+                                        w.transpose(0, 1).permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV), stride=s_,
+                                        padding=p_, output_padding=op_)
+        assert got.shape == ref.shape and rel_err(got, ref) < 3e-5
 
 
 @pytest.mark.gpu
