@@ -20,11 +20,56 @@
 
 namespace apsb {
 
+// Complex arithmetic on Blackwell's packed fp32 instructions (add/sub/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2 in SASS):
+// one instruction per complex add and two per complex multiply instead of two and four.  The packed forms have the
+// same lane throughput as the scalar ones (scripts/ubench/f32x2.cu) but halve the ISSUE slots, and ptxas folds the
+// real/imaginary swaps and negations of the butterflies (multiplication by -i) into operand modifiers (.LO_HI, .NP).
+// Results are IEEE-identical for add/sub; the multiply rounds a.y*b.y first instead of a.x*b.x (same error bound).
+#ifndef APSB_F32X2
+#define APSB_F32X2 1
+#endif
+#if APSB_F32X2
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(r));
+    return c;
+}
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = a.x * (b.x, b.y) + (-a.y, a.y) * (b.y, b.x)
+    unsigned long long t, r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(t) : "l"(f2_pack(-a.y, a.y)), "l"(f2_pack(b.y, b.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a.x, a.x)), "l"(f2_pack(b.x, b.y)), "l"(t));
+    return f2_unpack(r);
+}
+// element-wise product (window * samples)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(r);
+}
+#else
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.x, b.y, a.y * b.x));
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) {

@@ -337,8 +337,7 @@ __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(
                 const float2* ys2 = reinterpret_cast<const float2*>(ys);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const float2 w = sm_win[l + G * q], s2 = ys2[l + G * q];
-                    v[q] = make_float2(s2.x * w.x, s2.y * w.y);
+                    v[q] = mul2(ys2[l + G * q], sm_win[l + G * q]);
                 }
             } else {
 #pragma unroll

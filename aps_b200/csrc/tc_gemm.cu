@@ -13,12 +13,12 @@
 // of an activation is ever written to HBM.
 //
 // One persistent CTA per SM (320 threads) walks 128 x BN output tiles; roles:
-//   warp 8    : TMA producer for W_hi / W_lo tiles (BN rows x BK floats, swizzled), mbarrier tx
-//   warp 9    : allocates TMEM (2 x BN columns: double-buffered accumulator) and issues the UMMAs
-//   warps 4-7 : epilogue — tcgen05.ld of the finished accumulator while the NEXT tile's MMAs run into the other
+//   warp 0    : TMA producer for W_hi / W_lo tiles (BN rows x BK floats, swizzled), mbarrier tx
+//   warp 1    : allocates TMEM (2 x BN columns: double-buffered accumulator) and issues the UMMAs
+//   warps 2-5 : epilogue — tcgen05.ld of the finished accumulator while the NEXT tile's MMAs run into the other
 //               buffer; 32x32 transposes through shared memory, bias / activation / GLU / affine / residual, coalesced
 //               128-byte row stores
-//   warps 0-3 : A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
+//   warps 6-9 : A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
 //               taps), hi/lo split in registers, st.shared into the same 128-byte-swizzled K-major layout TMA would
 //               write, fence.proxy.async, mbarrier arrive
 // Replaces the cuBLAS / cuDNN calls behind F.linear, 1x1 convolutions and Conv2d / ConvTranspose2d of the reference
@@ -39,7 +39,7 @@ namespace apsb {
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 320;
 constexpr int TC_PRODUCERS = 128;          // warps 0..3
-constexpr int WARP_TMA = 8, WARP_MMA = 9;
+constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_PROD0 = 6;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,6 +74,30 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(s_u32(bar)), "r"(parity)
             : "memory");
         if (spin > (1u << 26)) __trap();
+    }
+}
+// Wait used by the roles that are expected to wait LONG (TMA thread and producer pollers on a free stage, epilogue on a
+// finished accumulator): try_wait with a suspend-time hint parks the thread in hardware instead of hot-spinning — an
+// unhinted try_wait returns after a few cycles, and the resulting ~100 M polling instructions per launch were stealing
+// the issue slots of the producer warps that share the scheduler (ncu: profiles/r01_tc_gemm_v2_spin.txt).
+__device__ __forceinline__ void tc_mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (spin > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tc_tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -216,10 +240,9 @@ __device__ __forceinline__ int tc_tile_class(const AGather& a, unsigned m_first,
         }
     return c0 == c1 ? c0 : -1;
 }
-// does tap (kh, kw) contribute to the rows of class `cls`?
-__device__ __forceinline__ bool tc_tap_valid(const AGather& a, int cls, int tap) {
+// does kernel row kh contribute to the output rows of class `cls`?
+__device__ __forceinline__ bool tc_kh_valid(const AGather& a, int cls, int kh) {
     if (cls < 0) return true;
-    const int kh = tap / a.KW;
     return ((cls + a.ph - kh) % a.sh) == 0;
 }
 // output row index (in units of rows of the [.., Cout] output) of GEMM row m
@@ -264,7 +287,8 @@ static int g_tc_trace_cap = 0;
 template <int BN> struct TcCfg {
     static constexpr int BK = BN == 256 ? 16 : 32;
     static constexpr int SWZ = BK * 4;                                          // bytes per operand row = swizzle span
-    static constexpr int STAGES = BN == 128 ? 3 : 4;
+    // BN = 64 keeps one stage less than would fit: the 48 KB it leaves become L1, which serves the kw reuse of the gathers
+    static constexpr int STAGES = BN == 256 ? 4 : 3;
     static constexpr int A_BYTES = TC_BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -280,7 +304,7 @@ template <int BN> struct TcCfg {
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ TcParams p) {
@@ -308,8 +332,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // k-blocks are walked tap by tap (convolutions: a k-block never crosses a (kh, kw) tap since Cin % 32 == 0) so that
     // a transposed-convolution tile can skip the taps that are zero for its row class; a linear layer is one "tap"
-    const int num_taps = p.a.mode == 0 ? 1 : p.a.KH * p.a.KW;
-    const int kb_per_tap = p.a.mode == 0 ? (p.K + BK - 1) / BK : p.a.Cin / BK;
+    // Order inside a tile: kernel row kh (skippable), then channel block cb, then kw INNERMOST: the three kw taps of one
+    // (kh, cb) read the same input pixels shifted by one, so consecutive k-blocks hit the lines the previous one pulled
+    // into L1 (the tex->L2 sector traffic of a 3x3 convolution drops towards a third).
+    // MODE (0 linear, 1 conv2d, 2 conv_transpose2d) is a template parameter: each instantiation carries only its own
+    // gather code — the producers are instruction-fetch bound when their per-k-block code does not fit the L0 i-cache.
+    const int num_kh = MODE == 0 ? 1 : p.a.KH;
+    const int num_kw = MODE == 0 ? 1 : p.a.KW;
+    const int kb_per_tap = MODE == 0 ? (p.K + BK - 1) / BK : p.a.Cin / BK;
+    // The channel blocks are walked in groups of 32 channels whatever BK is (SUB = 2 half-blocks for BK = 16), so the
+    // order of the k-steps — and with it every rounding — does not depend on the tile width: a row's result is bit
+    // identical for any batch size / sharding (tests: "batch-shard invariance").
+    constexpr int SUB = MODE == 0 ? 1 : 32 / BK;
+    const int cb32_per_tap = MODE == 0 ? kb_per_tap : p.a.Cin / 32;
     auto tile_class = [&](unsigned tile) {
         const unsigned m_first = (tile / (unsigned)p.tiles_n) * TC_BM;
         const unsigned m_last = m_first + TC_BM - 1 < (unsigned)p.M ? m_first + TC_BM - 1 : (unsigned)p.M - 1;
@@ -317,8 +352,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
 
     // Role -> warp assignment: the SM's schedulers prefer the HIGHEST warp id among eligible warps of a sub-partition
-    // (warp % 4), so the two single-thread, latency-critical roles get the top ids: warp 9 issues the MMAs, warp 8 the
-    // TMA loads; warps 4-7 are the epilogue (TMEM lane quarter = warp % 4), warps 0-3 the A producers.
+    // (warp % 4).  The A producers are the throughput-critical role, so they get the top ids (6-9); the single-thread
+    // TMA / MMA roles (warps 0 / 1) mostly wait and must never out-prioritise them; warps 2-5 are the epilogue (TMEM
+    // lane quarter = warp % 4).
     if (warp == WARP_TMA && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
@@ -355,13 +391,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int n_blk = (int)(tile % (unsigned)p.tiles_n);
                 const int cls = tile_class(tile);
-                for (int tap = 0; tap < num_taps; ++tap) {
-                    if (!tc_tap_valid(p.a, cls, tap)) continue;
-                    for (int cb = 0; cb < kb_per_tap; ++cb, ++it) {
-                        const int kb = tap * kb_per_tap + cb;
+                for (int kh = 0; kh < num_kh; ++kh) {
+                    if (!tc_kh_valid(p.a, cls, kh)) continue;
+                    for (int cb32 = 0; cb32 < cb32_per_tap; ++cb32)
+                    for (int kw = 0; kw < num_kw; ++kw)
+                    for (int h = 0; h < SUB; ++h, ++it) {
+                        const int kb = (kh * num_kw + kw) * kb_per_tap + cb32 * SUB + h;
                         const int s = it % S;
                         const uint32_t ph = (it / S) & 1;
-                        tc_mbar_wait(empty + s, ph ^ 1);
+                        tc_mbar_wait_parked(empty + s, ph ^ 1);
                         uint8_t* st = base + s * C::STAGE_BYTES + 2 * A_BYTES;
 #ifdef APSB_TC_TRACE
                         if (p.dbg & 2) {
@@ -386,14 +424,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             uint32_t it = 0, tcount = 0;
             for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1;
-                tc_mbar_wait(tmem_empty + buf, ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this buffer
+                tc_mbar_wait_parked(tmem_empty + buf, ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 const int cls = tile_class(tile);
                 uint32_t first = 1;
-                for (int tap = 0; tap < num_taps; ++tap) {
-                  if (!tc_tap_valid(p.a, cls, tap)) continue;
-                  for (int cb = 0; cb < kb_per_tap; ++cb, ++it) {
+                for (int kh = 0; kh < num_kh; ++kh) {
+                  if (!tc_kh_valid(p.a, cls, kh)) continue;
+                  for (int j = 0; j < kb_per_tap * num_kw; ++j, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     tc_mbar_wait(full_a + s, ph);
@@ -419,13 +457,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 TC_TR(3);
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue warps 4..7: TMEM lane quarter = warp % 4 =================
+    } else if (warp < WARP_PROD0) {
+        // ================= epilogue warps 2..5: TMEM lane quarter = warp % 4 =================
         // Fast path (p.epi_vec: 16-byte aligned output / residual rows, N % 4 == 0): lane = row straight out of TMEM,
         // vector loads / stores on the lane's own row.  Fallback (e.g. N = 257 mask rows): the 32x32 block is transposed
         // through a padded shared tile so that lane = column and the scalar accesses are still 128-byte rows.
         const int q = warp & 3;
-        float* tile_s = epi_tiles + (warp - 4) * (32 * 33);
+        float* tile_s = epi_tiles + (warp - WARP_EPI0) * (32 * 33);
         const Epilogue& e = p.e;
         const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
@@ -433,10 +471,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int n_blk = (int)(tile % (unsigned)p.tiles_n);
             const unsigned m_blk = tile / (unsigned)p.tiles_n;
             const uint32_t buf = tcount & 1;
-            if (lane == 0) tc_mbar_wait(tmem_full + buf, (tcount >> 1) & 1);
+            if (lane == 0) tc_mbar_wait_parked(tmem_full + buf, (tcount >> 1) & 1);
             __syncwarp();
             tc_fence_after();
-            if (threadIdx.x == 128) TC_TR(4);
+            if (threadIdx.x == 64) TC_TR(4);
             const long long m0 = (long long)m_blk * TC_BM + q * 32;
             const int ncols = min(BN, p.N - n_blk * BN);
             const int nchunks = (ncols + 31) >> 5;
@@ -481,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
-                    if (threadIdx.x == 128) TC_TR(5);
+                    if (threadIdx.x == 64) TC_TR(5);
                 }
                 if (p.epi_vec) {
                     if (glu) {
@@ -580,73 +618,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     __syncwarp();                  // tile_s is reused by the next chunk
                 }
             }
-            if (threadIdx.x == 128) TC_TR(6);
+            if (threadIdx.x == 64) TC_TR(6);
         }
     } else {
-        // ================= A producers (warps 0..3) =================
+        // ================= A producers (warps 6..9) =================
         // thread -> 16-byte chunk c of rows rg, rg + RSTEP, ...: a warp instruction reads whole SWZ-byte row segments.
         // The gather for k-block i+1 is issued BEFORE block i is split and stored, so the L2 round trip is hidden.
         constexpr int CPR = BK / 4;                 // 16-byte chunks per operand row
         constexpr int RSTEP = TC_PRODUCERS / CPR;   // rows covered by one pass of the 128 producer threads
         constexpr int RPT = TC_BM / RSTEP;          // rows per thread (= CPR)
-        const int pt = threadIdx.x;
+        const int pt = threadIdx.x - WARP_PROD0 * 32;
         const int c = pt % CPR, rg = pt / CPR;
         const AGather& a = p.a;
-        const float* rowp[RPT];     // linear: row pointer; conv: image base of the row's batch index; null: row >= M
-        int r_a[RPT], r_b[RPT];     // conv: ih0 / iw0;  tconv: oh + ph / ow + pw
+        // Per-row geometry is resolved when the tile or the kernel row kh changes (rare); the per-k-block path is then a
+        // bounds check on iw, one multiply-add and the load — about 50 instructions instead of 400, which matters
+        // because this role runs straight-line code once per k-block and is instruction-fetch bound otherwise.
+        const float* prow[RPT];     // linear: row pointer; conv: input row (nb, ih) of this kh; null: nothing to read
+        int r_nb[RPT], r_a[RPT], r_b[RPT];   // image index (-1: row >= M); conv: oh*sh - ph / ow*sw - pw; tconv: oh + ph / ow + pw
         auto set_tile = [&](unsigned tile) {
             const unsigned m_blk = tile / (unsigned)p.tiles_n;
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
                 const unsigned m = m_blk * TC_BM + rg + RSTEP * i;
-                r_a[i] = 0; r_b[i] = 0;
-                if (m >= (unsigned)p.M) {
-                    rowp[i] = nullptr;
-                } else if (a.mode == 0) {
-                    rowp[i] = a.x + (long long)m * a.ld;
-                } else {
-                    const RowPos rp = tc_decode_row(a, m);
-                    rowp[i] = a.x + (long long)rp.nb * a.H * a.W * a.Cin;
-                    if (a.mode == 1) { r_a[i] = rp.oh * a.sh - a.ph; r_b[i] = rp.ow * a.sw - a.pw; }
-                    else             { r_a[i] = rp.oh + a.ph;        r_b[i] = rp.ow + a.pw; }
+                r_nb[i] = -1; r_a[i] = 0; r_b[i] = 0; prow[i] = nullptr;
+                if (m < (unsigned)p.M) {
+                    if (MODE == 0) {
+                        r_nb[i] = 0;
+                        prow[i] = a.x + (long long)m * a.ld;
+                    } else {
+                        const RowPos rp = tc_decode_row(a, m);
+                        r_nb[i] = rp.nb;
+                        if (MODE == 1) { r_a[i] = rp.oh * a.sh - a.ph; r_b[i] = rp.ow * a.sw - a.pw; }
+                        else           { r_a[i] = rp.oh + a.ph;        r_b[i] = rp.ow + a.pw; }
+                    }
                 }
+            }
+        };
+        auto set_kh = [&](int kh) {             // convolutions: input row of every tile row for kernel row kh
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                int ih;
+                bool ok = r_nb[i] >= 0;
+                if (MODE == 1) {
+                    ih = r_a[i] + kh * a.dh;
+                    ok = ok && ih >= 0 && ih < a.H;
+                } else {
+                    const int nh = r_a[i] - kh;
+                    ok = ok && nh >= 0;
+                    if (a.sh == 1) ih = nh;
+                    else if (a.sh == 2) { ok = ok && !(nh & 1); ih = nh >> 1; }
+                    else { ok = ok && (nh % a.sh) == 0; ih = nh / a.sh; }
+                    ok = ok && ih < a.H;
+                }
+                prow[i] = ok ? a.x + (((long long)r_nb[i] * a.H + ih) * a.W) * a.Cin : nullptr;
             }
         };
         // Gather of one k-block into registers.  Plain (L1-allocating) loads on purpose: L1 merges a warp's 16-byte lane
         // requests into 128-byte line requests and serves the kw-overlap of neighbouring taps; both L1-bypassing forms
         // that were tried (ld.global.nc.L1::no_allocate, cp.async.cg into a shared-memory ring) were 15-50 % slower.
-        auto gather = [&](int kb, float4 (&v)[RPT]) {
-            const int k = kb * BK + c * 4;
-            if (a.mode == 0) {
+        auto gather = [&](int cb, int kw, float4 (&v)[RPT]) {
+            if (MODE == 0) {
+                const int k = cb * BK + c * 4;
 #pragma unroll
                 for (int i = 0; i < RPT; ++i)
-                    v[i] = (rowp[i] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(rowp[i] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (prow[i] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(prow[i] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-                // Cin % 32 == 0: the whole k-block lies inside one (kh, kw) tap
-                const int k0 = kb * BK;
-                const int tap = k0 / a.Cin, cc = k0 - tap * a.Cin + c * 4;
-                const int kw = tap % a.KW, kh = tap / a.KW;
+                // Cin % 32 == 0: the whole k-block lies inside one (kh, kw) tap; stride_w == 1 for MODE 2 (host check)
+                const int coff = cb * BK + c * 4;
+                const int dwk = MODE == 1 ? kw * a.dw : -kw;
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
-                    int ih, iw;
-                    bool ok = rowp[i] != nullptr && k < p.K;
-                    if (a.mode == 1) {
-                        ih = r_a[i] + kh * a.dh;
-                        iw = r_b[i] + kw * a.dw;
-                        ok = ok && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-                    } else {
-                        const int nh = r_a[i] - kh, nw = r_b[i] - kw;
-                        ok = ok && nh >= 0 && nw >= 0;
-                        // strides 1 and 2 (every reference model) without integer divisions
-                        if (a.sh == 1) ih = nh;
-                        else if (a.sh == 2) { ok = ok && !(nh & 1); ih = nh >> 1; }
-                        else { ok = ok && (nh % a.sh) == 0; ih = nh / a.sh; }
-                        if (a.sw == 1) iw = nw;
-                        else if (a.sw == 2) { ok = ok && !(nw & 1); iw = nw >> 1; }
-                        else { ok = ok && (nw % a.sw) == 0; iw = nw / a.sw; }
-                        ok = ok && ih < a.H && iw < a.W;
-                    }
-                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(rowp[i] + ((long long)ih * a.W + iw) * a.Cin + cc))
+                    const int iw = r_b[i] + dwk;
+                    const bool ok = prow[i] != nullptr && (unsigned)iw < (unsigned)a.W;
+                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(prow[i] + (long long)iw * a.Cin + coff))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -654,32 +698,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         constexpr int D = BK == 16 ? 3 : 2;     // k-blocks of gathers in flight (registers)
         // iterator over the (tile, tap, k-block) sequence of this CTA, skipping taps that are zero for the tile's class
         unsigned ltile = blockIdx.x;
-        int ltap = 0, lcb = 0, lcls = -1;
+        int lkh = 0, lcb = 0, lkw = 0, lh = 0, lcls = -1;   // lcb counts 32-channel groups, lh the half inside (BK = 16)
         bool lfresh = true;                     // the tile's rows have not been decoded yet
-        auto seek = [&]() {                     // move (ltile, ltap) to the next valid tap; false at the end
+        int lkh_set = -1;                       // kernel row the prow[] pointers were computed for
+        auto seek = [&]() {                     // move (ltile, lkh) to the next valid kernel row; false at the end
             while (ltile < p.tiles) {
                 if (lfresh) lcls = tile_class(ltile);
-                while (ltap < num_taps && !tc_tap_valid(a, lcls, ltap)) ++ltap;
-                if (ltap < num_taps) return true;
+                while (lkh < num_kh && !tc_kh_valid(a, lcls, lkh)) ++lkh;
+                if (lkh < num_kh) return true;
                 ltile += gridDim.x;
-                ltap = 0;
+                lkh = 0;
                 lcb = 0;
+                lkw = 0;
+                lh = 0;
                 lfresh = true;
             }
             return false;
         };
+        auto step = [&]() {                     // advance by one k-block: (half,) kw innermost, then channel group, then kh
+            if (++lh == SUB) {
+                lh = 0;
+                if (++lkw == num_kw) {
+                    lkw = 0;
+                    if (++lcb == cb32_per_tap) {
+                        lcb = 0;
+                        ++lkh;
+                    }
+                }
+            }
+        };
         float4 ring[D][RPT];
+#ifdef APSB_TC_TRACE
+        long long acc_seek = 0, acc_tile = 0, acc_ld = 0;
+#endif
         auto gather_next = [&](float4 (&dst)[RPT]) {
+#ifdef APSB_TC_TRACE
+            const long long g0_ = clock64();
+#endif
             if (!seek()) return false;
+#ifdef APSB_TC_TRACE
+            const long long g1_ = clock64();
+#endif
             if (lfresh) {
                 set_tile(ltile);
                 lfresh = false;
+                lkh_set = -1;
             }
-            gather(ltap * kb_per_tap + lcb, dst);
-            if (++lcb == kb_per_tap) {
-                lcb = 0;
-                ++ltap;
+            if (MODE != 0 && lkh_set != lkh) {
+                set_kh(lkh);
+                lkh_set = lkh;
             }
+#ifdef APSB_TC_TRACE
+            const long long g2_ = clock64();
+#endif
+            gather(lcb * SUB + lh, lkw, dst);
+            step();
+#ifdef APSB_TC_TRACE
+            acc_seek += g1_ - g0_; acc_tile += g2_ - g1_; acc_ld += clock64() - g2_;
+#endif
             return true;
         };
         bool live[D];
@@ -700,7 +776,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #ifdef APSB_TC_TRACE
                     const long long c0_ = clock64();
 #endif
-                    if (lane == 0) tc_mbar_wait(empty + s, ph ^ 1);   // one poller per warp
+                    if (lane == 0) tc_mbar_wait_parked(empty + s, ph ^ 1);   // one poller per warp
                     __syncwarp();
                     if (pt == 0) TC_TR(8);
 #ifdef APSB_TC_TRACE
@@ -736,7 +812,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const long long c2_ = clock64();
                     acc_wait += c1_ - c0_;
                     acc_store += c2_ - c1_;
-                    if (p.dbg & 8) { live[d] = seek(); if (live[d]) { if (++lcb == kb_per_tap) { lcb = 0; ++ltap; } } } else
+                    if (p.dbg & 8) { live[d] = seek(); if (live[d]) step(); } else
 #endif
                     live[d] = gather_next(ring[d]);
 #ifdef APSB_TC_TRACE
@@ -749,6 +825,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #ifdef APSB_TC_TRACE
         if (pt == 0 && p.trace && blockIdx.x == 0) {
             tr_smem[1020] = acc_wait; tr_smem[1021] = acc_store; tr_smem[1022] = acc_gather;
+            tr_smem[1017] = acc_seek; tr_smem[1018] = acc_tile; tr_smem[1019] = acc_ld;
         }
 #endif
     }
@@ -848,6 +925,22 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
     return 0;
 }
 
+template <int BN, int MODE>
+static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const TcParams& p, long long grid, cudaStream_t st) {
+    using C = TcCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        // smallest shared-memory carve-out that holds the CTA: what is left of the 228 KB array stays L1 for the gathers
+        APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (C::SMEM + 1024) * 100 / (228 * 1024) + 1));
+        attr = true;
+    }
+    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TC_THREADS, C::SMEM, st>>>(tB, tBl, p);
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int BN>
 static int launch_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, int M, int N, int K,
                      const Epilogue& e, cudaStream_t st) {
@@ -855,11 +948,6 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     CUtensorMap tB, tBl;
     if (int rc = make_map(&tB, W, N, K, ldw, BN, C::BK)) return rc;
     if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN, C::BK)) return rc;
-    static bool attr = false;
-    if (!attr) {
-        APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr = true;
-    }
     TcParams p{};
     p.M = M; p.N = N; p.K = K;
     p.tiles_n = (N + BN - 1) / BN;
@@ -881,9 +969,9 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     p.dbg = getenv("APS_B200_TC_DBG") ? atoi(getenv("APS_B200_TC_DBG")) : 0;
 #endif
     const long long grid = tiles < num_sms() ? tiles : num_sms();
-    tc_gemm_kernel<BN><<<(unsigned)grid, TC_THREADS, C::SMEM, st>>>(tB, tBl, p);
-    APSB_LAUNCH_CHECK();
-    return 0;
+    if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, p, grid, st);
+    if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, p, grid, st);
+    return launch_tc_mode<BN, 2>(tB, tBl, p, grid, st);
 }
 
 // Tile width from a small cost model fitted to B200 measurements (profiles/r01_tc_gemm_v2_microbench.txt, cycles):
@@ -1031,6 +1119,7 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t bat
                                pad_w))
         return rc;
     APSB_CHECK_ARG(out_pad_h >= 0 && out_pad_w >= 0 && out_channels > 0, "bad convolution geometry");
+    APSB_CHECK_ARG(stride_w == 1, "the tensor-core transposed convolution needs stride_w == 1 (got %d)", stride_w);
     a.mode = 2; a.dh = 1; a.dw = 1;
     const int64_t OH = (height - 1) * stride_h - 2 * pad_h + kernel_h + out_pad_h;
     const int64_t OW = (width - 1) * stride_w - 2 * pad_w + kernel_w + out_pad_w;

@@ -138,7 +138,7 @@ def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1,
     OW = (W - 1) * stride[1] - 2 * padding[1] + KW + output_padding[1]
     out = th.empty((B, OH, OW, Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, None, leaky)
-    if _tc_conv_ok(x, Cin, Cout, B * OH * OW):
+    if _tc_conv_ok(x, Cin, Cout, B * OH * OW) and stride[1] == 1:     # the engine's transposed gather needs stride_w == 1
         w2 = weight.view(Cout, KH * KW * Cin)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
         with th.cuda.device(dev):

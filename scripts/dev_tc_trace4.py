@@ -33,6 +33,6 @@ h = buf.cpu().tolist()
 n = min(h[0] & 0xFFFFFFFF, 1022)
 ev = sorted(((v & ((1 << 48) - 1)), (v >> 48) & 0xFFFF) for v in h[1:1 + n])
 t0 = ev[0][0]
-print(f"wall {e0.elapsed_time(e1)*1e3:.0f} us, {n} events; producer cycles: wait {h[1020]} store {h[1021]} gather {h[1022]}")
+print(f"wall {e0.elapsed_time(e1)*1e3:.0f} us, {n} events; producer cycles: wait {h[1020]} store {h[1021]} gather {h[1022]} (seek {h[1017]} set_tile {h[1018]} loads {h[1019]})")
 for t, e in ev[:40]:
     print(f"{t - t0:>8} {NAMES.get(e, e)}")
