@@ -28,20 +28,21 @@ int launch_gemm(const ALoader& a, const float* Wt, long long ldw, int M, int N, 
     return 0;
 }
 
-// Direct convolution for single-channel inputs (the first layer of the conv2d front, Cin = 1, K = KH*KW taps):
-// a GEMM with K = 9 would waste a 16-deep k-tile; this is a pure bandwidth kernel (one output row of Cout floats per
-// position).  Weights are staged tap-major in shared memory so channel reads are coalesced.
-struct Cin1Params {
+// Direct convolution for very narrow inputs (first layer of the conv2d front: Cin = 1, K = 9; first DCCRN encoder
+// layer: stacked re/im, Cin = 2, K = 18): a GEMM would waste most of a 16-deep k-tile; this is a pure bandwidth kernel
+// (one output row of Cout floats per position).  Weights are staged k-major in shared memory so channel reads are
+// coalesced.
+struct NarrowConvParams {
     const float* x;
     const float* w;     // [Cout, KH*KW]
-    int H, W, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW, Cout;
+    int H, W, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW, Cout, Cin;
     long long M;
     Epilogue e;
 };
 
-__global__ void __launch_bounds__(256) conv2d_cin1_kernel(const __grid_constant__ Cin1Params p) {
-    extern __shared__ float sw_[];                    // [K][Cout]
-    const int K = p.KH * p.KW;
+__global__ void __launch_bounds__(256) conv2d_narrow_kernel(const __grid_constant__ NarrowConvParams p) {
+    extern __shared__ float sw_[];                    // [K][Cout], k = (kh*KW + kw)*Cin + c
+    const int K = p.KH * p.KW * p.Cin;
     for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
         const int k = i / p.Cout, co = i - k * p.Cout;
         sw_[i] = __ldg(p.w + (long long)co * K + k);
@@ -63,11 +64,14 @@ __global__ void __launch_bounds__(256) conv2d_cin1_kernel(const __grid_constant_
             for (int kw = 0; kw < p.KW; ++kw) {
                 const int iw = ow * p.sw - p.pw + kw * p.dw;
                 if (iw < 0 || iw >= p.W) continue;
-                const float xv = __ldg(p.x + (nb * p.H + ih) * p.W + iw);
-                const float* wr = sw_ + (kh * p.KW + kw) * p.Cout + co;
+                const float* xp = p.x + ((nb * p.H + ih) * p.W + iw) * p.Cin;
+                for (int c = 0; c < p.Cin; ++c) {
+                    const float xv = __ldg(xp + c);
+                    const float* wr = sw_ + ((kh * p.KW + kw) * p.Cin + c) * p.Cout + co;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (co + j < p.Cout) acc[j] = fmaf(xv, wr[j], acc[j]);
+                    for (int j = 0; j < 4; ++j)
+                        if (co + j < p.Cout) acc[j] = fmaf(xv, wr[j], acc[j]);
+                }
             }
         }
 #pragma unroll
@@ -134,16 +138,16 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
     Epilogue e{};
     const int ncols = (int)out_channels;
     if (int rc = fill_epilogue(e, epi, ncols, out, epi && epi->act == ACT_GLU ? ncols / 2 : ncols)) return rc;
-    if (in_channels == 1 && K <= 64 && epi->act != ACT_GLU && !epi->residual &&
+    if (in_channels <= 4 && K <= 64 && epi->act != ACT_GLU && !epi->residual &&
         (size_t)K * out_channels * 4 <= 48 * 1024) {
-        Cin1Params c{};
+        NarrowConvParams c{};
         c.x = x; c.w = weight; c.H = (int)height; c.W = (int)width; c.KH = kernel_h; c.KW = kernel_w;
         c.sh = stride_h; c.sw = stride_w; c.ph = pad_h; c.pw = pad_w; c.dh = dil_h; c.dw = dil_w;
-        c.OH = (int)OH; c.OW = (int)OW; c.Cout = ncols; c.M = M; c.e = e;
+        c.OH = (int)OH; c.OW = (int)OW; c.Cout = ncols; c.Cin = (int)in_channels; c.M = M; c.e = e;
         const long long total = M * ((ncols + 3) / 4);
         const long long blocks = (total + 255) / 256;
         const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
-        conv2d_cin1_kernel<<<grid, 256, (size_t)K * ncols * 4, (cudaStream_t)stream>>>(c);
+        conv2d_narrow_kernel<<<grid, 256, (size_t)K * ncols * 4, (cudaStream_t)stream>>>(c);
         APSB_LAUNCH_CHECK();
         return 0;
     }

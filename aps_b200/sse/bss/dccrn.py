@@ -13,6 +13,7 @@ The two-layer LSTM bottleneck stays `torch.nn.LSTM` (cuDNN): a sequential recurr
 data-parallel contraction — its share is reported separately by bench.py.
 Inference (`eval()`) only; `cplx=True`, `share_decoder=True`, non-causal convolutions.
 """
+import os
 from typing import List, Optional, Tuple, Union
 
 import numpy as np
@@ -22,6 +23,7 @@ import torch.nn as nn
 from ... import _lib, ops
 
 EPSILON = float(np.finfo(np.float32).eps)
+LSTM_TF32 = os.environ.get("APS_B200_LSTM_TF32", "0") == "1"
 
 
 def parse_1dstr(s: str) -> List[int]:
@@ -103,7 +105,11 @@ class LSTMP(nn.Module):
         self.proj = nn.Linear(hidden_size * 2 if bidirectional else hidden_size, in_features, bias=False)
 
     def forward(self, x: th.Tensor) -> th.Tensor:            # N x T x D
-        out, _ = self.lstm(x)
+        # cuDNN would run the recurrent GEMMs as single-pass TF32 by default (torch.backends.cudnn.allow_tf32): switched
+        # off — the parity contract is against the reference's fp32 CPU path (APS_B200_LSTM_TF32=1 re-enables it:
+        # 66 -> 50 ms per B = 128 step, ~1e-3 relative error inside the recurrence)
+        with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
+            out, _ = self.lstm(x)
         N, T, H = out.shape
         return ops.linear(out.reshape(N * T, H), self.proj.weight.detach()).view(N, T, -1)
 
@@ -219,9 +225,14 @@ class DCCRN(nn.Module):
         Cc = C2 // 2
         hr = x[..., :Cc].permute(0, 2, 3, 1).reshape(N, T, Cc * Fq)
         hi = x[..., Cc:].permute(0, 2, 3, 1).reshape(N, T, Cc * Fq)
+        # complex LSTM (dccrn.py:97-110): out_r = R(hr) - I(hi), out_i = R(hi) + I(hr).  The two applications of each
+        # real LSTM run as ONE call on the batch-concatenated inputs: the recurrence is latency bound per time step, so
+        # this halves its cost (rows of a batch are independent in an LSTM)
         R, I = self.rnn.lstm.real, self.rnn.lstm.imag
-        out_r = R(hr) - I(hi)
-        out_i = R(hi) + I(hr)
+        r_all = R(th.cat([hr, hi], 0))
+        i_all = I(th.cat([hi, hr], 0))
+        out_r = r_all[:N] - i_all[:N]
+        out_i = r_all[N:] + i_all[N:]
         back = lambda t: t.view(N, T, Cc, Fq).permute(0, 3, 1, 2)          # -> N x F x T x Cc
         out = th.cat([back(out_r), back(out_i)], -1)
         x = x + out if self.connection == "sum" else _cat_complex(out, x)
