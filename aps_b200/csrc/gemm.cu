@@ -40,48 +40,60 @@ struct NarrowConvParams {
     Epilogue e;
 };
 
+// thread = (position, group of 4 output channels), positions walked with 32-bit arithmetic (the first version spent
+// its time in emulated 64-bit divisions: 1.07 ms for a layer whose HBM bound is 0.09 ms)
 __global__ void __launch_bounds__(256) conv2d_narrow_kernel(const __grid_constant__ NarrowConvParams p) {
-    extern __shared__ float sw_[];                    // [K][Cout], k = (kh*KW + kw)*Cin + c
+    extern __shared__ __align__(16) float sw_[];      // [K][Cout4], k = (kh*KW + kw)*Cin + c, rows padded to 4 channels
     const int K = p.KH * p.KW * p.Cin;
-    for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
-        const int k = i / p.Cout, co = i - k * p.Cout;
-        sw_[i] = __ldg(p.w + (long long)co * K + k);
+    const int cgroups = (p.Cout + 3) / 4, cpad = cgroups * 4;
+    for (int i = threadIdx.x; i < K * cpad; i += blockDim.x) {
+        const int k = i / cpad, co = i - k * cpad;
+        sw_[i] = co < p.Cout ? __ldg(p.w + (long long)co * K + k) : 0.f;
     }
     __syncthreads();
-    const int cgroups = (p.Cout + 3) / 4;
-    const long long total = p.M * cgroups;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / cgroups;
-        const int co = (int)(i - m * cgroups) * 4;
-        const int ow = (int)(m % p.OW);
-        const long long t = m / p.OW;
-        const int oh = (int)(t % p.OH);
-        const long long nb = t / p.OH;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int kh = 0; kh < p.KH; ++kh) {
-            const int ih = oh * p.sh - p.ph + kh * p.dh;
-            if (ih < 0 || ih >= p.H) continue;
-            for (int kw = 0; kw < p.KW; ++kw) {
-                const int iw = ow * p.sw - p.pw + kw * p.dw;
-                if (iw < 0 || iw >= p.W) continue;
-                const float* xp = p.x + ((nb * p.H + ih) * p.W + iw) * p.Cin;
-                for (int c = 0; c < p.Cin; ++c) {
-                    const float xv = __ldg(xp + c);
-                    const float* wr = sw_ + ((kh * p.KW + kw) * p.Cin + c) * p.Cout + co;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (co + j < p.Cout) acc[j] = fmaf(xv, wr[j], acc[j]);
+    const unsigned gpb = cgroups < 256 ? (unsigned)cgroups : 256u;        // channel groups handled side by side
+    const unsigned ppb = 256u / gpb;                                      // positions per block pass
+    const unsigned g0 = threadIdx.x % gpb, pp = threadIdx.x / gpb;
+    if (pp >= ppb) return;
+    const bool vec = (p.Cout & 3) == 0 && (p.e.ldo & 3) == 0 && ((uintptr_t)p.e.out & 15) == 0;
+    for (unsigned m = blockIdx.x * ppb + pp; m < (unsigned)p.M; m += gridDim.x * ppb) {
+        const unsigned t = m / (unsigned)p.OW, ow = m - t * (unsigned)p.OW;
+        const unsigned nb = t / (unsigned)p.OH, oh = t - nb * (unsigned)p.OH;
+        for (unsigned g = g0; g < (unsigned)cgroups; g += gpb) {
+            const int co = (int)g * 4;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kh = 0; kh < p.KH; ++kh) {
+                const int ih = (int)oh * p.sh - p.ph + kh * p.dh;
+                if (ih < 0 || ih >= p.H) continue;
+                for (int kw = 0; kw < p.KW; ++kw) {
+                    const int iw = (int)ow * p.sw - p.pw + kw * p.dw;
+                    if (iw < 0 || iw >= p.W) continue;
+                    const float* xp = p.x + (((long long)nb * p.H + ih) * p.W + iw) * p.Cin;
+                    for (int c = 0; c < p.Cin; ++c) {
+                        const float xv = __ldg(xp + c);
+                        const float4 wv = *reinterpret_cast<const float4*>(sw_ + ((kh * p.KW + kw) * p.Cin + c) * cpad + co);
+                        acc[0] = fmaf(xv, wv.x, acc[0]); acc[1] = fmaf(xv, wv.y, acc[1]);
+                        acc[2] = fmaf(xv, wv.z, acc[2]); acc[3] = fmaf(xv, wv.w, acc[3]);
+                    }
                 }
             }
-        }
+            float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = co + j;
-            if (n >= p.Cout) break;
-            float v = acc[j] + (p.e.bias ? __ldg(p.e.bias + n) : 0.f);
-            v = apply_act(v, p.e.act, p.e, n);
-            if (p.e.post_scale) v = fmaf(v, __ldg(p.e.post_scale + n), __ldg(p.e.post_shift + n));
-            p.e.out[m * p.e.ldo + n] = v * p.e.alpha;
+            for (int j = 0; j < 4; ++j) {
+                const int n = co + j;
+                float v = acc[j] + ((p.e.bias && n < p.Cout) ? __ldg(p.e.bias + n) : 0.f);
+                v = apply_act(v, p.e.act, p.e, n < p.Cout ? n : 0);
+                if (p.e.post_scale && n < p.Cout) v = fmaf(v, __ldg(p.e.post_scale + n), __ldg(p.e.post_shift + n));
+                o[j] = v * p.e.alpha;
+            }
+            float* op = p.e.out + (long long)m * p.e.ldo + co;
+            if (vec) {
+                *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (co + j < p.Cout) op[j] = o[j];
+            }
         }
     }
 }
@@ -139,15 +151,15 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
     const int ncols = (int)out_channels;
     if (int rc = fill_epilogue(e, epi, ncols, out, epi && epi->act == ACT_GLU ? ncols / 2 : ncols)) return rc;
     if (in_channels <= 4 && K <= 64 && epi->act != ACT_GLU && !epi->residual &&
-        (size_t)K * out_channels * 4 <= 48 * 1024) {
+        (size_t)K * (out_channels + 3) * 4 <= 48 * 1024) {
         NarrowConvParams c{};
         c.x = x; c.w = weight; c.H = (int)height; c.W = (int)width; c.KH = kernel_h; c.KW = kernel_w;
         c.sh = stride_h; c.sw = stride_w; c.ph = pad_h; c.pw = pad_w; c.dh = dil_h; c.dw = dil_w;
         c.OH = (int)OH; c.OW = (int)OW; c.Cout = ncols; c.Cin = (int)in_channels; c.M = M; c.e = e;
-        const long long total = M * ((ncols + 3) / 4);
-        const long long blocks = (total + 255) / 256;
+        const long long cg = (ncols + 3) / 4, ppb = 256 / (cg < 256 ? cg : 256);
+        const long long blocks = (M + ppb - 1) / ppb;
         const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
-        conv2d_narrow_kernel<<<grid, 256, (size_t)K * ncols * 4, (cudaStream_t)stream>>>(c);
+        conv2d_narrow_kernel<<<grid, 256, (size_t)K * cg * 16, (cudaStream_t)stream>>>(c);
         APSB_LAUNCH_CHECK();
         return 0;
     }
