@@ -34,6 +34,7 @@ struct Epilogue {
     float beta;
     float* out;
     long long ldo;
+    int dbg_nobias;        // tuning builds only: skip the bias loads of the tensor-core epilogue
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, const Epilogue& e, int n) {

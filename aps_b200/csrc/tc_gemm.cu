@@ -155,26 +155,25 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
 }
 
 // 32 accumulator columns of one row (lane = row, the native TMEM layout): everything is 16-byte vector traffic on the
-// lane's own row — 8 LDG.128 of the residual (prefetched by the caller), 8 broadcast LDG.128 per per-column vector,
-// 8 STG.128 — about 250 instructions per 32 x 32 block instead of ~1500 for the transposed scalar form.
-template <int ACT>
+// lane's own row — 8 LDG.128 of the residual (prefetched by the caller), 8 STG.128 — and the per-column vectors
+// (bias, post scale / shift, PReLU slope) come from the warp's shared-memory copy `cv` (staged while the main loop of
+// the tile was still running): [bias | scale | shift | slope], BN floats each, column index relative to the tile.
+template <int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue_vec(const uint32_t (&r)[32], const float4 (&res)[8], const Epilogue& e,
-                                                int n0, int N, bool row_ok, float* __restrict__ orow) {
+                                                const float* __restrict__ cv, int c0, int n0, int N, bool row_ok,
+                                                float* __restrict__ orow) {
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
         const int n = n0 + 4 * q4;
         if (n < N) {                                  // N % 4 == 0 on this path
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = b4;
+            const float4 b4 = *reinterpret_cast<const float4*>(cv + c0 + 4 * q4);
+            float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
-            if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
             if (e.post_scale) {
-                ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
-                pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                ps4 = *reinterpret_cast<const float4*>(cv + BN + c0 + 4 * q4);
+                pt4 = *reinterpret_cast<const float4*>(cv + 2 * BN + c0 + 4 * q4);
             }
-            if (ACT == ACT_PRELU) {
-                if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
-                else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
-            }
+            if (ACT == ACT_PRELU) sl4 = *reinterpret_cast<const float4*>(cv + 3 * BN + c0 + 4 * q4);
             float4 o;
             o.x = fmaf(e.beta, res[q4].x, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 0]) + b4.x, sl4.x), ps4.x, pt4.x) * e.alpha);
             o.y = fmaf(e.beta, res[q4].y, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 1]) + b4.y, sl4.y), ps4.y, pt4.y) * e.alpha);
@@ -295,11 +294,10 @@ template <int BN> struct TcCfg {
     static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
 #ifdef APSB_TC_TRACE
     static constexpr int TRACE_BYTES = 8 * 1024;
-    static constexpr int EPI_ALLOC = 0;                                        // trace builds alias the epilogue tiles
 #else
     static constexpr int TRACE_BYTES = 0;
-    static constexpr int EPI_ALLOC = EPI_BYTES;
 #endif
+    static constexpr int EPI_ALLOC = EPI_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_ALLOC + 256 + 1024 + TRACE_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -313,11 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
     uint8_t* after_stages = base + S * C::STAGE_BYTES;
-#ifdef APSB_TC_TRACE
-    float* epi_tiles = reinterpret_cast<float*>(base);   // trace builds: fallback epilogue not supported (aliases stage 0)
-#else
     float* epi_tiles = reinterpret_cast<float*>(after_stages);
-#endif
     uint64_t* full_a = reinterpret_cast<uint64_t*>(after_stages + C::EPI_ALLOC);
     uint64_t* full_b = full_a + S;
     uint64_t* empty = full_b + S;
@@ -471,16 +465,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int n_blk = (int)(tile % (unsigned)p.tiles_n);
             const unsigned m_blk = tile / (unsigned)p.tiles_n;
             const uint32_t buf = tcount & 1;
-            if (lane == 0) tc_mbar_wait_parked(tmem_full + buf, (tcount >> 1) & 1);
-            __syncwarp();
-            tc_fence_after();
-            if (threadIdx.x == 64) TC_TR(4);
             const long long m0 = (long long)m_blk * TC_BM + q * 32;
             const int ncols = min(BN, p.N - n_blk * BN);
             const int nchunks = (ncols + 31) >> 5;
             const long long rows_ll = (long long)p.M - m0;
             const int rows = rows_ll >= 32 ? 32 : (rows_ll > 0 ? (int)rows_ll : 0);
+#ifdef APSB_TC_TRACE
+            const bool row_ok = lane < rows && !(p.dbg & 64);      // ablation: no residual loads / output stores
+#else
             const bool row_ok = lane < rows;
+#endif
             const long long mrow = row_ok ? tc_out_row(p.a, (unsigned)(m0 + lane)) : 0;   // row of the output / residual matrices
             // residual of the lane's row, one chunk ahead (vector path)
             float4 res_nxt[8];
@@ -492,7 +486,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     dst[q4] = (ok && n0 + 4 * q4 < p.N) ? __ldg(reinterpret_cast<const float4*>(e.res + mrow * e.ldres + n0) + q4)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
             };
+            // Everything that does not depend on the accumulator happens BEFORE the wait, i.e. while the tile's main loop
+            // is still running: the first residual chunk is requested and the per-column vectors of the tile are staged
+            // into this warp's shared-memory area (the vector path does not use it as a transpose tile).
             fetch_res(0, res_nxt);
+            if (p.epi_vec && !glu) {
+                __syncwarp();                      // the previous tile's reads of the staged vectors are done
+                for (int j = lane; j < BN; j += 32) {
+                    const int n = n_blk * BN + j;
+                    const bool ok = n < p.N;
+                    tile_s[j] = (e.bias && ok && !e.dbg_nobias) ? __ldg(e.bias + n) : 0.f;
+                    if (e.post_scale) {
+                        tile_s[BN + j] = ok ? __ldg(e.post_scale + n) : 1.f;
+                        tile_s[2 * BN + j] = ok ? __ldg(e.post_shift + n) : 0.f;
+                    }
+                    if (e.act == ACT_PRELU) tile_s[3 * BN + j] = ok ? __ldg(e.slope + (long long)n * e.slope_stride) : 0.f;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tc_mbar_wait_parked(tmem_full + buf, (tcount >> 1) & 1);
+            __syncwarp();
+            tc_fence_after();
+            if (threadIdx.x == 64) TC_TR(4);
 #pragma unroll 1
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int c0 = ch * 32;
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     } else {
                         float* orow = e.out + mrow * e.ldo + n0;
 #define TC_EPI_CASE(A) \
-    case A: tc_epilogue_vec<A>(r, res_cur, e, n0, p.N, row_ok, orow); break;
+    case A: tc_epilogue_vec<A, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow); break;
                         switch (e.act) {
                             TC_EPI_CASE(ACT_RELU)
                             TC_EPI_CASE(ACT_SWISH)
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                             TC_EPI_CASE(ACT_PRELU)
                             TC_EPI_CASE(ACT_LEAKY)
                             TC_EPI_CASE(ACT_GELU)
-                            default: tc_epilogue_vec<ACT_NONE>(r, res_cur, e, n0, p.N, row_ok, orow);
+                            default: tc_epilogue_vec<ACT_NONE, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow);
                         }
 #undef TC_EPI_CASE
                     }
@@ -967,6 +982,7 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
 #ifdef APSB_TC_TRACE
     p.trace = g_tc_trace;
     p.dbg = getenv("APS_B200_TC_DBG") ? atoi(getenv("APS_B200_TC_DBG")) : 0;
+    p.e.dbg_nobias = (p.dbg & 128) ? 1 : 0;
 #endif
     const long long grid = tiles < num_sms() ? tiles : num_sms();
     if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, p, grid, st);
