@@ -42,6 +42,7 @@ CFG = dict(feats="fbank-log-cmvn", frame_len=400, frame_hop=HOP, window="hamm", 
            num_mels=MELS, stft_mode="librosa")
 WORKLOAD = "AsrTransform fbank-log-cmvn (400/160, hamm, preemph 0.97, librosa), B=256 x 4 s @ 16 kHz per GPU"
 ALG_BYTES_PER_STEP = BATCH * S * 4 + BATCH * T * MELS * 4   # read every sample once + write 80 floats/frame
+F1_DRAM_TRAFFIC_BYTES = 65502976 + 6131456                  # measured per launch (ncu, profiles/r01_fbank_s2.txt)
 
 
 def parse():
@@ -432,7 +433,11 @@ def main():
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": BATCH * T, "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "l2": f"{R} distinct resident input batches rotate (4 x 98 MB in+out > 126 MB L2), no flush inside the timed region"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "frontend_kernel<256,0,8> (fused framing+preemph+window+rFFT+|X|+mel+log+cmvn)",
+                     "traffic": F1_DRAM_TRAFFIC_BYTES,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
+                                       "kernel on this workload (profiles/r01_fbank_s2.txt: 65.50 MB read + 6.13 MB written; "
+                                       "the rest of the 32.5 MB output is still in L2 when the kernel ends)",
+                     "kernel": "frontend_kernel<256,0,5,FULL> (fused framing+preemph+window+rFFT+|X|+mel+log+cmvn)",
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP, "peak_source": peak_src,
                      "kernel_ms": kern_ms},
         "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
