@@ -1,2 +1,2 @@
 from .dccrn import DCCRN  # noqa: F401
-from .tcn import FreqConvTasNet  # noqa: F401
+from .tcn import FreqConvTasNet, TimeConvTasNet  # noqa: F401

@@ -124,6 +124,52 @@ def _bn_affine(bn: nn.BatchNorm1d):
     return scale.contiguous(), (bn.bias.detach() - bn.running_mean * scale).contiguous()
 
 
+def _pack_repeats(conv: Conv1dRepeat):
+    """Kernel-ready parameters of a Conv1dRepeat stack (1x1 weights with the ScaleLinear scale folded in, depthwise
+    weights tap-major, eval BatchNorm as an affine pair or the per-utterance norm description)."""
+    pk = {"blocks": [], "skip": []}
+    for rep in conv.repeat:
+        for blk in rep:
+            w1, b1 = blk.conv1.packed()
+            w2, b2 = blk.conv2.packed()
+            C = blk.dconv.weight.shape[0]
+            pk["blocks"].append(dict(
+                w1=w1, b1=b1, a1=blk.norm1[0].weight.detach(), n1=_norm_pack(blk.norm1[1]),
+                wd=blk.dconv.weight.detach().view(C, -1).t().contiguous(), bd=blk.dconv.bias.detach(),
+                a2=blk.norm2[0].weight.detach(), n2=_norm_pack(blk.norm2[1]), w2=w2, b2=b2,
+                dil=blk.dilation, lpad=blk.pad if blk.cau else blk.pad // 2))
+    if conv.skip_linear is not None:
+        pk["skip"] = [lin.packed() for lin in conv.skip_linear]
+    return pk
+
+
+def _run_repeats(lin, conv: Conv1dRepeat, pk, x: th.Tensor, N: int, T: int) -> th.Tensor:
+    """The repeat stack of tcn.py:162-226 on token rows [N*T, C]: three launches per block (see the module docstring)."""
+    outs, skip, bi = [x], 0, 0
+    nrep, nblk = len(conv.repeat), len(conv.repeat[0])
+    for r in range(nrep):
+        if conv.skip_residual:
+            for i in range(r):                       # in-place accumulation semantics of tcn.py:203-224
+                w, b = pk["skip"][skip + i]
+                x = lin(outs[i], w, b, residual=x)
+            outs[r] = x
+            skip += r
+        for _ in range(nblk):
+            d = pk["blocks"][bi]
+            bi += 1
+            (k1, n1), (k2, n2) = d["n1"], d["n2"]
+            h = lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=n1 if k1 == "bn" else None)
+            if k1 == "utt":
+                h = ops.utt_norm(h, N, T, inplace=True, **n1)
+            h = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
+                             slope=d["a2"], post=n2 if k2 == "bn" else None)
+            if k2 == "utt":
+                h = ops.utt_norm(h, N, T, inplace=True, **n2)
+            x = lin(h, d["w2"], d["b2"], residual=x)
+        outs.append(x)
+    return x
+
+
 class FreqConvTasNet(nn.Module):
     """Frequency domain ConvTasNet (arguments as in tcn.py:366-381)."""
 
@@ -162,19 +208,7 @@ class FreqConvTasNet(nn.Module):
         return ops.linear(x, w, b, cache=self._splits, **kw)
 
     def _build_packs(self):
-        pk = {"blocks": [], "skip": []}
-        for rep in self.conv.repeat:
-            for blk in rep:
-                w1, b1 = blk.conv1.packed()
-                w2, b2 = blk.conv2.packed()
-                C = blk.dconv.weight.shape[0]
-                pk["blocks"].append(dict(
-                    w1=w1, b1=b1, a1=blk.norm1[0].weight.detach(), n1=_norm_pack(blk.norm1[1]),
-                    wd=blk.dconv.weight.detach().view(C, -1).t().contiguous(), bd=blk.dconv.bias.detach(),
-                    a2=blk.norm2[0].weight.detach(), n2=_norm_pack(blk.norm2[1]), w2=w2, b2=b2,
-                    dil=blk.dilation, lpad=blk.pad if blk.cau else blk.pad // 2))
-        if self.conv.skip_linear is not None:
-            pk["skip"] = [lin.packed() for lin in self.conv.skip_linear]
+        pk = _pack_repeats(self.conv)
         C = self.mask[1].in_channels
         pk["ident"] = th.ones(1, C, device=self.mask[1].weight.device)
         pk["proj_w"] = self.proj[1].weight.detach()[..., 0].contiguous()
@@ -194,28 +228,7 @@ class FreqConvTasNet(nn.Module):
         N, T, Fi = feats.shape
         rows = ops.rows2d(feats.detach().float())
         x = self._lin(rows, pk["proj_w"], self.proj[1].bias.detach())
-        outs, skip, bi = [x], 0, 0
-        nrep, nblk = len(self.conv.repeat), len(self.conv.repeat[0])
-        for r in range(nrep):
-            if self.conv.skip_residual:
-                for i in range(r):                       # in-place accumulation semantics of tcn.py:203-224
-                    w, b = pk["skip"][skip + i]
-                    x = self._lin(outs[i], w, b, residual=x)
-                outs[r] = x
-                skip += r
-            for _ in range(nblk):
-                d = pk["blocks"][bi]
-                bi += 1
-                (k1, n1), (k2, n2) = d["n1"], d["n2"]
-                h = self._lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=n1 if k1 == "bn" else None)
-                if k1 == "utt":
-                    h = ops.utt_norm(h, N, T, inplace=True, **n1)
-                h = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
-                                 slope=d["a2"], post=n2 if k2 == "bn" else None)
-                if k2 == "utt":
-                    h = ops.utt_norm(h, N, T, inplace=True, **n2)
-                x = self._lin(h, d["w2"], d["b2"], residual=x)
-            outs.append(x)
+        x = _run_repeats(self._lin, self.conv, pk, x, N, T)
         # mask head: PReLU then 1x1 conv then relu / sigmoid
         a = ops.dwconv1d(x, N, T, pk["ident"], None, act="prelu", slope=self.mask[0].weight.detach())
         return self._lin(a, pk["mask_w"], self.mask[1].bias.detach(), act=self.non_linear)
@@ -253,3 +266,113 @@ class FreqConvTasNet(nn.Module):
         if mix.dim() not in (2, 3):
             raise RuntimeError(f"Expects 2/3D tensor (training), got {mix.dim()} instead")
         return self._infer(mix, mode=self.training_mode)
+
+
+class TimeConvTasNet(nn.Module):
+    """Time-domain Conv-TasNet (`sse@time_tcn`, arguments as in tcn.py:241-255).
+
+    Schedule on token rows [N*T, C] (T = (S - L) // (L/2) + 1 encoder frames):
+      encoder Conv1d(1, N, L, stride L/2) + ReLU = a GEMM on the (overlapping) waveform frames, K = L  ->  cLN (`ops.utt_norm`)  ->  1x1 proj  ->  the shared repeat stack  ->
+      PReLU, 1x1 mask conv with relu / sigmoid in the epilogue (softmax over speakers as one small device op)  ->
+      w * m  ->  decoder ConvTranspose1d(N, 1, L, stride L/2) = a GEMM to L samples per frame + a two-term
+      overlap-add (every output sample has exactly two contributing frames) + bias.
+    Inference only; `mixture_consistency` other than "none" is marked "current not working" in the reference
+    (tcn.py:305) and is refused here.
+    """
+
+    def __init__(self, L: int = 20, N: int = 256, X: int = 8, R: int = 4, B: int = 256, H: int = 512, P: int = 3,
+                 norm: str = "BN", causal: bool = False, num_spks: int = 2, non_linear: str = "relu",
+                 scaling_param: bool = False, skip_residual: bool = False, mixture_consistency: str = "none") -> None:
+        super().__init__()
+        assert mixture_consistency in ["none", "fix", "mag", "learn"]
+        if non_linear not in ("relu", "sigmoid", "softmax"):
+            raise ValueError(f"Unsupported nonlinear: {non_linear}")
+        if mixture_consistency != "none":
+            raise RuntimeError("aps_b200.TimeConvTasNet: mixture_consistency is not implemented "
+                               "(the reference marks it as not working, tcn.py:305)")
+        if L % 2:
+            raise RuntimeError("aps_b200.TimeConvTasNet needs an even encoder length L")
+        self.training_mode, self.enh_transform = "time", None
+        self.non_linear_type = non_linear
+        self.encoder = nn.Conv1d(1, N, L, stride=L // 2, padding=0)
+        self.ln = _norm_layer("cLN", N)
+        self.proj = nn.Conv1d(N, B, 1)
+        self.conv = Conv1dRepeat(R, X, in_channels=B, conv_channels=H, kernel_size=P, norm=norm,
+                                 skip_residual=skip_residual, scaling_param=scaling_param, causal=causal)
+        self.mask = nn.Sequential(nn.PReLU(), nn.Conv1d(B, num_spks * N, 1))
+        self.decoder = nn.ConvTranspose1d(N, 1, kernel_size=L, stride=L // 2, bias=True)
+        self.num_spks, self.mixture_consistency, self.L = num_spks, mixture_consistency, L
+        self._packs = None
+        self._splits = ops.SplitCache()
+        self.register_load_state_dict_post_hook(lambda m, k: m._reset())
+
+    def _reset(self):
+        self._packs = None
+        self._splits.clear()
+
+    def _apply(self, fn, *a, **k):
+        self._packs = None
+        if hasattr(self, "_splits"):
+            self._splits.clear()
+        return super()._apply(fn, *a, **k)
+
+    def _lin(self, x, w, b=None, **kw):
+        return ops.linear(x, w, b, cache=self._splits, **kw)
+
+    def _build_packs(self):
+        pk = _pack_repeats(self.conv)
+        dev = self.mask[1].weight.device
+        pk["ident"] = th.ones(1, self.mask[1].in_channels, device=dev)
+        pk["enc_w"] = self.encoder.weight.detach()[:, 0].contiguous()                    # [N, L]
+        pk["proj_w"] = self.proj.weight.detach()[..., 0].contiguous()
+        pk["mask_w"] = self.mask[1].weight.detach()[..., 0].contiguous()
+        pk["dec_w"] = self.decoder.weight.detach()[:, 0].t().contiguous()                # [L, N]: frame samples x channels
+        return pk
+
+    def forward(self, mix: th.Tensor):
+        """mix N x S -> [N x S', ...] (S' = (T - 1) * L/2 + L), tcn.py:326-358."""
+        if mix.dim() != 2:
+            raise RuntimeError(f"Expects 2D tensor (training), got {mix.dim()} instead")
+        if self.training:
+            raise RuntimeError("aps_b200.TimeConvTasNet implements the inference forward only: call .eval()")
+        dev = _lib.require_cuda(mix, "mixture")
+        if self._packs is None:
+            self._packs = self._build_packs()
+        pk = self._packs
+        mix = mix.detach().float().contiguous()
+        Nb, S = mix.shape
+        L, hop = self.L, self.L // 2
+        if S < L:
+            raise RuntimeError(f"mixture of {S} samples is shorter than the encoder window {L}")
+        T = (S - L) // hop + 1
+        nf = self.encoder.out_channels
+        # encoder: one GEMM per utterance batch over overlapping strided rows (row t = samples [t*hop, t*hop + L))
+        frames = mix.unfold(-1, L, hop).reshape(Nb * T, L).contiguous()   # materialised once: 2x the waveform, K = L
+        w = ops.linear(frames, pk["enc_w"], self.encoder.bias.detach(), act="relu")
+        g = self.ln
+        y = ops.utt_norm(w, Nb, T, g.weight.detach(), g.bias.detach(), g.eps)
+        y = self._lin(y, pk["proj_w"], self.proj.bias.detach())
+        y = _run_repeats(self._lin, self.conv, pk, y, Nb, T)
+        a = ops.dwconv1d(y, Nb, T, pk["ident"], None, act="prelu", slope=self.mask[0].weight.detach())
+        act = self.non_linear_type if self.non_linear_type != "softmax" else "none"
+        e = self._lin(a, pk["mask_w"], self.mask[1].bias.detach(), act=act)              # [N*T, spks*nf]
+        m = e.view(Nb * T, self.num_spks, nf)
+        if self.non_linear_type == "softmax":
+            m = th.softmax(m, 1)                                                          # over speakers (sse/base.py:50)
+        bss = []
+        To = (T - 1) * hop + L
+        for s in range(self.num_spks):
+            sw = (w * m[:, s]).contiguous()
+            f = ops.linear(sw, pk["dec_w"]).view(Nb, T, L)                                # frame-wise output samples
+            out = th.zeros((Nb, To), dtype=th.float32, device=dev)
+            out[:, :T * hop].view(Nb, T, hop).add_(f[..., :hop])
+            out[:, hop:(T + 1) * hop].view(Nb, T, hop).add_(f[..., hop:])
+            bss.append(out + self.decoder.bias.detach())
+        return bss[0] if self.num_spks == 1 else bss
+
+    def infer(self, mix: th.Tensor, mode: str = "time"):
+        if mix.dim() != 1:
+            raise RuntimeError(f"Expects 1D tensor (inference), got {mix.dim()} instead")
+        with th.no_grad():
+            sep = self.forward(mix[None, ...])
+            return sep[0] if self.num_spks == 1 else [s[0] for s in sep]

@@ -125,7 +125,39 @@ def norm_cases():
         save(f"enc_{7 + i}", cfg, **arrays)
 
 
+def time_tcn_cases():
+    """Time-domain Conv-TasNet (aps/sse/bss/tcn.py:228-358) on seeded mixtures."""
+    from aps.sse.bss.tcn import TimeConvTasNet
+    th.set_num_threads(4)
+    for i, kw in enumerate([dict(num_spks=2, non_linear="relu", norm="BN"),
+                            dict(num_spks=2, non_linear="softmax", norm="cLN", skip_residual=True, scaling_param=True),
+                            dict(num_spks=1, non_linear="sigmoid", norm="gLN", causal=True)]):
+        g = th.Generator().manual_seed(660 + i)
+        nkw = dict(L=20 if i != 1 else 16, N=48, X=3, R=2, B=16, H=24, P=3, **kw)
+        net = TimeConvTasNet(**nkw).eval()
+        with th.no_grad():
+            for name, buf in net.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+                if name.endswith("running_var"):
+                    buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+            for name, prm in net.named_parameters():
+                if prm.dim() <= 1 or name.endswith(("gamma", "beta")):
+                    prm.add_(0.1 * th.randn(prm.shape, generator=g))
+        mix = wave(660 + i, 3, 3003)
+        with th.no_grad():
+            wav = net(mix)
+            one = net.infer(mix[1])
+        stack = lambda v: th.stack(v) if isinstance(v, list) else v
+        arrays = dict(mix=mix, wav=stack(wav), one=stack(one))
+        arrays.update({"p." + k: v for k, v in net.state_dict().items()})
+        save(f"timetcn_{i}", dict(net=nkw), **arrays)
+
+
 def main():
+    if "--only-timetcn" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return time_tcn_cases()
     if "--only-norms" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         return norm_cases()
@@ -305,6 +337,7 @@ def main():
         save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
     objf_cases()
     norm_cases()
+    time_tcn_cases()
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)

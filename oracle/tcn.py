@@ -60,3 +60,27 @@ def tf_mask(sd: Dict[str, th.Tensor], feats: th.Tensor, num_repeats: int = 3, nu
     m = F.conv1d(F.prelu(x, sd["mask.0.weight"]), sd["mask.1.weight"], sd["mask.1.bias"])
     m = {"relu": th.relu, "sigmoid": th.sigmoid}[non_linear](m)
     return list(th.chunk(m, num_spks, 1))
+
+
+def time_tcn_forward(sd: Dict[str, th.Tensor], mix: th.Tensor, L: int = 20, num_repeats: int = 4, num_blocks: int = 8,
+                     num_spks: int = 2, norm: str = "BN", non_linear: str = "relu", causal: bool = False,
+                     skip_residual: bool = False) -> List[th.Tensor]:
+    """TimeConvTasNet.forward (tcn.py:326-358): mix N x S -> [N x S', ...]."""
+    w = th.relu(F.conv1d(mix[:, None], sd["encoder.weight"], sd["encoder.bias"], stride=L // 2))     # tcn.py:335
+    y = F.group_norm(w, 1, sd["ln.weight"], sd["ln.bias"])                                          # cLN, tcn.py:262
+    x = F.conv1d(y, sd["proj.weight"], sd["proj.bias"])
+    outs, skip = [x], 0
+    for r in range(num_repeats):
+        if skip_residual:
+            for i in range(r):
+                x = x + _scale_linear(sd, f"conv.skip_linear.{skip + i}.", outs[i])
+            outs[r] = x
+            skip += r
+        for b in range(num_blocks):
+            x = conv1d_block(sd, f"conv.repeat.{r}.{b}.", x, 2**b, norm, causal)
+        outs.append(x)
+    e = F.conv1d(F.prelu(x, sd["mask.0.weight"]), sd["mask.1.weight"], sd["mask.1.bias"])
+    m = th.stack(th.chunk(e, num_spks, 1), 0)                                                        # tcn.py:344-346
+    m = {"relu": th.relu, "sigmoid": th.sigmoid, "softmax": lambda t: th.softmax(t, 0)}[non_linear](m)
+    return [F.conv_transpose1d(w * m[n], sd["decoder.weight"], sd["decoder.bias"], stride=L // 2)[:, 0]
+            for n in range(num_spks)]
