@@ -15,7 +15,7 @@ import torch as th
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # APS_B200_LIB selects a tuning build of the same ABI (see aps_b200/build.py); default: the in-tree library
 LIB_PATH = os.environ.get("APS_B200_LIB") or os.path.join(_HERE, "libaps_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class StftDesc(Structure):
@@ -102,7 +102,7 @@ _SIGNATURES = {
     "aps_b200_conv2d_nhwc_tc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Epilogue),
                                             c_void_p, c_void_p]),
-    "aps_b200_conv_transpose2d_nhwc_tc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+    "aps_b200_conv_transpose2d_nhwc_tc_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                                       c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                       POINTER(Epilogue), c_void_p, c_void_p]),
     "aps_b200_conv2d_nhwc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,

@@ -194,6 +194,11 @@ struct AGather {
     // The GEMM rows are therefore enumerated CLASS-MAJOR (all rows with oh % sh == 0 first, then oh % sh == 1, ...), so
     // that a 128-row tile lies in one class and every role skips the k-blocks of the taps that are all-zero for it:
     // the zero-insertion work of the reference's conv_transpose2d (half of it at stride 2) is never done.
+    // Channel-concatenated input of the DCCRN decoder (dccrn.py "cat" connection on stacked complex channels):
+    // logical channels [re_a | re_b | im_a | im_b] with a = x, b = x2, each source holding 2*cat_c channels.  The gather
+    // reads the two tensors in place, so the concatenated tensor is never written (torch.cat was 9 % of the step).
+    const float* x2;
+    int cat_c;                // channels per part (0: single source x with Cin channels)
     int classes;              // sh (1 = plain row order)
     long long class_start[4]; // first GEMM row of each class
     int class_rows[4];        // output rows per image in each class
@@ -685,7 +690,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     else { ok = ok && (nh % a.sh) == 0; ih = nh / a.sh; }
                     ok = ok && ih < a.H;
                 }
-                prow[i] = ok ? a.x + (((long long)r_nb[i] * a.H + ih) * a.W) * a.Cin : nullptr;
+                const int csrc = a.cat_c ? 2 * a.cat_c : a.Cin;          // channels of the tensor(s) actually read
+                prow[i] = ok ? a.x + (((long long)r_nb[i] * a.H + ih) * a.W) * csrc : nullptr;
             }
         };
         // Gather of one k-block into registers.  Plain (L1-allocating) loads on purpose: L1 merges a warp's 16-byte lane
@@ -699,13 +705,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     v[i] = (prow[i] && k < p.K) ? __ldg(reinterpret_cast<const float4*>(prow[i] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
                 // Cin % 32 == 0: the whole k-block lies inside one (kh, kw) tap; stride_w == 1 for MODE 2 (host check)
-                const int coff = cb * BK + c * 4;
+                int coff = cb * BK + c * 4, csrc = a.Cin;
+                long long delta = 0;
+                if (a.cat_c) {                   // which of the four parts this (32-channel aligned) k-block lies in
+                    const int c0 = cb * BK, seg = c0 / a.cat_c;
+                    coff = (seg >> 1) * a.cat_c + (c0 - seg * a.cat_c) + c * 4;
+                    csrc = 2 * a.cat_c;
+                    delta = (seg & 1) ? (a.x2 - a.x) : 0;
+                }
                 const int dwk = MODE == 1 ? kw * a.dw : -kw;
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
                     const int iw = r_b[i] + dwk;
                     const bool ok = prow[i] != nullptr && (unsigned)iw < (unsigned)a.W;
-                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(prow[i] + (long long)iw * a.Cin + coff))
+                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(prow[i] + (long long)iw * csrc + coff + delta))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -1124,8 +1137,8 @@ extern "C" int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_
     return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream);
 }
 
-extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
-                                                     int64_t in_channels, const float* weight_hi,
+extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float* x_skip, int64_t batch, int64_t height,
+                                                     int64_t width, int64_t in_channels, const float* weight_hi,
                                                      const float* weight_lo, int64_t out_channels, int kernel_h,
                                                      int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
                                                      int out_pad_h, int out_pad_w, const aps_b200_epilogue* epi,
@@ -1137,6 +1150,13 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t bat
     APSB_CHECK_ARG(out_pad_h >= 0 && out_pad_w >= 0 && out_channels > 0, "bad convolution geometry");
     APSB_CHECK_ARG(stride_w == 1, "the tensor-core transposed convolution needs stride_w == 1 (got %d)", stride_w);
     a.mode = 2; a.dh = 1; a.dw = 1;
+    if (x_skip) {
+        APSB_CHECK_ARG(in_channels % 128 == 0 && ((uintptr_t)x_skip & 15) == 0,
+                       "a concatenated input needs four parts of a multiple of 32 channels (in_channels = %lld)",
+                       (long long)in_channels);
+        a.x2 = x_skip;
+        a.cat_c = (int)(in_channels / 4);
+    }
     const int64_t OH = (height - 1) * stride_h - 2 * pad_h + kernel_h + out_pad_h;
     const int64_t OW = (width - 1) * stride_w - 2 * pad_w + kernel_w + out_pad_w;
     APSB_CHECK_ARG(OH > 0 && OW > 0, "transposed convolution output is empty");

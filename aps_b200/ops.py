@@ -127,15 +127,30 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
     return out
 
 
+def cat_complex(a: th.Tensor, b: th.Tensor) -> th.Tensor:
+    """Channel concat of two stacked-complex NHWC tensors: [re_a | re_b | im_a | im_b]."""
+    ca, cb = a.shape[-1] // 2, b.shape[-1] // 2
+    return th.cat([a[..., :ca], b[..., :cb], a[..., ca:], b[..., cb:]], -1)
+
+
 def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0),
                           output_padding=(0, 0), act: str = "none", leaky: float = 0.0,
-                          cache: Optional["SplitCache"] = None) -> th.Tensor:
-    """x [B, H, W, Cin], weight [Cout, KH, KW, Cin] -> [B, OH, OW, Cout] (transposed convolution)."""
+                          cache: Optional["SplitCache"] = None, skip: Optional[th.Tensor] = None) -> th.Tensor:
+    """x [B, H, W, Cin], weight [Cout, KH, KW, Cin] -> [B, OH, OW, Cout] (transposed convolution).
+    `skip` (same shape as x): the input is cat_complex(x, skip); the tensor-core engine reads both in place."""
     dev = _lib.require_cuda(x, "conv input")
-    B, H, W, Cin = x.shape
     Cout, KH, KW, _ = weight.shape
+    B, H, W, Cx = x.shape
     OH = (H - 1) * stride[0] - 2 * padding[0] + KH + output_padding[0]
     OW = (W - 1) * stride[1] - 2 * padding[1] + KW + output_padding[1]
+    fused_skip = None
+    if skip is not None:
+        if (skip.shape == x.shape and Cx % 64 == 0 and stride[1] == 1 and x.is_contiguous() and skip.is_contiguous()
+                and skip.data_ptr() % 16 == 0 and _tc_conv_ok(x, 2 * Cx, Cout, B * OH * OW)):
+            fused_skip = skip
+        else:
+            x = cat_complex(x, skip)
+    Cin = 2 * Cx if fused_skip is not None else x.shape[-1]
     out = th.empty((B, OH, OW, Cout), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, 1.0, None, leaky)
     if _tc_conv_ok(x, Cin, Cout, B * OH * OW) and stride[1] == 1:     # the engine's transposed gather needs stride_w == 1
@@ -143,8 +158,9 @@ def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1,
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
         with th.cuda.device(dev):
             _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_tc_fwd(
-                x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
-                padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
+                x.data_ptr(), _lib.ptr(fused_skip), B, H, W, Cin, w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW,
+                stride[0], stride[1], padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(),
+                _lib.stream_ptr(dev)))
         return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_fwd(

@@ -150,10 +150,7 @@ def _pack_complex(real, imag, cbn, transposed: bool):
     return w.permute(0, 2, 3, 1).contiguous(), b.contiguous()
 
 
-def _cat_complex(a: th.Tensor, b: th.Tensor) -> th.Tensor:
-    """Channel concat of two stacked-complex NHWC tensors: [re_a | re_b | im_a | im_b]."""
-    ca, cb = a.shape[-1] // 2, b.shape[-1] // 2
-    return th.cat([a[..., :ca], b[..., :cb], a[..., ca:], b[..., cb:]], -1)
+_cat_complex = ops.cat_complex
 
 
 class DCCRN(nn.Module):
@@ -235,14 +232,17 @@ class DCCRN(nn.Module):
         out_i = r_all[N:] + i_all[N:]
         back = lambda t: t.view(N, T, Cc, Fq).permute(0, 3, 1, 2)          # -> N x F x T x Cc
         out = th.cat([back(out_r), back(out_i)], -1)
-        x = x + out if self.connection == "sum" else _cat_complex(out, x)
+        # "cat" skip connections are not materialised: the transposed-conv gather reads both tensors in place
+        cat = self.connection != "sum"
+        x, other = (out, x) if cat else (x + out, None)
         skips = skips[::-1]
         for i, (blk, (w, b)) in enumerate(zip(self.decoder[0].layers, pk["dec"])):
             if i:
-                x = x + skips[i - 1] if self.connection == "sum" else _cat_complex(x, skips[i - 1])
+                x, other = (x, skips[i - 1]) if cat else (x + skips[i - 1], None)
             x = ops.conv_transpose2d_nhwc(x.contiguous(), w, b, stride=blk.stride, padding=blk.padding,
                                           output_padding=blk.output_padding,
-                                          act="none" if blk.last else "leaky_relu", leaky=0.01, cache=self._splits)
+                                          act="none" if blk.last else "leaky_relu", leaky=0.01, cache=self._splits,
+                                          skip=other.contiguous() if other is not None else None)
         return x
 
     def _infer(self, mix: th.Tensor, mode: str):

@@ -267,8 +267,10 @@ def run_extra(args):
         frames, launches = B * (S // HOP), 1 + 7 + 7 + 2 * 2 + 2 + 6
         ach = flops / (ms / args.steps * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "kernel": "gemm_kernel<.., ConvA/ConvT> (exact-fp32 SIMT implicit GEMM on stacked re/im "
-                                           "channels) dominates; STFT, iSTFT x2, cmask, cuDNN LSTM bottleneck, fused Si-SNR",
+                "traffic": None, "kernel": "tc_gemm_kernel<BN, conv / conv_transpose> (tcgen05 3xTF32 implicit GEMMs on stacked "
+                                           "re/im channels; FLOPs counted as the reference computes them, incl. the zero taps "
+                                           "of the transposed convolutions that the kernel skips) + cuDNN LSTM bottleneck "
+                                           "(exact fp32, ~45 % of the step), STFT, iSTFT x2, cmask, fused Si-SNR",
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"}
         wl = ("DCCRN (C=16..256, cat, 2 spk) forward + PIT Si-SNR on B=128 x 4 s (configs[4]); value in 10 ms frames/s")
     else:

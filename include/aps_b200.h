@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define APS_B200_ABI_VERSION 2
+#define APS_B200_ABI_VERSION 3
 
 /* library / device ------------------------------------------------------------------------ */
 int aps_b200_abi_version(void);
@@ -226,9 +226,12 @@ int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, i
                                 int64_t out_channels, int kernel_h, int kernel_w, int stride_h, int stride_w,
                                 int pad_h, int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
                                 float* out, void* stream);
-/* ConvTranspose2d as an implicit gather GEMM (as aps_b200_conv_transpose2d_nhwc_fwd): dcunet.py:48-70       */
-int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
-                                          int64_t in_channels, const float* weight_hi,
+/* ConvTranspose2d as an implicit gather GEMM (as aps_b200_conv_transpose2d_nhwc_fwd; stride_w == 1): dcunet.py:48-70.
+ * x_skip != NULL: the input is the "cat" skip connection of the DCCRN decoder on stacked complex channels,
+ * [re(x) | re(x_skip) | im(x) | im(x_skip)] (aps/sse/enh/dcunet.py:258-262, dccrn.py:285), with x and x_skip of
+ * in_channels / 2 channels each, read in place — the concatenated tensor is never materialised.                   */
+int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float* x_skip, int64_t batch, int64_t height,
+                                          int64_t width, int64_t in_channels, const float* weight_hi,
                                           const float* weight_lo, int64_t out_channels, int kernel_h,
                                           int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
                                           int out_pad_h, int out_pad_w, const aps_b200_epilogue* epi,

@@ -194,6 +194,30 @@ def test_tensor_core_conv_transpose_vs_torch(monkeypatch, classes):
 
 
 @pytest.mark.gpu
+def test_tensor_core_conv_transpose_fused_skip(monkeypatch):
+    """DCCRN "cat" skip connection read in place by the transposed-conv gather == conv_transpose2d(cat_complex(x, skip))."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    th.manual_seed(6)
+    for (B, H, W, C2, Co) in ((2, 9, 30, 64, 32), (3, 4, 25, 128, 128), (2, 17, 40, 64, 4)):
+        x, sk = th.randn(B, H, W, C2), th.randn(B, H, W, C2)
+        w, b = th.randn(Co, 3, 3, 2 * C2) * 0.05, th.randn(Co)
+        cat = ops.cat_complex(x, sk)                                            # [re_x | re_s | im_x | im_s]
+        ref = F.conv_transpose2d(cat.permute(0, 3, 1, 2).double(), w.permute(3, 0, 1, 2).double(), b.double(),
+                                 stride=(2, 1), padding=(1, 1)).permute(0, 2, 3, 1)
+        got = ops.conv_transpose2d_nhwc(x.to(DEV), w.to(DEV), b.to(DEV), stride=(2, 1), padding=(1, 1), skip=sk.to(DEV))
+        assert got.shape == ref.shape and rel_err(got, ref) < 3e-5
+        # a shape the engine does not take (C2 = 16) goes through the materialised concat
+    x, sk = th.randn(1, 5, 7, 16), th.randn(1, 5, 7, 16)
+    w, b = th.randn(6, 3, 3, 32) * 0.1, th.randn(6)
+    ref = F.conv_transpose2d(ops.cat_complex(x, sk).permute(0, 3, 1, 2), w.permute(3, 0, 1, 2), b, stride=(2, 1),
+                             padding=(1, 1)).permute(0, 2, 3, 1)
+    got = ops.conv_transpose2d_nhwc(x.to(DEV), w.to(DEV), b.to(DEV), stride=(2, 1), padding=(1, 1), skip=sk.to(DEV))
+    assert rel_err(got, ref) < 1e-5
+
+
+@pytest.mark.gpu
 def test_dense_kernels_vs_torch(monkeypatch):
     """Exact-fp32 (SIMT) GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the
     CPU (the tensor-core engine has its own tests above)."""
