@@ -169,6 +169,21 @@ struct SmallFFT<16, INV> {
     }
 };
 
+// exp(-i pi q / 16), q = 0..15: the split twiddle of bin k = l + G q is W^l * this constant (pi k / NC = pi l / NC + pi q / 16
+// for every supported NC), so a lane keeps ONE table value in a register and derives its 16 split twiddles with two packed
+// instructions each instead of 16 shared-memory loads per frame (the F1 kernel is shared-memory-wavefront bound).
+__device__ __forceinline__ float2 split_step(int q) {
+    const float c[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                         0.f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                         -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+    const float s[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                         0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                         1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+    return make_float2(c[q], -s[q]);
+}
+
 // ---- plan: radices for a complex length NC (32..512) ------------------------------------------
 template <int NC>
 struct FFTPlan {

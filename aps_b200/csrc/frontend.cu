@@ -352,6 +352,12 @@ __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(
             // partner bins come by shuffle; the first shuffle is also the point where every lane of the
             // group is done reading the exchange buffer, so the magnitudes may overwrite it afterwards
             const int psrc = (lane & ~(G - 1)) | ((G - l) & (G - 1));
+#ifndef APSB_PTW_TABLE
+            const float2 ptw_l = sm_ptw[l];     // h * exp(-i pi l / NC); bin l + G q needs this times exp(-i pi q / 16)
+#define APSB_PTW(k_, q_) cmul(ptw_l, split_step(q_))
+#else
+#define APSB_PTW(k_, q_) sm_ptw[k_]
+#endif
 
             if constexpr (MODE == 1) {
                 // ---- F2: write the one-sided spectrum into the transposed tile ------------------------
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(
                 for (int q = 0; q < 16; ++q) {
                     const int k = l + G * q;
                     const float2 zp = partner_of<NC>(v, 15 - q, (16 - q) & 15, psrc, l, mask);
-                    float2 X = rfft_split(v[q], zp, sm_ptw[k], half);
+                    float2 X = rfft_split(v[q], zp, APSB_PTW(k, q), half);
                     if (p.polar) X = make_float2(sqrtf(fmaf(X.x, X.x, fmaf(X.y, X.y, p.polar_eps))), atan2f(X.y, X.x));
                     if (f < nf) sm_tile[k * ts + f] = X;
                 }
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, APSB_FRONTEND_MINB) frontend_kernel(
                 for (int q = 0; q < 16; ++q) {
                     const int k = l + G * q;
                     const float2 zp = partner_of<NC>(v, 15 - q, (16 - q) & 15, psrc, l, mask);
-                    const float2 X = rfft_split(v[q], zp, sm_ptw[k], half);
+                    const float2 X = rfft_split(v[q], zp, APSB_PTW(k, q), half);
                     const float pw = fmaf(X.x, X.x, X.y * X.y);
                     mag[k] = (p.ft.power == 2) ? pw : fast_sqrt(pw);
                 }
