@@ -723,7 +723,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
             }
         };
-        constexpr int D = BK == 16 ? 3 : 2;     // k-blocks of gathers in flight (registers)
+        // k-blocks of gathers in flight (registers): as deep as the register budget of the role allows — the linear
+        // mode carries no per-row convolution geometry, so it affords one more block
+        constexpr int D = BK == 16 ? 4 : (MODE == 0 ? 3 : 2);
         // iterator over the (tile, tap, k-block) sequence of this CTA, skipping taps that are zero for the tile's class
         unsigned ltile = blockIdx.x;
         int lkh = 0, lcb = 0, lkw = 0, lh = 0, lcls = -1;   // lcb counts 32-channel groups, lh the half inside (BK = 16)
