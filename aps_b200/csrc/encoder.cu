@@ -133,7 +133,7 @@ struct AttnParams {
     long long ldo;
 };
 
-constexpr int kAttnWarps = 8;    // queries per CTA
+constexpr int kAttnWarps = 16;   // queries per CTA: the K / V / position tiles are re-read once per query tile, so fewer, larger tiles
 constexpr int kKeyTile = 32;
 
 // CTA = (query tile, head, batch); one warp per query; lane = key inside the tile; dh <= 128

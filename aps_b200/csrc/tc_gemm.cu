@@ -958,7 +958,10 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
 template <int BN, int MODE>
 static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const TcParams& p, long long grid, cudaStream_t st) {
     using C = TcCfg<BN>;
-    static bool attr = false;
+    static bool attr_done[64] = {false};       // function attributes are per device (one context per GPU)
+    int dev = 0;
+    APSB_CUDA(cudaGetDevice(&dev));
+    bool& attr = attr_done[dev & 63];
     if (!attr) {
         APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         // smallest shared-memory carve-out that holds the CTA: what is left of the 228 KB array stays L1 for the gathers
