@@ -154,7 +154,41 @@ def time_tcn_cases():
         save(f"timetcn_{i}", dict(net=nkw), **arrays)
 
 
+def reference_fixture_cases():
+    """The reference's OWN test fixtures (tests/python/test_transform.py:102-150 on tests/data/transform/egs1.wav and
+    egs2.wav): the shapes its tests assert (807 frames; [1, 5, 257, 366, 2]) plus the values it computes.  Outputs are
+    stored for every `STEP`-th frame to keep the files small; the int16 samples are stored losslessly."""
+    from scipy.io import wavfile
+
+    from aps.transform import AsrTransform, EnhTransform
+    th.set_num_threads(4)
+    STEP = 8
+    data = os.path.join(REF, "tests", "data", "transform")
+    _, w1 = wavfile.read(os.path.join(data, "egs1.wav"))
+    x1 = th.from_numpy(w1.astype(np.float32) / 32768.0)[None]
+    arrays, shapes = {"pcm": w1}, {}
+    for mode in ("librosa", "torch"):
+        for feats in ("spectrogram-log", "emph-fbank-log-cmvn", "mfcc", "mfcc-splice", "mfcc-delta"):
+            t = AsrTransform(feats=feats, stft_mode=mode, frame_len=400, frame_hop=160, use_power=True, pre_emphasis=0.96)
+            y, _ = t(x1.clone(), None)
+            key = f"{mode}.{feats}"
+            shapes[key] = list(y.shape)
+            arrays[key] = y[:, ::STEP]
+    save("ref_egs1", dict(step=STEP, shapes=shapes, frame_len=400, frame_hop=160, use_power=True, pre_emphasis=0.96), **arrays)
+    _, w2 = wavfile.read(os.path.join(data, "egs2.wav"))
+    x2 = th.from_numpy(w2.T.astype(np.float32) / 32768.0)[None]                # 1 x 5 x S
+    t = EnhTransform(feats="ipd", frame_len=512, frame_hop=256, ipd_index="0,1;0,2;0,3;0,4")
+    packed, _ = t.encode(x2, None)
+    feats = t(packed)
+    save("ref_egs2", dict(step=STEP, packed_shape=list(packed.shape), feats_shape=list(feats.shape), frame_len=512,
+                          frame_hop=256, ipd_index="0,1;0,2;0,3;0,4"),
+         pcm=w2, packed=packed[..., ::STEP, :], feats=feats[:, ::STEP])
+
+
 def main():
+    if "--only-fixtures" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return reference_fixture_cases()
     if "--only-timetcn" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         return time_tcn_cases()
@@ -338,6 +372,7 @@ def main():
     objf_cases()
     norm_cases()
     time_tcn_cases()
+    reference_fixture_cases()
     # state-dict layout of the recipe transform (conf/asr/aishell_v1/1e.yaml:17-40)
     t = AsrTransform(feats="perturb-fbank-log-cmvn-aug", frame_len=400, frame_hop=160, window="hamm",
                      audio_norm=False, pre_emphasis=0.97, stft_mode="kaldi", log_lower_bound=1, num_mels=80)

@@ -302,6 +302,40 @@ class AsrFeatCfg:
     eps: float = F32_EPS
     gmean: Optional[th.Tensor] = field(default=None, repr=False)
     gstd: Optional[th.Tensor] = field(default=None, repr=False)
+    num_ceps: int = 13
+    lifter: float = 0
+    lctx: int = 1
+    rctx: int = 1
+    subsampling_factor: int = 1
+    delta_ctx: int = 2
+    delta_order: int = 2
+
+
+def dct_matrix(num_ceps: int, num_mels: int) -> th.Tensor:
+    """Orthonormal DCT-II rows (scipy.fftpack.dct(eye, norm="ortho")[:, :num_ceps].T, asr.py:483-487): [num_ceps, num_mels]."""
+    n = th.arange(num_mels, dtype=th.float64)
+    k = th.arange(num_ceps, dtype=th.float64)[:, None]
+    m = th.cos(math.pi * (2 * n + 1) * k / (2 * num_mels)) * math.sqrt(2.0 / num_mels)
+    m[0] = m[0] / math.sqrt(2.0)
+    return m.float()
+
+
+def splice(feats: th.Tensor, lctx: int, rctx: int, op: str = "cat") -> th.Tensor:
+    """aps/transform/utils.py:193-224 (edge frames repeat)."""
+    if lctx + rctx == 0:
+        return feats
+    T = feats.shape[-2]
+    ctx = [feats.index_select(-2, th.arange(c, c + T).clamp(0, T - 1)) for c in range(-lctx, rctx + 1)]
+    return th.cat(ctx, -1) if op == "cat" else th.stack(ctx, -1)
+
+
+def delta(feats: th.Tensor, ctx: int = 2, order: int = 2) -> th.Tensor:
+    """asr.py:731-781 (delta_as_channel=False)."""
+    scale = th.arange(-ctx, ctx + 1, dtype=th.float32) / sum(i * i for i in range(-ctx, ctx + 1))
+    out = [feats]
+    for _ in range(order):
+        out.append(th.sum(splice(out[-1], ctx, ctx, "stack") * scale, -1))
+    return th.cat(out, -1)
 
 
 class AsrFeatures:
@@ -349,11 +383,22 @@ class AsrFeatures:
             if tok == "emph":                                # asr.py:111-113 (utterance level)
                 if c.pre_emphasis > 0:
                     x = th.cat([x[..., :1], x[..., 1:] - c.pre_emphasis * x[..., :-1]], -1)
-            elif tok in ("spectrogram", "fbank"):
+            elif tok in ("spectrogram", "fbank", "mfcc"):
                 x = magnitude(self.stft(x)).transpose(-1, -2)
                 x = x**(2 if c.use_power else 1)             # asr.py:357
-                if tok == "fbank":
+                if tok != "spectrogram":
                     x = F.linear(x, self.mel)                # asr.py:427
+                if tok == "mfcc":                            # asr.py:931-945: fbank -> log -> DCT (+ lifter)
+                    x = F.linear(log_compress(x, c.eps, c.log_lower_bound), dct_matrix(c.num_ceps, c.num_mels))
+                    if c.lifter > 0:
+                        x = x * (1 + c.lifter * 0.5 * th.sin(math.pi * th.arange(1, 1 + c.num_ceps) / c.lifter))
+            elif tok == "splice":                            # asr.py:687-728
+                x = splice(x, max(c.lctx, 0), max(c.rctx, 0))
+                if c.subsampling_factor != 1:
+                    end = (x.shape[-2] // c.subsampling_factor) * c.subsampling_factor
+                    x = x[..., :end:c.subsampling_factor, :]
+            elif tok == "delta":
+                x = delta(x, c.delta_ctx, c.delta_order)
             elif tok == "log":
                 x = log_compress(x, c.eps, c.log_lower_bound)
             elif tok == "cmvn":
