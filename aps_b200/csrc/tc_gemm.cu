@@ -649,6 +649,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         constexpr int RPT = TC_BM / RSTEP;          // rows per thread (= CPR)
         const int pt = threadIdx.x - WARP_PROD0 * 32;
         const int c = pt % CPR, rg = pt / CPR;
+        static_assert(RSTEP % 8 == 0, "rows of one thread must share the swizzle phase");
+        const uint32_t prod_base = s_u32(base) + (uint32_t)rg * (uint32_t)SWZ +
+                                   (uint32_t)((c ^ (SWZ == 128 ? (rg & 7) : ((rg >> 1) & 3))) << 4);
         const AGather& a = p.a;
         // Per-row geometry is resolved when the tile or the kernel row kh changes (rare); the per-k-block path is then a
         // bounds check on iw, one multiply-add and the load — about 50 instructions instead of 400, which matters
@@ -812,24 +815,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #ifdef APSB_TC_TRACE
                     const long long c1_ = clock64();
 #endif
-                    uint8_t* st = base + s * C::STAGE_BYTES;
+                    // 32-bit shared-window addresses and st.shared: through the generic pointer the compiler emitted generic
+                    // ST.E with 64-bit address arithmetic per store.  Rows rg + RSTEP * i share the swizzle term
+                    // (RSTEP % 8 == 0), so the row offsets are immediates.
+                    const uint32_t sa = prod_base + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
 #ifdef APSB_TC_TRACE
                     if (!(p.dbg & 1))
 #endif
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
-                        const int r = rg + RSTEP * i;
-                        const int sw = SWZ == 128 ? (r & 7) : ((r >> 1) & 3);
-                        const uint32_t off = (uint32_t)r * (uint32_t)SWZ + (uint32_t)((c ^ sw) << 4);
                         const float4 v = ring[d][i];
-                        // lo = v - hi is exact; the tensor core drops its low mantissa bits itself (tf32 operand)
-                        float4 h, l;
-                        h.x = rn_tf32(v.x); l.x = v.x - h.x;
-                        h.y = rn_tf32(v.y); l.y = v.y - h.y;
-                        h.z = rn_tf32(v.z); l.z = v.z - h.z;
-                        h.w = rn_tf32(v.w); l.w = v.w - h.w;
-                        *reinterpret_cast<float4*>(st + off) = h;
-                        *reinterpret_cast<float4*>(st + A_BYTES + off) = l;
+                        // hi = rn_tf32(v) as two integer ops: add half an ulp of the 10-bit mantissa, clear the low 13 bits
+                        // (bit-identical to cvt.rna.tf32.f32 for finite inputs; sm_100a emulates that cvt with four
+                        // instructions).  lo = v - hi is exact; the tensor core drops its low mantissa bits itself.
+                        const uint32_t hx = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u;
+                        const uint32_t hy = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
+                        const uint32_t hz = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u;
+                        const uint32_t hw = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
+                        const float lx = v.x - __uint_as_float(hx), ly = v.y - __uint_as_float(hy);
+                        const float lz = v.z - __uint_as_float(hz), lw = v.w - __uint_as_float(hw);
+                        const uint32_t dst = sa + (uint32_t)(i * RSTEP * SWZ);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hx), "r"(hy), "r"(hz), "r"(hw)
+                                     : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)A_BYTES), "f"(lx), "f"(ly),
+                                     "f"(lz), "f"(lw)
+                                     : "memory");
                     }
 #ifdef APSB_TC_TRACE
                     if (!(p.dbg & 4))

@@ -214,6 +214,41 @@ def utt_norm(x: th.Tensor, N: int, T: int, gamma=None, beta=None, eps: float = 1
     return out
 
 
+def lstm(x: th.Tensor, lstm_mod, cache: Optional[dict] = None) -> th.Tensor:
+    """torch.nn.LSTM forward (batch_first, zero initial state, inference) on x [N, T, In] with the parameters of
+    `lstm_mod` (an nn.LSTM): per layer and direction one tensor-core GEMM for the input projections of all frames and
+    the fused per-frame recurrence kernel (aps_b200_lstm_fwd).  Returns [N, T, H * directions]."""
+    dev = _lib.require_cuda(x, "LSTM input")
+    if not lstm_mod.batch_first or getattr(lstm_mod, "proj_size", 0):
+        raise RuntimeError("ops.lstm: only batch_first nn.LSTM without projections is implemented")
+    if lstm_mod.training and lstm_mod.dropout > 0 and lstm_mod.num_layers > 1:
+        raise RuntimeError("ops.lstm: inter-layer dropout (training mode) is not implemented")
+    N, T, _ = x.shape
+    H, dirs = lstm_mod.hidden_size, 2 if lstm_mod.bidirectional else 1
+    if H % 4:
+        raise RuntimeError(f"ops.lstm: hidden_size ({H}) must be a multiple of 4")
+    lib = _lib.load()
+    cell = th.empty(N, H, dtype=th.float32, device=dev)
+    inp = x.contiguous().float()
+    for layer in range(lstm_mod.num_layers):
+        y = th.empty(N, T, H * dirs, dtype=th.float32, device=dev)
+        for d in range(dirs):
+            sfx = f"_l{layer}" + ("_reverse" if d else "")
+            w_ih = getattr(lstm_mod, "weight_ih" + sfx).detach()
+            w_hh = getattr(lstm_mod, "weight_hh" + sfx).detach().contiguous()
+            if lstm_mod.bias:
+                bias = getattr(lstm_mod, "bias_ih" + sfx).detach() + getattr(lstm_mod, "bias_hh" + sfx).detach()
+            else:
+                bias = None
+            xg = linear(inp.view(N * T, -1), w_ih, bias, cache=cache)
+            with th.cuda.device(dev):
+                _lib.check(lib.aps_b200_lstm_fwd(xg.data_ptr(), xg.stride(0), N, T, H, w_hh.data_ptr(), d,
+                                                 cell.data_ptr(), y.data_ptr() + 4 * H * d, H * dirs,
+                                                 _lib.stream_ptr(dev)))
+        inp = y
+    return inp
+
+
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
              stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
              residual=None, post=None) -> th.Tensor:

@@ -9,8 +9,9 @@ into weight and bias and LeakyReLU in the epilogue.  Activations are channels-la
 packed STFT [N, F, T, 2] is already that layout for the first layer.  STFT / iSTFT are the F2 / F3
 kernels, the complex ratio mask + mask application one small kernel.
 
-The two-layer LSTM bottleneck stays `torch.nn.LSTM` (cuDNN): a sequential recurrence over T, not a
-data-parallel contraction — its share is reported separately by bench.py.
+The two-layer complex LSTM bottleneck (dccrn.py:20-110) keeps its parameters in `torch.nn.LSTM` modules
+(reference `state_dict` layout) but runs through `ops.lstm`: one tensor-core GEMM per layer for the input
+projections of all frames and a fused recurrence + cell-update launch per frame (csrc/lstm.cu).
 Inference (`eval()`) only; `cplx=True`, `share_decoder=True`, non-causal convolutions.
 """
 import os
@@ -24,6 +25,7 @@ from ... import _lib, ops
 
 EPSILON = float(np.finfo(np.float32).eps)
 LSTM_TF32 = os.environ.get("APS_B200_LSTM_TF32", "0") == "1"
+LSTM_ENGINE = os.environ.get("APS_B200_LSTM", "fused")        # "cudnn": torch.nn.LSTM (library), A/B only
 
 
 def parse_1dstr(s: str) -> List[int]:
@@ -105,11 +107,17 @@ class LSTMP(nn.Module):
         self.proj = nn.Linear(hidden_size * 2 if bidirectional else hidden_size, in_features, bias=False)
 
     def forward(self, x: th.Tensor) -> th.Tensor:            # N x T x D
-        # cuDNN would run the recurrent GEMMs as single-pass TF32 by default (torch.backends.cudnn.allow_tf32): switched
-        # off — the parity contract is against the reference's fp32 CPU path (APS_B200_LSTM_TF32=1 re-enables it:
-        # 66 -> 50 ms per B = 128 step, ~1e-3 relative error inside the recurrence)
-        with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
-            out, _ = self.lstm(x)
+        if LSTM_ENGINE == "cudnn":
+            # library path kept for A/B only.  cuDNN would run the recurrent GEMMs as single-pass TF32 by default
+            # (torch.backends.cudnn.allow_tf32): off unless APS_B200_LSTM_TF32=1 (~1e-3 error inside the recurrence)
+            with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
+                out, _ = self.lstm(x)
+        else:
+            # input projections of all frames on the tensor-core engine + one fused launch per frame for the
+            # recurrence and the cell update (csrc/lstm.cu), exact fp32
+            if not hasattr(self, "_splits"):
+                self._splits = ops.SplitCache()
+            out = ops.lstm(x, self.lstm, cache=self._splits)
         N, T, H = out.shape
         return ops.linear(out.reshape(N * T, H), self.proj.weight.detach()).view(N, T, -1)
 

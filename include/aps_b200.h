@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define APS_B200_ABI_VERSION 3
+#define APS_B200_ABI_VERSION 4
 
 /* library / device ------------------------------------------------------------------------ */
 int aps_b200_abi_version(void);
@@ -323,6 +323,17 @@ int aps_b200_utt_norm_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t n
                           int64_t stride_n, int64_t stride_t, int per_channel, const float* gamma,
                           const float* beta, float eps, int relu, void* workspace, int64_t workspace_bytes,
                           float* out, int64_t ld_out, void* stream);
+
+/* LSTM recurrence of one layer and direction ---------------------------------------------------
+ * torch.nn.LSTM semantics (gate order i, f, g, o; h_0 = c_0 = 0), as used by the DCCRN bottleneck
+ * (aps/sse/bss/dccrn.py:20-50: LSTMP -> nn.LSTM, batch_first).  xg [rows, num_frames, ld_xg >= 4H]
+ * holds x_t W_ih^T + b_ih + b_hh of every frame (one aps_b200_linear_*_fwd call); this entry adds
+ * h_{t-1} W_hh^T (w_hh [4H, H] row-major), applies the cell update and writes h_t to
+ * y [rows, num_frames, ld_y >= H] (a bidirectional layer passes ld_y = 2H and y + H for the
+ * reverse direction, reverse != 0 walks the frames backwards).  cell: [rows, H] scratch.
+ * One fused launch per frame, exact fp32 arithmetic.  hidden % 4 == 0, ld_y % 4 == 0.             */
+int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
+                      const float* w_hh, int reverse, float* cell, float* y, int64_t ld_y, void* stream);
 
 /* Time-domain separation objectives ----------------------------------------------------------
  * Si-SNR / SNR between every estimate and every reference of an utterance in ONE pass over the

@@ -103,4 +103,4 @@ def test_c5_dccrn_full_size_subset_vs_oracle():
     assert rel_err(y[rows], ref) < FLOAT_TOL
     assert float(sisnr(y[rows].cpu(), ref).min()) > 70.0
     alone = dev_net(x[rows].to(DEV))
-    assert rel_err(alone, y[rows]) < 1e-5        # cuDNN LSTM may pick a different algorithm per batch size
+    assert rel_err(alone, y[rows]) < 1e-5        # projection GEMM tiles differ with the batch size
