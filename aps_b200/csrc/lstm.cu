@@ -4,9 +4,10 @@
 // The input projection x_t W_ih^T + b_ih + b_hh of ALL frames is one large GEMM done beforehand on the tensor-core
 // engine (ops.linear); what is left per frame is gates = xg_t + h_{t-1} W_hh^T, the cell update and h_t — a
 // [rows, H] x [H, 4H] product that is sequential over frames.  One launch per frame fuses the product with the cell
-// update: a CTA owns 32 rows x 16 hidden units (all four gates of a unit sit in one thread, so the cell update needs
-// no exchange), walks K = H in 32-wide chunks through double-buffered shared memory and writes h_t straight into the
-// layer output y[:, t, :], which is also where frame t + 1 reads h_{t-1} from.  Exact fp32 FMA arithmetic, precise
+// update: a CTA owns 64 rows x 16 hidden units (all four gates of a unit sit in one thread, so the cell update needs
+// no exchange), walks K = H in 32-wide chunks through a 4-stage cp.async ring and writes h_t straight into the
+// layer output y[:, t, :], which is also where frame t + 1 reads h_{t-1} from.  Launches are chained with
+// programmatic dependent launch: frame t + 1 prefetches W_hh and its input projections while frame t finishes.  Exact fp32 FMA arithmetic, precise
 // expf / tanhf: the recurrence amplifies rounding, and parity is against the reference's fp32 CPU path.
 //
 // Bound by the fp32 FMA pipe: 2 * rows * 4H * H flop per frame (0.54 GFLOP at rows = 256, H = 512) against
@@ -16,16 +17,19 @@
 
 namespace apsb {
 
-constexpr int kLstmBM = 32;        // rows per CTA
+constexpr int kLstmBM = 64;        // rows per CTA
 constexpr int kLstmBU = 16;        // hidden units per CTA (x 4 gates = 64 gate columns)
 constexpr int kLstmBK = 32;        // k chunk
-constexpr int kLstmThreads = 128;  // thread = 4 rows x 1 unit x 4 gates
-constexpr int kLstmALd = kLstmBK + 4;
+constexpr int kLstmStages = 4;     // cp.async ring depth (3 chunks = 24 KB per CTA in flight: covers the L2 latency)
+constexpr int kLstmThreads = 256;  // thread = 4 rows x 1 unit x 4 gates
+constexpr int kLstmLd = kLstmBK + 4;                                   // padded row: conflict-free float4 reads
+constexpr int kLstmTile = (kLstmBM + 4 * kLstmBU) * kLstmLd;           // floats per stage: h rows, then W_hh rows
+constexpr int kLstmSmem = kLstmStages * kLstmTile * 4;
 
 struct LstmStepParams {
     const float* xg;      // [rows][4H] of this frame, row stride ldx
     long long ldx;
-    const float* h_prev;  // [rows][H] of the previous frame, row stride ldh; null on the first frame (h = 0)
+    const float* h_prev;  // [rows][H] of the previous frame, row stride ldh (unused on the first frame: h = 0)
     long long ldh;
     float* c;             // [rows, H] cell state, updated in place
     float* y;             // [rows][H] of this frame, row stride ldy
@@ -36,25 +40,75 @@ struct LstmStepParams {
 
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.f / (1.f + expf(-x)); }
 
+// 16-byte global -> shared copy, zero-filled when !valid
+__device__ __forceinline__ void lstm_cp16(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_constant__ LstmStepParams p) {
-    __shared__ __align__(16) float As[2][kLstmBM][kLstmALd];
-    __shared__ __align__(16) float Ws[2][kLstmBK][kLstmBU * 4];
+    extern __shared__ __align__(16) float lstm_smem[];
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int u0 = blockIdx.x * kLstmBU, r0 = blockIdx.y * kLstmBM;
     const int H = p.H;
     const int unit = u0 + tx;
     const bool unit_ok = unit < H;
+    const int nchunks = p.first ? 0 : (H + kLstmBK - 1) / kLstmBK;
 
-    // gate pre-activations from the input projection and the old cell state: issued first, consumed last
-    float xg[4][4], c_old[4];
+    // gate pre-activations from the input projection: independent of the previous frame, issued first, consumed last
+    float xg[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int row = r0 + ty * 4 + r;
         const bool ok = unit_ok && row < p.rows;
 #pragma unroll
         for (int g = 0; g < 4; ++g) xg[r][g] = ok ? __ldg(p.xg + (long long)row * p.ldx + (long long)g * H + unit) : 0.f;
-        c_old[r] = (ok && !p.first) ? p.c[(long long)row * H + unit] : 0.f;
+    }
+
+    // chunk -> ring stage: this thread copies two 16-byte pieces of the h tile and two of the W_hh tile (k-major rows,
+    // exactly as they lie in global memory: no transposition, so the copies can be asynchronous)
+    const int lrow = tid >> 3, lkq = tid & 7;                       // + 32 rows for the second piece
+    auto issue_w = [&](int chunk) {
+        float* st = lstm_smem + (chunk % kLstmStages) * kLstmTile + kLstmBM * kLstmLd;
+        const int k = chunk * kLstmBK + 4 * lkq;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = lrow + 32 * j, g = col >> 4, u = u0 + (col & 15);
+            const bool ok = u < H && k < H;
+            lstm_cp16(st + col * kLstmLd + 4 * lkq, ok ? p.w + ((long long)g * H + u) * H + k : p.w, ok);
+        }
+    };
+    auto issue_h = [&](int chunk) {
+        float* st = lstm_smem + (chunk % kLstmStages) * kLstmTile;
+        const int k = chunk * kLstmBK + 4 * lkq;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = lrow + 32 * j;
+            const bool ok = r0 + row < p.rows && k < H;
+            lstm_cp16(st + row * kLstmLd + 4 * lkq, ok ? p.h_prev + (long long)(r0 + row) * p.ldh + k : p.w, ok);
+        }
+    };
+
+    // W_hh does not depend on the previous frame: its first stages are requested before waiting for the previous
+    // launch (programmatic dependent launch), which hides the launch latency and the first L2 round trip
+#pragma unroll
+    for (int st = 0; st < kLstmStages - 1; ++st)
+        if (st < nchunks) issue_w(st);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#pragma unroll
+    for (int st = 0; st < kLstmStages - 1; ++st) {
+        if (st < nchunks) issue_h(st);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    float c_old[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = r0 + ty * 4 + r;
+        c_old[r] = (unit_ok && row < p.rows && !p.first) ? p.c[(long long)row * H + unit] : 0.f;
     }
 
     float acc[4][4];
@@ -63,70 +117,32 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
 
-    if (!p.first) {
-        const int nchunks = (H + kLstmBK - 1) / kLstmBK;
-        float4 ra[2], rw[4];
-        auto load_global = [&](int chunk) {
-            const int k0 = chunk * kLstmBK;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kLstmStages - 2) : "memory");
+        __syncthreads();                      // chunk landed for everyone; everyone is done with chunk - 1's stage
+        if (chunk + kLstmStages - 1 < nchunks) {
+            issue_w(chunk + kLstmStages - 1);
+            issue_h(chunk + kLstmStages - 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const float* As = lstm_smem + (chunk % kLstmStages) * kLstmTile + (ty * 4) * kLstmLd;
+        const float* Ws = lstm_smem + (chunk % kLstmStages) * kLstmTile + (kLstmBM + tx) * kLstmLd;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int idx = tid + kLstmThreads * j, kq = idx & 7, row = r0 + (idx >> 3), k = k0 + 4 * kq;
-                ra[j] = (row < p.rows && k < H) ? __ldg(reinterpret_cast<const float4*>(p.h_prev + (long long)row * p.ldh + k))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int kq = 0; kq < kLstmBK / 4; ++kq) {
+            float4 a[4], w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + kLstmThreads * j, kq = idx & 7, g = (idx >> 3) & 3, u = u0 + (idx >> 5), k = k0 + 4 * kq;
-                rw[j] = (u < H && k < H) ? __ldg(reinterpret_cast<const float4*>(p.w + ((long long)g * H + u) * H + k))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        auto store_smem = [&](int buf) {
+            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(As + r * kLstmLd + 4 * kq);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int idx = tid + kLstmThreads * j, kq = idx & 7, row = idx >> 3;
-                *reinterpret_cast<float4*>(&As[buf][row][4 * kq]) = ra[j];
-            }
-            // W transposed to [k][unit][gate]; the unit index is XOR-swizzled with k / 4 so that the 32 lanes of a
-            // store (8 k-quads x 4 gates) hit 32 different banks, and the float4 reads below stay a permutation
+            for (int g = 0; g < 4; ++g) w[g] = *reinterpret_cast<const float4*>(Ws + g * kLstmBU * kLstmLd + 4 * kq);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + kLstmThreads * j, kq = idx & 7, g = (idx >> 3) & 3, u = idx >> 5;
-                const int col = ((u ^ kq) << 2) + g;
-                Ws[buf][4 * kq + 0][col] = rw[j].x;
-                Ws[buf][4 * kq + 1][col] = rw[j].y;
-                Ws[buf][4 * kq + 2][col] = rw[j].z;
-                Ws[buf][4 * kq + 3][col] = rw[j].w;
-            }
-        };
-
-        load_global(0);
-        store_smem(0);
-        __syncthreads();
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
-            const int buf = chunk & 1;
-            if (chunk + 1 < nchunks) load_global(chunk + 1);
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int kq = 0; kq < kLstmBK / 4; ++kq) {
-                float4 a[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&As[buf][ty * 4 + r][4 * kq]);
-                const int col = (tx ^ kq) << 2;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][4 * kq + e][col]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float av = e == 0 ? a[r].x : e == 1 ? a[r].y : e == 2 ? a[r].z : a[r].w;
-                        acc[r][0] = fmaf(av, w.x, acc[r][0]);
-                        acc[r][1] = fmaf(av, w.y, acc[r][1]);
-                        acc[r][2] = fmaf(av, w.z, acc[r][2]);
-                        acc[r][3] = fmaf(av, w.w, acc[r][3]);
-                    }
+                for (int g = 0; g < 4; ++g) {
+                    acc[r][g] = fmaf(a[r].x, w[g].x, acc[r][g]);
+                    acc[r][g] = fmaf(a[r].y, w[g].y, acc[r][g]);
+                    acc[r][g] = fmaf(a[r].z, w[g].z, acc[r][g]);
+                    acc[r][g] = fmaf(a[r].w, w[g].w, acc[r][g]);
                 }
-            }
-            if (chunk + 1 < nchunks) store_smem(buf ^ 1);
-            __syncthreads();
         }
     }
 
@@ -164,15 +180,32 @@ extern "C" int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, i
     p.ldx = num_frames * ld_xg;
     p.ldh = p.ldy = num_frames * ld_y;
     p.c = cell; p.w = w_hh; p.rows = (int)rows; p.H = (int)hidden;
-    const dim3 grid((unsigned)((hidden + kLstmBU - 1) / kLstmBU), (unsigned)grid_y);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    APSB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        APSB_CUDA(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSmem));
+        attr_set[dev] = true;
+    }
+    // every frame's launch may start (and prefetch its W_hh tiles and input projections) while the previous frame is
+    // still running; the kernel waits for it (griddepcontrol.wait) before touching h_{t-1} or the cell state
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((hidden + kLstmBU - 1) / kLstmBU), (unsigned)grid_y);
+    cfg.blockDim = dim3(kLstmThreads);
+    cfg.dynamicSmemBytes = kLstmSmem;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     for (int64_t t = 0; t < num_frames; ++t) {
         const int64_t f = reverse ? num_frames - 1 - t : t, fp = reverse ? f + 1 : f - 1;
         p.xg = xg + f * ld_xg;
         p.y = y + f * ld_y;
         p.first = t == 0;
-        p.h_prev = t ? y + fp * ld_y : nullptr;
-        lstm_step_kernel<<<grid, kLstmThreads, 0, (cudaStream_t)stream>>>(p);
+        p.h_prev = t ? y + fp * ld_y : y;
+        APSB_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel, p));
     }
-    APSB_LAUNCH_CHECK();
     return 0;
 }

@@ -694,7 +694,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     ok = ok && ih < a.H;
                 }
                 const int csrc = a.cat_c ? 2 * a.cat_c : a.Cin;          // channels of the tensor(s) actually read
-                prow[i] = ok ? a.x + (((long long)r_nb[i] * a.H + ih) * a.W) * csrc : nullptr;
+                // pointer to the pixel at iw = r_b[i] (the tap offset kw is added per k-block; may lie outside the row)
+                prow[i] = ok ? a.x + (((long long)r_nb[i] * a.H + ih) * a.W + r_b[i]) * csrc : nullptr;
             }
         };
         // Gather of one k-block into registers.  Plain (L1-allocating) loads on purpose: L1 merges a warp's 16-byte lane
@@ -711,18 +712,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 int coff = cb * BK + c * 4, csrc = a.Cin;
                 long long delta = 0;
                 if (a.cat_c) {                   // which of the four parts this (32-channel aligned) k-block lies in
-                    const int c0 = cb * BK, seg = c0 / a.cat_c;
+                    const int c0 = cb * BK;                                  // c0 < 4 * cat_c: no integer division
+                    const int seg = (c0 >= a.cat_c) + (c0 >= 2 * a.cat_c) + (c0 >= 3 * a.cat_c);
                     coff = (seg >> 1) * a.cat_c + (c0 - seg * a.cat_c) + c * 4;
                     csrc = 2 * a.cat_c;
                     delta = (seg & 1) ? (a.x2 - a.x) : 0;
                 }
                 const int dwk = MODE == 1 ? kw * a.dw : -kw;
+                const long long common = (long long)dwk * csrc + coff + delta;     // same for every row of the k-block
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
-                    const int iw = r_b[i] + dwk;
-                    const bool ok = prow[i] != nullptr && (unsigned)iw < (unsigned)a.W;
-                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(prow[i] + (long long)iw * csrc + coff + delta))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool ok = prow[i] != nullptr && (unsigned)(r_b[i] + dwk) < (unsigned)a.W;
+                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(prow[i] + common)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         };
