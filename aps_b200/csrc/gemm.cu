@@ -107,6 +107,135 @@ __global__ void __launch_bounds__(256) conv2d_narrow_kernel(const __grid_constan
     }
 }
 
+// Transposed convolution with very few OUTPUT channels (<= 8): the last DCCRN decoder layer maps 64 channels to
+// 2 * num_spks (dccrn.py:133-147).  On the GEMM engine such a layer pays for a 64-column tile and is bound by the
+// operand gather (6.9 ms at B = 128 x 4 s for 1.2 GB of traffic); here 8 lanes share one output pixel, each reads
+// one float4 of the pixel's channels per tap (a warp request covers whole 128-byte pixel rows of 4 pixels), the
+// weights sit in shared memory as [tap][channel][CO] and the 8 partial sums meet in three shuffles.  `x2` is the
+// skip tensor of a "cat" connection read in place (channel order of cat_complex: [x_re, skip_re, x_im, skip_im]).
+struct NarrowTConvParams {
+    const float* x;
+    const float* x2;
+    int H, W, Cx, cat_c, Cin, KH, KW, sh, sw, ph, pw, OH, OW, M, Cout;
+    const float* w;       // [Cout, KH, KW, Cin]
+    Epilogue e;
+};
+
+// input index i with i * stride == n (n >= 0), or -1; strides 1 and 2 (every reference model) without a division
+__device__ __forceinline__ int tconv_src(int n, int stride) {
+    if (stride == 1) return n;
+    if (stride == 2) return (n & 1) ? -1 : (n >> 1);
+    const int i = n / stride;
+    return i * stride == n ? i : -1;
+}
+
+// channel quads per tap in the shared-memory weight layout (padded so that the swizzle stays in range) and the swizzle
+__host__ __device__ __forceinline__ int tconv_slots(int cin) { return ((cin / 4 + 15) / 16) * 16; }
+__device__ __forceinline__ int tconv_swz(int quad) { return quad ^ (((quad >> 3) & 1) << 2); }
+
+template <int CO, int KW_>   // KW_ > 0: compile-time kernel width (3 in every reference model), 0: run-time
+__global__ void __launch_bounds__(256) tconv_narrow_kernel(const __grid_constant__ NarrowTConvParams p) {
+    // weights as [tap][c % 4][swz(c / 4)][CO]: the 8 lanes of a pixel hold consecutive channel quads, so their float4
+    // reads of one (tap, c % 4) are 128 contiguous bytes; the XOR moves the second half of a cat segment pair
+    // (quads 8..11 next to 0..3 when each tensor has 32 channels) onto the other 16 banks.  The first version,
+    // [tap][c][CO], had 64-byte lane strides: 4-way conflicts, shared-memory pipe 92 % busy (ncu).
+    extern __shared__ __align__(16) float sw_[];
+    constexpr int KWM = KW_ > 0 ? KW_ : 1;            // taps gathered together (all loads of a kernel row in flight)
+    const int KW = KW_ > 0 ? KW_ : p.KW;
+    const int K = p.KH * KW * p.Cin;
+    const int SL = tconv_slots(p.Cin);
+    for (int i = threadIdx.x; i < K * CO; i += blockDim.x) {
+        const int k = i / CO, co = i - k * CO;
+        const int tap = k / p.Cin, c = k - tap * p.Cin;
+        sw_[((tap * 4 + (c & 3)) * SL + tconv_swz(c >> 2)) * CO + co] = co < p.Cout ? __ldg(p.w + (long long)co * K + k) : 0.f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x & 7, slot = threadIdx.x >> 3;
+    const bool two = p.x2 != nullptr;
+    for (unsigned base = blockIdx.x * 32u; base < (unsigned)p.M; base += gridDim.x * 32u) {
+        const unsigned m = base + slot;
+        const bool valid = m < (unsigned)p.M;
+        const unsigned t = m / (unsigned)p.OW, ow = m - t * (unsigned)p.OW;
+        const unsigned nb = t / (unsigned)p.OH, oh = t - nb * (unsigned)p.OH;
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+        if (valid) {
+            for (int kh = 0; kh < p.KH; ++kh) {
+                const int nh = (int)oh + p.ph - kh;
+                if (nh < 0) continue;
+                const int ih = tconv_src(nh, p.sh);                 // -1: no input row feeds this tap
+                if (ih < 0 || ih >= p.H) continue;
+                const long long rowp = ((long long)nb * p.H + ih) * p.W;
+                for (int kw0 = 0; kw0 < KW; kw0 += KWM) {
+                    for (int q = j * 4; q < p.Cx; q += 32) {
+                        // phase 1: every load of this kernel row (taps x both tensors) is issued before any is used
+                        float4 v[KWM][2];
+                        bool ok[KWM];
+#pragma unroll
+                        for (int i = 0; i < KWM; ++i) {
+                            const int nw = (int)ow + p.pw - (kw0 + i);
+                            const int iw = nw < 0 ? -1 : tconv_src(nw, p.sw);
+                            ok[i] = iw >= 0 && iw < p.W;
+                            const long long off = (rowp + iw) * p.Cx + q;
+                            v[i][0] = ok[i] ? __ldg(reinterpret_cast<const float4*>(p.x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[i][1] = (ok[i] && two) ? __ldg(reinterpret_cast<const float4*>(p.x2 + off))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        // phase 2
+#pragma unroll
+                        for (int i = 0; i < KWM; ++i) {
+                            if (!ok[i]) continue;
+                            const float* wt = sw_ + (kh * KW + kw0 + i) * 4 * SL * CO;
+#pragma unroll
+                            for (int tn = 0; tn < 2; ++tn) {
+                                if (tn && !two) break;
+                                int c = q;
+                                if (p.cat_c) {
+                                    const int half = q >= p.cat_c;
+                                    c = (2 * half + tn) * p.cat_c + q - half * p.cat_c;
+                                }
+                                const float* wp = wt + tconv_swz(c >> 2) * CO;
+                                const float4 vv = v[i][tn];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float xv = e == 0 ? vv.x : e == 1 ? vv.y : e == 2 ? vv.z : vv.w;
+#pragma unroll
+                                    for (int g = 0; g < CO / 4; ++g) {
+                                        const float4 wv = *reinterpret_cast<const float4*>(wp + e * SL * CO + 4 * g);
+                                        acc[4 * g + 0] = fmaf(xv, wv.x, acc[4 * g + 0]);
+                                        acc[4 * g + 1] = fmaf(xv, wv.y, acc[4 * g + 1]);
+                                        acc[4 * g + 2] = fmaf(xv, wv.z, acc[4 * g + 2]);
+                                        acc[4 * g + 3] = fmaf(xv, wv.w, acc[4 * g + 3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // the 8 lanes of a pixel hold partial sums over their channels; afterwards lane j owns output channel j
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            float v = acc[c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (c == j) mine = v;
+        }
+        if (valid && j < p.Cout) {
+            float v = mine + (p.e.bias ? __ldg(p.e.bias + j) : 0.f);
+            v = apply_act(v, p.e.act, p.e, j);
+            if (p.e.post_scale) v = fmaf(v, __ldg(p.e.post_scale + j), __ldg(p.e.post_shift + j));
+            v *= p.e.alpha;
+            if (p.e.res) v = fmaf(p.e.beta, __ldg(p.e.res + (long long)m * p.e.ldres + j), v);
+            p.e.out[(long long)m * p.e.ldo + j] = v;
+        }
+    }
+}
+
 static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* out, int64_t ldo) {
     APSB_CHECK_ARG(d && out, "null pointer argument");
     APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_GELU, "unknown activation %d", d->act);
@@ -208,4 +337,49 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_fwd(const float* x, int64_t batch,
     a.OH = (int)OH; a.OW = (int)OW; a.M = (int)M; a.K = (int)K;
     a.vec = (((uintptr_t)x & 15) == 0 && (in_channels & 3) == 0) ? 1 : 0;
     return launch_gemm(a, weight, K, (int)M, ncols, (int)K, e, (cudaStream_t)stream);
+}
+
+extern "C" int aps_b200_conv_transpose2d_nhwc_narrow_fwd(const float* x, const float* x_skip, int64_t batch,
+                                                         int64_t height, int64_t width, int64_t in_channels,
+                                                         const float* weight, int64_t out_channels, int kernel_h,
+                                                         int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                                                         int out_pad_h, int out_pad_w, const aps_b200_epilogue* epi,
+                                                         float* out, void* stream) {
+    APSB_CHECK_ARG(x && weight, "null pointer argument");
+    APSB_CHECK_ARG(batch > 0 && height > 0 && width > 0 && in_channels > 0 && out_channels > 0, "bad shape");
+    APSB_CHECK_ARG(kernel_h > 0 && kernel_w > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0 &&
+                       out_pad_h >= 0 && out_pad_w >= 0, "bad convolution geometry");
+    APSB_CHECK_ARG(out_channels <= 8, "narrow transposed convolution: at most 8 output channels (got %lld)",
+                   (long long)out_channels);
+    const int64_t cx = x_skip ? in_channels / 2 : in_channels;      // channels of each tensor that is read
+    APSB_CHECK_ARG(cx % (x_skip ? 8 : 4) == 0 && (!x_skip || in_channels % 2 == 0) && ((uintptr_t)x & 15) == 0 &&
+                       ((uintptr_t)x_skip & 15) == 0,
+                   "narrow transposed convolution: %lld channels per tensor need 16-byte aligned float4 groups",
+                   (long long)cx);
+    const int64_t OH = (height - 1) * stride_h - 2 * pad_h + kernel_h + out_pad_h;
+    const int64_t OW = (width - 1) * stride_w - 2 * pad_w + kernel_w + out_pad_w;
+    APSB_CHECK_ARG(OH > 0 && OW > 0, "transposed convolution output is empty");
+    const int64_t M = batch * OH * OW, K = (int64_t)kernel_h * kernel_w * in_channels;
+    const int co = out_channels <= 4 ? 4 : 8;
+    const size_t smem = (size_t)kernel_h * kernel_w * 4 * tconv_slots((int)in_channels) * co * 4;
+    APSB_CHECK_ARG(M < (1LL << 31) - 64 && K < (1LL << 24) && smem <= 48 * 1024, "shape too large for the narrow kernel");
+    NarrowTConvParams c{};
+    const int ncols = (int)out_channels;
+    if (int rc = fill_epilogue(c.e, epi, ncols, out, ncols)) return rc;
+    APSB_CHECK_ARG(epi->act != ACT_GLU, "GLU is not available here");
+    c.x = x; c.x2 = x_skip; c.H = (int)height; c.W = (int)width; c.Cx = (int)cx; c.cat_c = x_skip ? (int)(cx / 2) : 0;
+    c.Cin = (int)in_channels; c.KH = kernel_h; c.KW = kernel_w; c.sh = stride_h; c.sw = stride_w; c.ph = pad_h;
+    c.pw = pad_w; c.OH = (int)OH; c.OW = (int)OW; c.M = (int)M; c.Cout = ncols; c.w = weight;
+    const long long blocks = (M + 31) / 32;
+    const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kernel_w == 3) {
+        if (co == 4) tconv_narrow_kernel<4, 3><<<grid, 256, smem, st>>>(c);
+        else tconv_narrow_kernel<8, 3><<<grid, 256, smem, st>>>(c);
+    } else {
+        if (co == 4) tconv_narrow_kernel<4, 0><<<grid, 256, smem, st>>>(c);
+        else tconv_narrow_kernel<8, 0><<<grid, 256, smem, st>>>(c);
+    }
+    APSB_LAUNCH_CHECK();
+    return 0;
 }

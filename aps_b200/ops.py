@@ -143,6 +143,18 @@ def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1,
     B, H, W, Cx = x.shape
     OH = (H - 1) * stride[0] - 2 * padding[0] + KH + output_padding[0]
     OW = (W - 1) * stride[1] - 2 * padding[1] + KW + output_padding[1]
+    Cskip = Cx if skip is not None else 0
+    if (Cout <= 8 and KH * KW * ((Cx + Cskip + 63) // 64) * 64 * 32 <= 48 * 1024 and Cx % (8 if skip is not None else 4) == 0
+            and x.is_contiguous() and x.data_ptr() % 16 == 0
+            and (skip is None or (skip.shape == x.shape and skip.is_contiguous() and skip.data_ptr() % 16 == 0))):
+        # a handful of output channels (the last decoder layer): dedicated kernel, skip tensor read in place
+        out = th.empty((B, OH, OW, Cout), dtype=th.float32, device=dev)
+        e = _epilogue(bias, act, 1.0, None, leaky)
+        with th.cuda.device(dev):
+            _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_narrow_fwd(
+                x.data_ptr(), _lib.ptr(skip), B, H, W, Cx + Cskip, weight.data_ptr(), Cout, KH, KW, stride[0], stride[1],
+                padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
+        return out
     fused_skip = None
     if skip is not None:
         if (skip.shape == x.shape and Cx % 64 == 0 and stride[1] == 1 and x.is_contiguous() and skip.is_contiguous()

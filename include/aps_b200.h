@@ -324,6 +324,16 @@ int aps_b200_utt_norm_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t n
                           const float* beta, float eps, int relu, void* workspace, int64_t workspace_bytes,
                           float* out, int64_t ld_out, void* stream);
 
+/* Transposed convolution with at most 8 output channels (the last DCCRN decoder layer, dccrn.py:133-147:
+ * 2 * num_spks channels) on a dedicated kernel: 8 lanes per output pixel, weights in shared memory, exact fp32.
+ * x_skip (same shape as x, may be NULL): the input is cat_complex(x, x_skip) read in place; in_channels counts
+ * both.  Channels per tensor % 4 == 0 (% 8 with x_skip); kernel_h * kernel_w * in_channels * 8 floats <= 48 KB. */
+int aps_b200_conv_transpose2d_nhwc_narrow_fwd(const float* x, const float* x_skip, int64_t batch, int64_t height,
+                                              int64_t width, int64_t in_channels, const float* weight,
+                                              int64_t out_channels, int kernel_h, int kernel_w, int stride_h,
+                                              int stride_w, int pad_h, int pad_w, int out_pad_h, int out_pad_w,
+                                              const aps_b200_epilogue* epi, float* out, void* stream);
+
 /* LSTM recurrence of one layer and direction ---------------------------------------------------
  * torch.nn.LSTM semantics (gate order i, f, g, o; h_0 = c_0 = 0), as used by the DCCRN bottleneck
  * (aps/sse/bss/dccrn.py:20-50: LSTMP -> nn.LSTM, batch_first).  xg [rows, num_frames, ld_xg >= 4H]

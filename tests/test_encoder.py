@@ -218,6 +218,31 @@ def test_tensor_core_conv_transpose_fused_skip(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_narrow_output_conv_transpose_vs_torch():
+    """Transposed convolution with <= 8 output channels (last DCCRN decoder layer) on its dedicated kernel: plain and
+    with the cat-skip tensor read in place, strides 1 / 2 / 3, ragged channel counts, LeakyReLU epilogue."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    th.manual_seed(8)
+    for (B, H, W, Cx, Co, k, s_, p_, op_, skip) in ((2, 17, 30, 32, 4, (3, 3), (2, 1), (1, 1), (0, 0), True),
+                                                    (3, 9, 11, 16, 6, (3, 3), (2, 1), (1, 1), (0, 0), True),
+                                                    (1, 5, 7, 40, 8, (3, 2), (2, 2), (1, 0), (1, 1), True),
+                                                    (2, 6, 9, 12, 1, (5, 3), (3, 1), (2, 1), (2, 0), False),
+                                                    (2, 8, 8, 4, 3, (1, 1), (1, 1), (0, 0), (0, 0), False),
+                                                    (1, 33, 70, 64, 2, (3, 3), (2, 1), (0, 1), (1, 0), False)):
+        x = th.randn(B, H, W, Cx)
+        sk = th.randn(B, H, W, Cx) if skip else None
+        Cin = 2 * Cx if skip else Cx
+        w, b = th.randn(Co, *k, Cin) * 0.1, th.randn(Co)
+        full = ops.cat_complex(x, sk) if skip else x
+        ref = F.leaky_relu(F.conv_transpose2d(full.permute(0, 3, 1, 2).double(), w.permute(3, 0, 1, 2).double(), b.double(),
+                                              stride=s_, padding=p_, output_padding=op_), 0.01).permute(0, 2, 3, 1)
+        got = ops.conv_transpose2d_nhwc(x.to(DEV), w.to(DEV), b.to(DEV), stride=s_, padding=p_, output_padding=op_,
+                                        act="leaky_relu", leaky=0.01, skip=sk.to(DEV) if skip else None)
+        assert got.shape == ref.shape and rel_err(got, ref) < 2e-6
+
+
+@pytest.mark.gpu
 def test_dense_kernels_vs_torch(monkeypatch):
     """Exact-fp32 (SIMT) GEMM epilogues / implicit conv / LayerNorm / depthwise conv against plain fp32 torch on the
     CPU (the tensor-core engine has its own tests above)."""
