@@ -125,6 +125,8 @@ _SIGNATURES = {
     "aps_b200_conv_transpose2d_nhwc_narrow_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                                           c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                           c_int, POINTER(Epilogue), c_void_p, c_void_p]),
+    "aps_b200_lstm_group_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
+                                        c_int64, c_int, c_void_p]),
     "aps_b200_lstm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                   c_int64, c_void_p]),
     "aps_b200_pair_objf_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),

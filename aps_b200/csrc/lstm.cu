@@ -27,15 +27,17 @@ constexpr int kLstmTile = (kLstmBM + 4 * kLstmBU) * kLstmLd;           // floats
 constexpr int kLstmSmem = kLstmStages * kLstmTile * 4;
 
 struct LstmStepParams {
-    const float* xg;      // [rows][4H] of this frame, row stride ldx
-    long long ldx;
-    const float* h_prev;  // [rows][H] of the previous frame, row stride ldh (unused on the first frame: h = 0)
-    long long ldh;
-    float* c;             // [rows, H] cell state, updated in place
-    float* y;             // [rows][H] of this frame, row stride ldy
-    long long ldy;
-    const float* w;       // W_hh [4H, H]
-    int rows, H, first;
+    // up to APS_B200_LSTM_MAX_GROUPS independent recurrences of the same shape run side by side (grid.z): the two
+    // LSTMs of DCCRN's complex bottleneck, or the two directions of a bidirectional layer.  One recurrence is
+    // 128 CTAs at the DCCRN size — one per SM with a dependent-issue-bound inner loop; two of them co-resident
+    // double the warps per scheduler
+    const float* xg[APS_B200_LSTM_MAX_GROUPS];   // [rows, T, >= 4H] input projections (+ both biases)
+    const float* w[APS_B200_LSTM_MAX_GROUPS];    // W_hh [4H, H]
+    float* c[APS_B200_LSTM_MAX_GROUPS];          // [rows, H] cell state, updated in place
+    float* y[APS_B200_LSTM_MAX_GROUPS];          // [rows, T, >= H] outputs; frame t - 1 (t + 1 reversed) is h_{t-1}
+    long long ld_xg, ld_y;                       // floats between consecutive frames of a row
+    int reverse_mask;                            // bit g: group g walks the frames backwards
+    int rows, H, T, step;                        // step: 0 .. T - 1 (h = c = 0 before step 0)
 };
 
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.f / (1.f + expf(-x)); }
@@ -51,11 +53,20 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
     extern __shared__ __align__(16) float lstm_smem[];
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int u0 = blockIdx.x * kLstmBU, r0 = blockIdx.y * kLstmBM;
+    const int u0 = blockIdx.x * kLstmBU, r0 = blockIdx.y * kLstmBM, grp = blockIdx.z;
     const int H = p.H;
     const int unit = u0 + tx;
     const bool unit_ok = unit < H;
-    const int nchunks = p.first ? 0 : (H + kLstmBK - 1) / kLstmBK;
+    const bool first = p.step == 0;
+    const int nchunks = first ? 0 : (H + kLstmBK - 1) / kLstmBK;
+    const bool rev = (p.reverse_mask >> grp) & 1;
+    const int frame = rev ? p.T - 1 - p.step : p.step, frame_prev = rev ? frame + 1 : frame - 1;
+    const long long ldx = (long long)p.T * p.ld_xg, ldy = (long long)p.T * p.ld_y;   // row strides
+    const float* const g_xg = p.xg[grp] + (long long)frame * p.ld_xg;
+    const float* const g_w = p.w[grp];
+    float* const g_c = p.c[grp];
+    float* const g_y = p.y[grp] + (long long)frame * p.ld_y;
+    const float* const g_h = p.y[grp] + (long long)(first ? frame : frame_prev) * p.ld_y;
 
     // gate pre-activations from the input projection: independent of the previous frame, issued first, consumed last
     float xg[4][4];
@@ -64,7 +75,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         const int row = r0 + ty * 4 + r;
         const bool ok = unit_ok && row < p.rows;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) xg[r][g] = ok ? __ldg(p.xg + (long long)row * p.ldx + (long long)g * H + unit) : 0.f;
+        for (int g = 0; g < 4; ++g) xg[r][g] = ok ? __ldg(g_xg + (long long)row * ldx + (long long)g * H + unit) : 0.f;
     }
 
     // chunk -> ring stage: this thread copies two 16-byte pieces of the h tile and two of the W_hh tile (k-major rows,
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         for (int j = 0; j < 2; ++j) {
             const int col = lrow + 32 * j, g = col >> 4, u = u0 + (col & 15);
             const bool ok = u < H && k < H;
-            lstm_cp16(st + col * kLstmLd + 4 * lkq, ok ? p.w + ((long long)g * H + u) * H + k : p.w, ok);
+            lstm_cp16(st + col * kLstmLd + 4 * lkq, ok ? g_w + ((long long)g * H + u) * H + k : g_w, ok);
         }
     };
     auto issue_h = [&](int chunk) {
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         for (int j = 0; j < 2; ++j) {
             const int row = lrow + 32 * j;
             const bool ok = r0 + row < p.rows && k < H;
-            lstm_cp16(st + row * kLstmLd + 4 * lkq, ok ? p.h_prev + (long long)(r0 + row) * p.ldh + k : p.w, ok);
+            lstm_cp16(st + row * kLstmLd + 4 * lkq, ok ? g_h + (long long)(r0 + row) * ldy + k : g_w, ok);
         }
     };
 
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int row = r0 + ty * 4 + r;
-        c_old[r] = (unit_ok && row < p.rows && !p.first) ? p.c[(long long)row * H + unit] : 0.f;
+        c_old[r] = (unit_ok && row < p.rows && !first) ? g_c[(long long)row * H + unit] : 0.f;
     }
 
     float acc[4][4];
@@ -156,8 +167,8 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         const float gg = tanhf(acc[r][2] + xg[r][2]);
         const float og = sigmoid_precise(acc[r][3] + xg[r][3]);
         const float c = fmaf(fg, c_old[r], ig * gg);
-        p.c[(long long)row * H + unit] = c;
-        p.y[(long long)row * p.ldy + unit] = og * tanhf(c);
+        g_c[(long long)row * H + unit] = c;
+        g_y[(long long)row * ldy + unit] = og * tanhf(c);
     }
 }
 
@@ -165,21 +176,27 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
 
 using namespace apsb;
 
-extern "C" int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
-                                 const float* w_hh, int reverse, float* cell, float* y, int64_t ld_y, void* stream) {
+extern "C" int aps_b200_lstm_group_fwd(const float* const* xg, int64_t ld_xg, int64_t rows, int64_t num_frames,
+                                       int64_t hidden, const float* const* w_hh, int reverse_mask, float* const* cell,
+                                       float* const* y, int64_t ld_y, int groups, void* stream) {
     APSB_CHECK_ARG(xg && w_hh && cell && y, "null pointer argument");
+    APSB_CHECK_ARG(groups >= 1 && groups <= APS_B200_LSTM_MAX_GROUPS, "lstm: 1..%d groups (got %d)",
+                   APS_B200_LSTM_MAX_GROUPS, groups);
     APSB_CHECK_ARG(rows > 0 && num_frames > 0 && hidden > 0 && rows < (1LL << 31) && num_frames < (1LL << 31) &&
                        hidden < (1LL << 29), "bad shape");
-    APSB_CHECK_ARG(hidden % 4 == 0 && ld_y % 4 == 0 && ld_y >= hidden && ld_xg >= 4 * hidden &&
-                       ((uintptr_t)y & 15) == 0 && ((uintptr_t)w_hh & 15) == 0,
-                   "lstm: hidden (%lld) and ld_y (%lld) must be multiples of 4 and y, w_hh 16-byte aligned",
-                   (long long)hidden, (long long)ld_y);
+    APSB_CHECK_ARG(hidden % 4 == 0 && ld_y % 4 == 0 && ld_y >= hidden && ld_xg >= 4 * hidden,
+                   "lstm: hidden (%lld) and ld_y (%lld) must be multiples of 4", (long long)hidden, (long long)ld_y);
     const int64_t grid_y = (rows + kLstmBM - 1) / kLstmBM;
     APSB_CHECK_ARG(grid_y <= 65535, "lstm: too many rows (%lld)", (long long)rows);
     LstmStepParams p{};
-    p.ldx = num_frames * ld_xg;
-    p.ldh = p.ldy = num_frames * ld_y;
-    p.c = cell; p.w = w_hh; p.rows = (int)rows; p.H = (int)hidden;
+    for (int g = 0; g < groups; ++g) {
+        APSB_CHECK_ARG(xg[g] && w_hh[g] && cell[g] && y[g], "null pointer argument (group %d)", g);
+        APSB_CHECK_ARG(((uintptr_t)y[g] & 15) == 0 && ((uintptr_t)w_hh[g] & 15) == 0,
+                       "lstm: y and w_hh must be 16-byte aligned (group %d)", g);
+        p.xg[g] = xg[g]; p.w[g] = w_hh[g]; p.c[g] = cell[g]; p.y[g] = y[g];
+    }
+    p.ld_xg = ld_xg; p.ld_y = ld_y; p.reverse_mask = reverse_mask;
+    p.rows = (int)rows; p.H = (int)hidden; p.T = (int)num_frames;
     static bool attr_set[64] = {};
     int dev = 0;
     APSB_CUDA(cudaGetDevice(&dev));
@@ -193,19 +210,20 @@ extern "C" int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, i
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((hidden + kLstmBU - 1) / kLstmBU), (unsigned)grid_y);
+    cfg.gridDim = dim3((unsigned)((hidden + kLstmBU - 1) / kLstmBU), (unsigned)grid_y, (unsigned)groups);
     cfg.blockDim = dim3(kLstmThreads);
     cfg.dynamicSmemBytes = kLstmSmem;
     cfg.stream = (cudaStream_t)stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     for (int64_t t = 0; t < num_frames; ++t) {
-        const int64_t f = reverse ? num_frames - 1 - t : t, fp = reverse ? f + 1 : f - 1;
-        p.xg = xg + f * ld_xg;
-        p.y = y + f * ld_y;
-        p.first = t == 0;
-        p.h_prev = t ? y + fp * ld_y : y;
+        p.step = (int)t;
         APSB_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel, p));
     }
     return 0;
+}
+
+extern "C" int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
+                                 const float* w_hh, int reverse, float* cell, float* y, int64_t ld_y, void* stream) {
+    return aps_b200_lstm_group_fwd(&xg, ld_xg, rows, num_frames, hidden, &w_hh, reverse ? 1 : 0, &cell, &y, ld_y, 1, stream);
 }

@@ -226,39 +226,60 @@ def utt_norm(x: th.Tensor, N: int, T: int, gamma=None, beta=None, eps: float = 1
     return out
 
 
-def lstm(x: th.Tensor, lstm_mod, cache: Optional[dict] = None) -> th.Tensor:
-    """torch.nn.LSTM forward (batch_first, zero initial state, inference) on x [N, T, In] with the parameters of
-    `lstm_mod` (an nn.LSTM): per layer and direction one tensor-core GEMM for the input projections of all frames and
-    the fused per-frame recurrence kernel (aps_b200_lstm_fwd).  Returns [N, T, H * directions]."""
-    dev = _lib.require_cuda(x, "LSTM input")
-    if not lstm_mod.batch_first or getattr(lstm_mod, "proj_size", 0):
-        raise RuntimeError("ops.lstm: only batch_first nn.LSTM without projections is implemented")
-    if lstm_mod.training and lstm_mod.dropout > 0 and lstm_mod.num_layers > 1:
-        raise RuntimeError("ops.lstm: inter-layer dropout (training mode) is not implemented")
-    N, T, _ = x.shape
-    H, dirs = lstm_mod.hidden_size, 2 if lstm_mod.bidirectional else 1
+def lstm_multi(xs, mods, caches=None):
+    """torch.nn.LSTM forward (batch_first, zero initial state, inference) of several modules of identical shape on
+    identically shaped inputs x [N, T, In]: per layer one tensor-core GEMM per module and direction for the input
+    projections of all frames, then ONE fused recurrence launch per frame that advances all modules and directions
+    together (aps_b200_lstm_group_fwd).  Returns a list of [N, T, H * directions]."""
+    import ctypes
+    m0 = mods[0]
+    dev = _lib.require_cuda(xs[0], "LSTM input")
+    for m in mods:
+        if not m.batch_first or getattr(m, "proj_size", 0):
+            raise RuntimeError("ops.lstm: only batch_first nn.LSTM without projections is implemented")
+        if m.training and m.dropout > 0 and m.num_layers > 1:
+            raise RuntimeError("ops.lstm: inter-layer dropout (training mode) is not implemented")
+        if (m.hidden_size, m.num_layers, m.bidirectional, m.input_size, m.bias) != (
+                m0.hidden_size, m0.num_layers, m0.bidirectional, m0.input_size, m0.bias):
+            raise RuntimeError("ops.lstm_multi: the modules must have the same shape")
+    N, T, _ = xs[0].shape
+    H, dirs = m0.hidden_size, 2 if m0.bidirectional else 1
     if H % 4:
         raise RuntimeError(f"ops.lstm: hidden_size ({H}) must be a multiple of 4")
+    if any(x.shape != xs[0].shape for x in xs):
+        raise RuntimeError("ops.lstm_multi: the inputs must have the same shape")
+    caches = caches or [None] * len(mods)
     lib = _lib.load()
-    cell = th.empty(N, H, dtype=th.float32, device=dev)
-    inp = x.contiguous().float()
-    for layer in range(lstm_mod.num_layers):
-        y = th.empty(N, T, H * dirs, dtype=th.float32, device=dev)
-        for d in range(dirs):
-            sfx = f"_l{layer}" + ("_reverse" if d else "")
-            w_ih = getattr(lstm_mod, "weight_ih" + sfx).detach()
-            w_hh = getattr(lstm_mod, "weight_hh" + sfx).detach().contiguous()
-            if lstm_mod.bias:
-                bias = getattr(lstm_mod, "bias_ih" + sfx).detach() + getattr(lstm_mod, "bias_hh" + sfx).detach()
-            else:
-                bias = None
-            xg = linear(inp.view(N * T, -1), w_ih, bias, cache=cache)
+    max_groups = 4                                               # APS_B200_LSTM_MAX_GROUPS
+    inps = [x.contiguous().float() for x in xs]
+    for layer in range(m0.num_layers):
+        ys = [th.empty(N, T, H * dirs, dtype=th.float32, device=dev) for _ in mods]
+        jobs = []                                                # (xg, w_hh, cell, y pointer, reverse)
+        for inp, mod, cache, y in zip(inps, mods, caches, ys):
+            for d in range(dirs):
+                sfx = f"_l{layer}" + ("_reverse" if d else "")
+                w_ih = getattr(mod, "weight_ih" + sfx).detach()
+                w_hh = getattr(mod, "weight_hh" + sfx).detach().contiguous()
+                bias = (getattr(mod, "bias_ih" + sfx).detach() + getattr(mod, "bias_hh" + sfx).detach()) if mod.bias else None
+                xg = linear(inp.view(N * T, -1), w_ih, bias, cache=cache)
+                jobs.append((xg, w_hh, th.empty(N, H, dtype=th.float32, device=dev), y.data_ptr() + 4 * H * d, d))
+        for i in range(0, len(jobs), max_groups):
+            part = jobs[i:i + max_groups]
+            n = len(part)
+            arr = lambda vals: (ctypes.c_void_p * n)(*vals)
+            mask = sum(1 << g for g, j in enumerate(part) if j[4])
             with th.cuda.device(dev):
-                _lib.check(lib.aps_b200_lstm_fwd(xg.data_ptr(), xg.stride(0), N, T, H, w_hh.data_ptr(), d,
-                                                 cell.data_ptr(), y.data_ptr() + 4 * H * d, H * dirs,
-                                                 _lib.stream_ptr(dev)))
-        inp = y
-    return inp
+                _lib.check(lib.aps_b200_lstm_group_fwd(arr([j[0].data_ptr() for j in part]), part[0][0].stride(0), N, T, H,
+                                                       arr([j[1].data_ptr() for j in part]), mask,
+                                                       arr([j[2].data_ptr() for j in part]), arr([j[3] for j in part]),
+                                                       H * dirs, n, _lib.stream_ptr(dev)))
+        inps = ys
+    return inps
+
+
+def lstm(x: th.Tensor, lstm_mod, cache: Optional[dict] = None) -> th.Tensor:
+    """One nn.LSTM (see lstm_multi)."""
+    return lstm_multi([x], [lstm_mod], [cache])[0]
 
 
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,

@@ -106,20 +106,30 @@ class LSTMP(nn.Module):
                             bidirectional=bidirectional, batch_first=True)
         self.proj = nn.Linear(hidden_size * 2 if bidirectional else hidden_size, in_features, bias=False)
 
-    def forward(self, x: th.Tensor) -> th.Tensor:            # N x T x D
-        if LSTM_ENGINE == "cudnn":
-            # library path kept for A/B only.  cuDNN would run the recurrent GEMMs as single-pass TF32 by default
-            # (torch.backends.cudnn.allow_tf32): off unless APS_B200_LSTM_TF32=1 (~1e-3 error inside the recurrence)
-            with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
-                out, _ = self.lstm(x)
-        else:
-            # input projections of all frames on the tensor-core engine + one fused launch per frame for the
-            # recurrence and the cell update (csrc/lstm.cu), exact fp32
-            if not hasattr(self, "_splits"):
-                self._splits = ops.SplitCache()
-            out = ops.lstm(x, self.lstm, cache=self._splits)
+    def project(self, out: th.Tensor) -> th.Tensor:
         N, T, H = out.shape
         return ops.linear(out.reshape(N * T, H), self.proj.weight.detach()).view(N, T, -1)
+
+    def splits(self):
+        if not hasattr(self, "_splits"):
+            self._splits = ops.SplitCache()
+        return self._splits
+
+    def forward(self, x: th.Tensor) -> th.Tensor:            # N x T x D
+        return lstmp_pair([self], [x])[0]
+
+
+def lstmp_pair(mods, xs):
+    """Several LSTMP modules of one shape on same-shaped inputs: input projections of all frames on the tensor-core
+    engine, then one fused recurrence + cell-update launch per frame for all of them together (csrc/lstm.cu), exact
+    fp32.  APS_B200_LSTM=cudnn: torch.nn.LSTM (library), kept for A/B only — cuDNN would run the recurrent GEMMs as
+    single-pass TF32 by default (torch.backends.cudnn.allow_tf32): off unless APS_B200_LSTM_TF32=1."""
+    if LSTM_ENGINE == "cudnn":
+        with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
+            outs = [m.lstm(x)[0] for m, x in zip(mods, xs)]
+    else:
+        outs = ops.lstm_multi(xs, [m.lstm for m in mods], [m.splits() for m in mods])
+    return [m.project(o) for m, o in zip(mods, outs)]
 
 
 class ComplexLSTMP(nn.Module):
@@ -231,11 +241,10 @@ class DCCRN(nn.Module):
         hr = x[..., :Cc].permute(0, 2, 3, 1).reshape(N, T, Cc * Fq)
         hi = x[..., Cc:].permute(0, 2, 3, 1).reshape(N, T, Cc * Fq)
         # complex LSTM (dccrn.py:97-110): out_r = R(hr) - I(hi), out_i = R(hi) + I(hr).  The two applications of each
-        # real LSTM run as ONE call on the batch-concatenated inputs: the recurrence is latency bound per time step, so
-        # this halves its cost (rows of a batch are independent in an LSTM)
+        # real LSTM run as ONE call on the batch-concatenated inputs (rows of a batch are independent in an LSTM), and
+        # the two LSTMs advance together, one launch per frame for both
         R, I = self.rnn.lstm.real, self.rnn.lstm.imag
-        r_all = R(th.cat([hr, hi], 0))
-        i_all = I(th.cat([hi, hr], 0))
+        r_all, i_all = lstmp_pair([R, I], [th.cat([hr, hi], 0), th.cat([hi, hr], 0)])
         out_r = r_all[:N] - i_all[:N]
         out_i = r_all[N:] + i_all[N:]
         back = lambda t: t.view(N, T, Cc, Fq).permute(0, 3, 1, 2)          # -> N x F x T x Cc

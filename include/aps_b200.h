@@ -344,6 +344,14 @@ int aps_b200_conv_transpose2d_nhwc_narrow_fwd(const float* x, const float* x_ski
  * One fused launch per frame, exact fp32 arithmetic.  hidden % 4 == 0, ld_y % 4 == 0.             */
 int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
                       const float* w_hh, int reverse, float* cell, float* y, int64_t ld_y, void* stream);
+/* `groups` (<= APS_B200_LSTM_MAX_GROUPS) independent recurrences of the same shape advanced together, one launch per
+ * frame for all of them: the real and imaginary LSTMs of DCCRN's complex bottleneck (dccrn.py:97-110), or the two
+ * directions of a bidirectional layer (bit g of reverse_mask: group g walks the frames backwards).  Pointer arrays
+ * are host arrays of device pointers; everything else as above.                                                    */
+#define APS_B200_LSTM_MAX_GROUPS 4
+int aps_b200_lstm_group_fwd(const float* const* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
+                            const float* const* w_hh, int reverse_mask, float* const* cell, float* const* y,
+                            int64_t ld_y, int groups, void* stream);
 
 /* Time-domain separation objectives ----------------------------------------------------------
  * Si-SNR / SNR between every estimate and every reference of an utterance in ONE pass over the

@@ -1,5 +1,7 @@
 """LSTM recurrence kernel (csrc/lstm.cu, aps_b200_lstm_fwd) against torch.nn.LSTM on the CPU in fp32/fp64 — the
 module the reference's DCCRN bottleneck uses (aps/sse/bss/dccrn.py:29-34)."""
+import copy
+
 import pytest
 import torch as th
 
@@ -59,3 +61,19 @@ def test_lstm_refuses_unsupported():
         ops.lstm(th.zeros(2, 3, 8, device="cuda"), mod)
     with pytest.raises(RuntimeError, match="batch_first"):
         ops.lstm(th.zeros(2, 3, 8, device="cuda"), th.nn.LSTM(8, 8).cuda())
+
+
+@gpu
+@pytest.mark.parametrize("bidir", [False, True])
+def test_lstm_multi_matches_single(bidir):
+    """Two modules advanced together (one launch per frame for both) == each module on its own, bit for bit."""
+    from aps_b200 import ops
+    th.manual_seed(11)
+    mods = [th.nn.LSTM(24, 40, num_layers=2, bidirectional=bidir, batch_first=True).eval().cuda() for _ in range(2)]
+    xs = [th.randn(9, 13, 24, device="cuda") for _ in range(2)]
+    with th.no_grad():
+        both = ops.lstm_multi(xs, mods)
+        for x, m, y in zip(xs, mods, both):
+            assert th.equal(ops.lstm(x, m), y)
+            want, _ = copy.deepcopy(m).cpu().double()(x.cpu().double())
+            assert rel_err(y.cpu(), want) < 2e-5
