@@ -122,11 +122,14 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         c_old[r] = (unit_ok && row < p.rows && !first) ? g_c[(long long)row * H + unit] : 0.f;
     }
 
-    float acc[4][4];
+    // accumulators as packed pairs {sum over even k, sum over odd k}: the shared-memory float4s already hold
+    // (k, k + 1) pairs in adjacent registers, so fma.rn.f32x2 (FFMA2) needs no packing and halves the issue slots of
+    // the inner loop, which is what bounds it (512 FFMA + 64 LDS per chunk and warp otherwise)
+    unsigned long long acc2[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
+        for (int g = 0; g < 4; ++g) acc2[r][g] = 0ull;
 
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kLstmStages - 2) : "memory");
@@ -140,22 +143,29 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_step_kernel(const __grid_co
         const float* Ws = lstm_smem + (chunk % kLstmStages) * kLstmTile + (kLstmBM + tx) * kLstmLd;
 #pragma unroll
         for (int kq = 0; kq < kLstmBK / 4; ++kq) {
-            float4 a[4], w[4];
+            ulonglong2 a[4], w[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(As + r * kLstmLd + 4 * kq);
+            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const ulonglong2*>(As + r * kLstmLd + 4 * kq);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) w[g] = *reinterpret_cast<const float4*>(Ws + g * kLstmBU * kLstmLd + 4 * kq);
+            for (int g = 0; g < 4; ++g) w[g] = *reinterpret_cast<const ulonglong2*>(Ws + g * kLstmBU * kLstmLd + 4 * kq);
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    acc[r][g] = fmaf(a[r].x, w[g].x, acc[r][g]);
-                    acc[r][g] = fmaf(a[r].y, w[g].y, acc[r][g]);
-                    acc[r][g] = fmaf(a[r].z, w[g].z, acc[r][g]);
-                    acc[r][g] = fmaf(a[r].w, w[g].w, acc[r][g]);
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][g]) : "l"(a[r].x), "l"(w[g].x));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][g]) : "l"(a[r].y), "l"(w[g].y));
                 }
         }
     }
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2[r][g]));
+            acc[r][g] = lo + hi;
+        }
 
     if (!unit_ok) return;
 #pragma unroll
