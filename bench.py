@@ -264,13 +264,13 @@ def run_extra(args):
         dec_o = [128, 128, 64, 64, 32, 16, 2]
         for i in range(7):
             flops += 2.0 * B * fqs[7 - i] * Tf * (2 * dec_c[i]) * (9 * 2 * dec_o[i])
-        frames, launches = B * (S // HOP), 1 + 7 + 7 + 2 * 2 + 2 + 6
+        frames, launches = B * (S // HOP), 1 + 7 + 7 + 2 * 3 + 2 * (S // 256 + 1) + 2 + 6   # + one LSTM launch per STFT frame and layer
         ach = flops / (ms / args.steps * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                 "traffic": None, "kernel": "tc_gemm_kernel<BN, conv / conv_transpose> (tcgen05 3xTF32 implicit GEMMs on stacked "
                                            "re/im channels; FLOPs counted as the reference computes them, incl. the zero taps "
-                                           "of the transposed convolutions that the kernel skips) + cuDNN LSTM bottleneck "
-                                           "(exact fp32, ~45 % of the step), STFT, iSTFT x2, cmask, fused Si-SNR",
+                                           "of the transposed convolutions that the kernel skips) + fused LSTM recurrence (csrc/lstm.cu) "
+                                           "(exact fp32, ~35 % of the step), narrow-output transposed conv, STFT, iSTFT x2, cmask, fused Si-SNR",
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"}
         wl = ("DCCRN (C=16..256, cat, 2 spk) forward + PIT Si-SNR on B=128 x 4 s (configs[4]); value in 10 ms frames/s")
     else:
