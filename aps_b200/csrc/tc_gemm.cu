@@ -37,8 +37,16 @@
 namespace apsb {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 320;
-constexpr int TC_PRODUCERS = 128;          // warps 0..3
+// A-producer warps: 4 for linear layers and the 256-wide tiles (MMA / shared-memory bound), 8 for the convolution
+// gathers on 64- and 128-wide tiles, which are bound by the producers' own instruction latency (0.14 IPC per warp)
+#ifndef APSB_TC_PW_CONV
+#define APSB_TC_PW_CONV 8
+#endif
+template <int BN, int MODE> struct TcRoles {
+    static constexpr int PW = (MODE != 0 && BN <= 128) ? APSB_TC_PW_CONV : 4;
+    static constexpr int PRODUCERS = PW * 32;
+    static constexpr int THREADS = (6 + PW) * 32;
+};
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_PROD0 = 6;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -247,6 +255,7 @@ __device__ __forceinline__ int tc_tile_class(const AGather& a, unsigned m_first,
 // does kernel row kh contribute to the output rows of class `cls`?
 __device__ __forceinline__ bool tc_kh_valid(const AGather& a, int cls, int kh) {
     if (cls < 0) return true;
+    if (a.sh == 2) return ((cls + a.ph - kh) & 1) == 0;          // every reference model; no emulated modulo
     return ((cls + a.ph - kh) % a.sh) == 0;
 }
 // output row index (in units of rows of the [.., Cout] output) of GEMM row m
@@ -308,7 +317,7 @@ template <int BN> struct TcCfg {
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ TcParams p) {
     using C = TcCfg<BN>;
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                tc_mbar_init(full_a + s, TC_PRODUCERS / 32);
+                tc_mbar_init(full_a + s, TcRoles<BN, MODE>::PW);
                 tc_mbar_init(full_b + s, 1);
                 tc_mbar_init(empty + s, 1);
             }
@@ -645,7 +654,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // thread -> 16-byte chunk c of rows rg, rg + RSTEP, ...: a warp instruction reads whole SWZ-byte row segments.
         // The gather for k-block i+1 is issued BEFORE block i is split and stored, so the L2 round trip is hidden.
         constexpr int CPR = BK / 4;                 // 16-byte chunks per operand row
-        constexpr int RSTEP = TC_PRODUCERS / CPR;   // rows covered by one pass of the 128 producer threads
+        constexpr int RSTEP = TcRoles<BN, MODE>::PRODUCERS / CPR;   // rows covered by one pass of the producer threads
         constexpr int RPT = TC_BM / RSTEP;          // rows per thread (= CPR)
         const int pt = threadIdx.x - WARP_PROD0 * 32;
         const int c = pt % CPR, rg = pt / CPR;
@@ -658,22 +667,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // because this role runs straight-line code once per k-block and is instruction-fetch bound otherwise.
         const float* prow[RPT];     // linear: row pointer; conv: input row (nb, ih) of this kh; null: nothing to read
         int r_nb[RPT], r_a[RPT], r_b[RPT];   // image index (-1: row >= M); conv: oh*sh - ph / ow*sw - pw; tconv: oh + ph / ow + pw
+        int lcls = -1;                          // row class of the current tile (-1: none / straddling)
         auto set_tile = [&](unsigned tile) {
             const unsigned m_blk = tile / (unsigned)p.tiles_n;
+            const unsigned m0 = m_blk * TC_BM + rg;
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const unsigned m = m0 + RSTEP * i;
+                    const bool in = m < (unsigned)p.M;
+                    r_nb[i] = in ? 0 : -1; r_a[i] = 0; r_b[i] = 0;
+                    prow[i] = in ? a.x + (long long)m * a.ld : nullptr;
+                }
+                return;
+            }
+            // Convolutions: the first row is decoded with divisions, the others follow by stepping RSTEP columns (the
+            // divisions are emulated: decoding every row cost ~8 k cycles per tile and thread).  Tiles that straddle two
+            // row classes of a strided transposed convolution (a handful per launch) decode every row.
+            const bool cls_on = MODE == 2 && a.classes > 1;
+            const bool stepping = !cls_on || lcls >= 0;
+            const int rows_img = cls_on ? (lcls >= 0 ? a.class_rows[lcls] : 1) : a.OH;
+            int nb = 0, j = 0, ow = 0;                      // image, row index inside the image (class), column
+            if (stepping && m0 < (unsigned)p.M) {
+                const unsigned mm = cls_on ? m0 - (unsigned)a.class_start[lcls] : m0;
+                const unsigned t = mm / (unsigned)a.OW;
+                ow = (int)(mm - t * (unsigned)a.OW);
+                nb = (int)(t / (unsigned)rows_img);
+                j = (int)(t - (unsigned)nb * (unsigned)rows_img);
+            }
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-                const unsigned m = m_blk * TC_BM + rg + RSTEP * i;
+                const unsigned m = m0 + RSTEP * i;
                 r_nb[i] = -1; r_a[i] = 0; r_b[i] = 0; prow[i] = nullptr;
                 if (m < (unsigned)p.M) {
-                    if (MODE == 0) {
-                        r_nb[i] = 0;
-                        prow[i] = a.x + (long long)m * a.ld;
+                    RowPos rp;
+                    if (stepping) {
+                        rp.nb = nb; rp.ow = ow; rp.oh = cls_on ? j * a.sh + lcls : j;
+                        ow += RSTEP;
+                        while (ow >= a.OW) {
+                            ow -= a.OW;
+                            if (++j == rows_img) { j = 0; ++nb; }
+                        }
                     } else {
-                        const RowPos rp = tc_decode_row(a, m);
-                        r_nb[i] = rp.nb;
-                        if (MODE == 1) { r_a[i] = rp.oh * a.sh - a.ph; r_b[i] = rp.ow * a.sw - a.pw; }
-                        else           { r_a[i] = rp.oh + a.ph;        r_b[i] = rp.ow + a.pw; }
+                        rp = tc_decode_row(a, m);
                     }
+                    r_nb[i] = rp.nb;
+                    if (MODE == 1) { r_a[i] = rp.oh * a.sh - a.ph; r_b[i] = rp.ow * a.sw - a.pw; }
+                    else           { r_a[i] = rp.oh + a.ph;        r_b[i] = rp.ow + a.pw; }
                 }
             }
         };
@@ -729,16 +769,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         };
         // k-blocks of gathers in flight (registers): as deep as the register budget of the role allows — the linear
         // mode carries no per-row convolution geometry, so it affords one more block
-        constexpr int D = BK == 16 ? 4 : (MODE == 0 ? 3 : 2);
+        constexpr int D = BK == 16 ? 4 : (MODE == 0 ? 3 : (TcRoles<BN, MODE>::PW == 8 ? 4 : 2));
         // iterator over the (tile, tap, k-block) sequence of this CTA, skipping taps that are zero for the tile's class
         unsigned ltile = blockIdx.x;
-        int lkh = 0, lcb = 0, lkw = 0, lh = 0, lcls = -1;   // lcb counts 32-channel groups, lh the half inside (BK = 16)
+        int lkh = 0, lcb = 0, lkw = 0, lh = 0;              // lcb counts 32-channel groups, lh the half inside (BK = 16)
         bool lfresh = true;                     // the tile's rows have not been decoded yet
+        unsigned lmask = 0, lmask_tile = 0xffffffffu;
         int lkh_set = -1;                       // kernel row the prow[] pointers were computed for
         auto seek = [&]() {                     // move (ltile, lkh) to the next valid kernel row; false at the end
             while (ltile < p.tiles) {
-                if (lfresh) lcls = tile_class(ltile);
-                while (lkh < num_kh && !tc_kh_valid(a, lcls, lkh)) ++lkh;
+                if (lfresh && lmask_tile != ltile) {       // once per tile: class and the bit mask of its non-zero kernel rows
+                    lcls = tile_class(ltile);
+                    lmask = 0;
+                    for (int kh = 0; kh < num_kh && kh < 32; ++kh) lmask |= tc_kh_valid(a, lcls, kh) ? (1u << kh) : 0u;
+                    lmask_tile = ltile;
+                }
+                while (lkh < num_kh && !(lkh < 32 ? (bool)((lmask >> lkh) & 1u) : tc_kh_valid(a, lcls, lkh))) ++lkh;
                 if (lkh < num_kh) return true;
                 ltile += gridDim.x;
                 lkh = 0;
@@ -874,7 +920,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
 #ifdef APSB_TC_TRACE
     if (p.trace && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < TC_TRACE_WORDS; i += TC_THREADS) p.trace[i] = tr_smem[i];
+        for (int i = threadIdx.x; i < TC_TRACE_WORDS; i += blockDim.x) p.trace[i] = tr_smem[i];
 #endif
     if (warp == WARP_MMA) {
         tc_fence_after();
@@ -980,7 +1026,7 @@ static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const T
                                        (C::SMEM + 1024) * 100 / (228 * 1024) + 1));
         attr = true;
     }
-    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TC_THREADS, C::SMEM, st>>>(tB, tBl, p);
+    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TcRoles<BN, MODE>::THREADS, C::SMEM, st>>>(tB, tBl, p);
     APSB_LAUNCH_CHECK();
     return 0;
 }

@@ -13,7 +13,7 @@ NAMES = {1: "tma_issue", 2: "mma_start", 3: "mma_tile_commit", 4: "epi_start", 5
 dev = "cuda:0"
 lib = _lib.load()
 lib.aps_b200_tc_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
-B, H, W, Ci, Co = 16, 129, 251, 64, 4
+B, H, W, Ci, Co = (int(v) for v in (sys.argv[1:6] if len(sys.argv) > 5 else (16, 129, 251, 64, 4)))
 x = th.randn(B, H, W, Ci, device=dev)
 w = th.randn(Co, 3, 3, Ci, device=dev) * 0.05
 b = th.randn(Co, device=dev)
