@@ -7,6 +7,7 @@
 // (Conv2dEncoder.outp), aps/sse/bss/tcn.py:112-159 (1x1 convolutions of Conv1dBlock).
 #include "../../include/aps_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm.cuh"
 
 namespace apsb {
@@ -236,6 +237,120 @@ __global__ void __launch_bounds__(256) tconv_narrow_kernel(const __grid_constant
     }
 }
 
+// Same operation for the common geometry (kernel width 3, stride 1 along the width axis): the 8 lanes of a group own
+// FOUR neighbouring output pixels of a row.  Their taps overlap — 6 input columns feed 4 pixels x 3 taps — so a kernel
+// row costs 12 float4 loads instead of 24, and every weight float4 read from shared memory is used for 16 FMAs instead
+// of 4 (the one-pixel kernel above is bound by exactly those shared-memory reads).
+template <int CO>
+__global__ void __launch_bounds__(256) tconv_narrow_tiled_kernel(const __grid_constant__ NarrowTConvParams p) {
+    constexpr int P = 4, KW = 3, NC = P + KW - 1;
+    extern __shared__ __align__(16) float sw_[];
+    const int K = p.KH * KW * p.Cin;
+    const int SL = tconv_slots(p.Cin);
+    for (int i = threadIdx.x; i < K * CO; i += blockDim.x) {
+        const int k = i / CO, co = i - k * CO;
+        const int tap = k / p.Cin, c = k - tap * p.Cin;
+        sw_[((tap * 4 + (c & 3)) * SL + tconv_swz(c >> 2)) * CO + co] = co < p.Cout ? __ldg(p.w + (long long)co * K + k) : 0.f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x & 7, slot = threadIdx.x >> 3;
+    const bool two = p.x2 != nullptr;
+    const unsigned gpr = ((unsigned)p.OW + P - 1) / P;                 // pixel groups per output row
+    const unsigned G = ((unsigned)p.M / (unsigned)p.OW) * gpr;
+    for (unsigned base = blockIdx.x * 32u; base < G; base += gridDim.x * 32u) {
+        const unsigned g = base + slot;
+        const bool valid = g < G;
+        const unsigned t = g / gpr, og = g - t * gpr;                  // t = nb * OH + oh
+        const unsigned nb = t / (unsigned)p.OH, oh = t - nb * (unsigned)p.OH;
+        const int ow0 = (int)og * P;
+        float acc[P][CO];
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[i][c] = 0.f;
+        if (valid) {
+            const int iw0 = ow0 + p.pw - (KW - 1);                     // input column of (pixel 0, tap KW - 1)
+            for (int kh = 0; kh < p.KH; ++kh) {
+                const int nh = (int)oh + p.ph - kh;
+                if (nh < 0) continue;
+                const int ih = tconv_src(nh, p.sh);
+                if (ih < 0 || ih >= p.H) continue;
+                const long long rowp = ((long long)nb * p.H + ih) * p.W;
+                for (int q = j * 4; q < p.Cx; q += 32) {
+                    float4 v[NC][2];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int iw = iw0 + c;
+                        const bool ok = iw >= 0 && iw < p.W;
+                        const long long off = (rowp + iw) * p.Cx + q;
+                        v[c][0] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[c][1] = (ok && two) ? __ldg(reinterpret_cast<const float4*>(p.x2 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int kw = 0; kw < KW; ++kw) {
+                        const float* wt = sw_ + (kh * KW + kw) * 4 * SL * CO;
+#pragma unroll
+                        for (int tn = 0; tn < 2; ++tn) {
+                            if (tn && !two) break;
+                            int c = q;
+                            if (p.cat_c) {
+                                const int half = q >= p.cat_c;
+                                c = (2 * half + tn) * p.cat_c + q - half * p.cat_c;
+                            }
+                            const float* wp = wt + tconv_swz(c >> 2) * CO;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                                for (int g4 = 0; g4 < CO / 4; ++g4) {
+                                    const float4 wv = *reinterpret_cast<const float4*>(wp + e * SL * CO + 4 * g4);
+#pragma unroll
+                                    for (int i = 0; i < P; ++i) {
+                                        const float4 vv = v[i + KW - 1 - kw][tn];       // pixel i, tap kw -> column i + 2 - kw
+                                        const float xv = e == 0 ? vv.x : e == 1 ? vv.y : e == 2 ? vv.z : vv.w;
+                                        acc[i][4 * g4 + 0] = fmaf(xv, wv.x, acc[i][4 * g4 + 0]);
+                                        acc[i][4 * g4 + 1] = fmaf(xv, wv.y, acc[i][4 * g4 + 1]);
+                                        acc[i][4 * g4 + 2] = fmaf(xv, wv.z, acc[i][4 * g4 + 2]);
+                                        acc[i][4 * g4 + 3] = fmaf(xv, wv.w, acc[i][4 * g4 + 3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // sum the 8 channel slices; afterwards lane j owns pixel j / 2, channels (j % 2) * CO / 2 ...
+        float mine[CO / 2];
+#pragma unroll
+        for (int c = 0; c < CO / 2; ++c) mine[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) {
+                float v = acc[i][c];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (i == (j >> 1) && c / (CO / 2) == (j & 1)) mine[c % (CO / 2)] = v;
+            }
+        const int pi = j >> 1;
+        if (valid && ow0 + pi < p.OW) {
+            const long long m = (long long)t * p.OW + ow0 + pi;
+#pragma unroll
+            for (int c = 0; c < CO / 2; ++c) {
+                const int n = (j & 1) * (CO / 2) + c;
+                if (n >= p.Cout) continue;
+                float v = mine[c] + (p.e.bias ? __ldg(p.e.bias + n) : 0.f);
+                v = apply_act(v, p.e.act, p.e, n);
+                if (p.e.post_scale) v = fmaf(v, __ldg(p.e.post_scale + n), __ldg(p.e.post_shift + n));
+                v *= p.e.alpha;
+                if (p.e.res) v = fmaf(p.e.beta, __ldg(p.e.res + m * p.e.ldres + n), v);
+                p.e.out[m * p.e.ldo + n] = v;
+            }
+        }
+    }
+}
+
 static int fill_epilogue(Epilogue& e, const aps_b200_epilogue* d, int N, float* out, int64_t ldo) {
     APSB_CHECK_ARG(d && out, "null pointer argument");
     APSB_CHECK_ARG(d->act >= ACT_NONE && d->act <= ACT_GELU, "unknown activation %d", d->act);
@@ -373,7 +488,13 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_narrow_fwd(const float* x, const f
     const long long blocks = (M + 31) / 32;
     const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (kernel_w == 3) {
+    static const bool no_tiled = getenv("APS_B200_TCONV_NARROW_1PX") != nullptr;     // A/B switch
+    if (kernel_w == 3 && stride_w == 1 && !no_tiled) {
+        const long long groups = (M / OW) * ((OW + 3) / 4), gblocks = (groups + 31) / 32;
+        const unsigned tgrid = (unsigned)(gblocks < (long long)num_sms() * 16 ? gblocks : (long long)num_sms() * 16);
+        if (co == 4) tconv_narrow_tiled_kernel<4><<<tgrid, 256, smem, st>>>(c);
+        else tconv_narrow_tiled_kernel<8><<<tgrid, 256, smem, st>>>(c);
+    } else if (kernel_w == 3) {
         if (co == 4) tconv_narrow_kernel<4, 3><<<grid, 256, smem, st>>>(c);
         else tconv_narrow_kernel<8, 3><<<grid, 256, smem, st>>>(c);
     } else {

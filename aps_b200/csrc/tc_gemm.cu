@@ -42,8 +42,11 @@ constexpr int TC_BM = 128;
 #ifndef APSB_TC_PW_CONV
 #define APSB_TC_PW_CONV 8
 #endif
+#ifndef APSB_TC_PW_LINEAR
+#define APSB_TC_PW_LINEAR 4
+#endif
 template <int BN, int MODE> struct TcRoles {
-    static constexpr int PW = (MODE != 0 && BN <= 128) ? APSB_TC_PW_CONV : 4;
+    static constexpr int PW = BN > 128 ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR);
     static constexpr int PRODUCERS = PW * 32;
     static constexpr int THREADS = (6 + PW) * 32;
 };
