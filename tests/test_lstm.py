@@ -18,6 +18,32 @@ def test_lstm_symbol_exported():
     assert "aps_b200_lstm_fwd" in _lib.exported_symbols()
 
 
+def test_oracle_lstm_matches_torch_lstm():
+    """The oracle's LSTM restatement (oracle/dccrn.py:_lstmp, used by every DCCRN parity test) against torch.nn.LSTM,
+    the module the reference instantiates (aps/sse/bss/dccrn.py:29-34)."""
+    from oracle import dccrn as OD
+    th.manual_seed(0)
+    mod = th.nn.LSTM(12, 8, num_layers=2, batch_first=True).eval()
+    proj = th.nn.Linear(8, 12, bias=False)
+    sd = {"p.lstm." + k: v.detach() for k, v in mod.state_dict().items()}
+    sd["p.proj.weight"] = proj.weight.detach()
+    x = th.randn(3, 5, 4, 3)
+    with th.no_grad():
+        want = proj(mod(x.view(3, 5, 12))[0]).view(3, 5, 4, -1)
+        got = OD._lstmp(sd, "p.", x, 2)
+    assert rel_err(got, want) < 1e-6
+
+
+def test_lstm_host_checks_without_gpu():
+    """Argument errors surface before any device work; CPU tensors are refused (no CPU fallback)."""
+    from aps_b200 import ops
+    mod = th.nn.LSTM(8, 8, batch_first=True).eval()
+    with pytest.raises(RuntimeError):
+        ops.lstm(th.zeros(2, 3, 8), mod)
+    with pytest.raises(RuntimeError):
+        ops.lstm_multi([th.zeros(2, 3, 8)] * 2, [mod, th.nn.LSTM(8, 12, batch_first=True)])
+
+
 @gpu
 @pytest.mark.parametrize("rows,frames,feats,hidden,layers,bidir", [
     (5, 7, 12, 32, 1, False),          # ragged rows, K handled by the SIMT projection
