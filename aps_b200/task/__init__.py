@@ -1,5 +1,5 @@
 from .objf import pair_objf_matrix, sisnr_objf, snr_objf, permu_invarint_objf, multiple_objf, hybrid_permu_objf
-from .sse import SisnrTask, SnrTask
+from .sse import SisnrTask, SnrTask, LinearFreqSaTask, MelFreqSaTask
 
 __all__ = ["pair_objf_matrix", "sisnr_objf", "snr_objf", "permu_invarint_objf", "multiple_objf", "hybrid_permu_objf",
-           "SisnrTask", "SnrTask"]
+           "SisnrTask", "SnrTask", "LinearFreqSaTask", "MelFreqSaTask"]

@@ -68,6 +68,48 @@ def objf_cases():
     save("objf_0", dict(N=N, S=S), **arrays)
 
 
+def freqsa_cases():
+    """Frequency-domain spectral-approximation tasks (aps/task/sse.py:207-455, row f1): the live reference's
+    LinearFreqSaTask / MelFreqSaTask on seeded mixtures with a stub network that returns fixed masks."""
+    import torch.nn as nn
+    from aps.task.sse import LinearFreqSaTask, MelFreqSaTask
+    from aps.transform import EnhTransform
+    th.set_num_threads(4)
+    g = th.Generator().manual_seed(2600)
+    N, S = 4, 4000
+    enh_kw = dict(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, window="sqrthann", center=True)
+    enh = EnhTransform(**enh_kw)
+    refs = [0.1 * th.randn(N, S, generator=g) for _ in range(2)]
+    mix = refs[0] + refs[1] + 0.01 * th.randn(N, S, generator=g)
+    T = int(enh.num_frames(th.tensor([S]))[0])
+    masks = [th.rand(N, 257, T, generator=g) for _ in range(2)]
+    masks[0][1::2], masks[1][1::2] = masks[1][1::2].clone(), masks[0][1::2].clone()
+
+    class Stub(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enh_transform = enh
+
+        def forward(self, mix):
+            return masks
+
+    egs = {"mix": mix, "ref": refs}
+    arrays = {"mix": mix, "ref0": refs[0], "ref1": refs[1], "mask0": masks[0], "mask1": masks[1]}
+    cfgs = {
+        "lin_l2": ("linear", dict()),
+        "lin_l1_psa": ("linear", dict(objf="L1", phase_sensitive=True)),
+        "lin_tpsa_nopermute": ("linear", dict(phase_sensitive=True, truncated=1.0, permute=False, weight="0.7,0.3")),
+        "lin_mapping": ("linear", dict(masking=False)),
+        "mel_plain": ("mel", dict()),
+        "mel_log_power": ("mel", dict(mel_log=True, power_mag=True, mel_scale=10, num_mels=40, phase_sensitive=True)),
+    }
+    with th.no_grad():
+        for name, (kind, kw) in cfgs.items():
+            task = (LinearFreqSaTask if kind == "linear" else MelFreqSaTask)(Stub(), **kw)
+            arrays["loss_" + name] = task(egs)["loss"]
+    save("freqsa_0", dict(N=N, S=S, enh=enh_kw, cfgs={k: [v[0], v[1]] for k, v in cfgs.items()}), **arrays)
+
+
 def norm_cases():
     """Per-utterance normalisations over time: TCN with cLN / gLN / IN (tcn.py:75-88) and the transformer
     encoder behind LinearProj(norm="LN") (proj.py:30-56, component.py:86-114)."""
@@ -198,6 +240,9 @@ def main():
     if "--only-objf" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         return objf_cases()
+    if "--only-freqsa" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return freqsa_cases()
     from aps.transform import AsrTransform, EnhTransform
     from aps.transform.utils import STFT, iSTFT
     th.set_num_threads(4)
@@ -370,6 +415,7 @@ def main():
         arrays.update({"p." + k: v for k, v in net.state_dict().items() if not k.endswith(".K")})  # K: 2 MB each
         save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
     objf_cases()
+    freqsa_cases()
     norm_cases()
     time_tcn_cases()
     reference_fixture_cases()
