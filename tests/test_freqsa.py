@@ -78,8 +78,6 @@ def test_freqsa_argument_errors():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: composes kernels that have "
-                                        "their own GPU tests (polar STFT), but has not run on a GPU yet")
 def test_freqsa_gpu_vs_reference():
     from aps_b200.transform import EnhTransform
     kw, g = load_golden("freqsa_0")
