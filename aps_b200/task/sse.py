@@ -1,8 +1,11 @@
-"""Time-domain separation tasks (network forward + Si-SNR / SNR value) on the fused objective kernel.
+"""Separation / enhancement tasks (network forward + objective value).
 
-Same constructor arguments, `forward(egs) -> {"loss": scalar}` contract and registry aliases
-("sse@sisnr", "sse@snr") as aps/task/sse.py:60-167.  Forward (evaluation) only: the loss tensor
-carries no autograd graph, training through it is out of scope.
+Time-domain Si-SNR / SNR on the fused objective kernel ("sse@sisnr", "sse@snr", aps/task/sse.py:60-167); the
+frequency- and time-domain spectral-approximation tasks and the complex mapping / masking tasks
+("sse@freq_linear_sa", "sse@freq_mel_sa", "sse@time_linear_sa", "sse@time_mel_sa", "sse@complex_mapping",
+"sse@complex_masking", sse.py:207-841) on the fused STFT kernel plus device tensor ops.  Same constructor arguments
+and `forward(egs) -> {"loss": scalar}` contract as the reference.  Forward (evaluation) only: the loss tensor carries
+no autograd graph, training through it is out of scope.
 """
 from typing import Dict, Optional
 
@@ -184,3 +187,182 @@ class MelFreqSaTask(FreqSaTask):
     def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:
         d = out - ref
         return th.sum((d * d).mean(-1), -1)
+
+
+class _MelLoss:
+    """mel projection + L2 distance shared by MelFreqSaTask and MelTimeSaTask (sse.py:430-455, 660-681)"""
+
+    def _init_mel(self, num_bins, num_mels, sr, fmax, mel_norm, mel_scale, mel_log, power_mag):
+        from ..transform.utils import mel_filter
+        mel = mel_filter(None, num_bins=num_bins, sr=sr, num_mels=num_mels, fmax=fmax, norm=mel_norm)
+        self.mel = nn.Parameter(mel[..., None] * mel_scale, requires_grad=False)       # M x F x 1, as in the reference
+        self.log = mel_log
+        self.power_mag = power_mag
+
+
+class TimeSaTask(Task):
+    """Time-domain networks scored on STFT magnitudes (to be inherited).  aps/task/sse.py:458-541.
+
+    The reference pre-emphasises `wav[:, 1:] -= a * wav[:, :-1]` IN PLACE, which also rewrites the caller's reference
+    signals; here the pre-emphasised signal is a new tensor (same loss value, the inputs are left alone)."""
+
+    def __init__(self, nnet: nn.Module, frame_len: int = 512, frame_hop: int = 256, center: bool = False,
+                 window: str = "sqrthann", round_pow_of_two: bool = True, stft_normalized: bool = False,
+                 pre_emphasis: float = 0, permute: bool = True, weight: Optional[str] = None, num_spks: int = 2,
+                 description: str = "") -> None:
+        from ..transform.utils import STFT
+        sa_ctx = STFT(frame_len, frame_hop, window=window, center=center, round_pow_of_two=round_pow_of_two,
+                      normalized=stft_normalized)
+        super(TimeSaTask, self).__init__(nnet, ctx=sa_ctx, description=description)
+        self.weight = list(map(float, weight.split(","))) if weight is not None else None
+        self.permute = permute
+        self.num_spks = num_spks
+        self.pre_emphasis = pre_emphasis
+
+    def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:
+        raise NotImplementedError
+
+    def transform(self, tensor: th.Tensor) -> th.Tensor:
+        raise NotImplementedError
+
+    def _stft_mag(self, wav: th.Tensor) -> th.Tensor:
+        if self.pre_emphasis > 0:
+            wav = th.cat([wav[:, :1], wav[:, 1:] - self.pre_emphasis * wav[:, :-1]], 1)
+        return self.ctx(wav, return_polar=True)[..., 0]
+
+    def forward(self, egs: Dict) -> Dict:
+        """egs: mix N x (C) x S, ref N x S or [N x S, ...]"""
+        mix, ref = egs["mix"], egs["ref"]
+        spk = self.nnet(mix)
+        if isinstance(spk, th.Tensor):
+            spk, ref = [spk], [ref]
+        spk_mag = [self._stft_mag(s) for s in spk]
+        ref_mag = [self._stft_mag(r) for r in ref]
+        loss = hybrid_permu_objf(spk_mag, ref_mag, self.objf, transform=self.transform, weight=self.weight,
+                                 permute=self.permute, permu_num_spks=self.num_spks)
+        return {"loss": th.mean(loss)}
+
+
+class LinearTimeSaTask(TimeSaTask):
+    """L1 / L2 distance between STFT magnitudes of the separated and reference waveforms.
+    aps/task/sse.py:544-603 ("sse@time_linear_sa")"""
+
+    def __init__(self, nnet: nn.Module, frame_len: int = 512, frame_hop: int = 256, center: bool = False,
+                 window: str = "sqrthann", round_pow_of_two: bool = True, stft_normalized: bool = False,
+                 permute: bool = True, weight: Optional[str] = None, num_spks: int = 2, objf: str = "L2") -> None:
+        super(LinearTimeSaTask, self).__init__(nnet, frame_len=frame_len, frame_hop=frame_hop, window=window,
+                                               center=center, round_pow_of_two=round_pow_of_two,
+                                               stft_normalized=stft_normalized, permute=permute, num_spks=num_spks,
+                                               weight=weight,
+                                               description="Using L1/L2 loss on magnitude of the waveform")
+        self.l1 = objf == "L1"
+
+    def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:
+        d = out - ref
+        return th.sum((d.abs() if self.l1 else d * d).mean(-1), -1)
+
+    def transform(self, tensor: th.Tensor) -> th.Tensor:
+        return tensor
+
+
+class MelTimeSaTask(TimeSaTask, _MelLoss):
+    """L2 distance between (log-)mel spectrograms of the waveforms.  aps/task/sse.py:606-681 ("sse@time_mel_sa")"""
+
+    def __init__(self, nnet: nn.Module, frame_len: int = 512, frame_hop: int = 256, window: str = "sqrthann",
+                 center: bool = False, round_pow_of_two: bool = True, stft_normalized: bool = False,
+                 permute: bool = True, weight: Optional[str] = None, num_spks: int = 2, num_bins: int = 257,
+                 num_mels: int = 80, power_mag: bool = False, mel_log: bool = False, mel_scale: int = 1,
+                 mel_norm: bool = False, sr: int = 16000, fmax: int = 7690) -> None:
+        super(MelTimeSaTask, self).__init__(nnet, frame_len=frame_len, frame_hop=frame_hop, window=window,
+                                            center=center, round_pow_of_two=round_pow_of_two,
+                                            stft_normalized=stft_normalized, permute=permute, num_spks=num_spks,
+                                            weight=weight,
+                                            description="Using L2 loss on the mel features of the waveform")
+        self._init_mel(num_bins, num_mels, sr, fmax, mel_norm, mel_scale, mel_log, power_mag)
+
+    transform = MelFreqSaTask.transform
+    objf = MelFreqSaTask.objf
+
+
+class ComplexMappingTask(Task):
+    """Complex spectral mapping: L1 / L2 on real and imaginary parts (+ magnitude).
+    aps/task/sse.py:684-752 ("sse@complex_mapping")"""
+
+    def __init__(self, nnet: nn.Module, num_spks: int = 2, weight: Optional[str] = None, permute: bool = True,
+                 objf: str = "L1", add_magnitude_loss: bool = True) -> None:
+        super(ComplexMappingTask, self).__init__(nnet, ctx=nnet.enh_transform.ctx("forward_stft"),
+                                                 description="Using complex mapping function for training")
+        self.weight = list(map(float, weight.split(","))) if weight is not None else None
+        self.permute = permute
+        self.num_spks = num_spks
+        self.l1 = objf == "L1"
+        self.add_magnitude_loss = add_magnitude_loss
+
+    def _dist(self, a: th.Tensor, b: th.Tensor) -> th.Tensor:
+        d = a - b
+        return d.abs() if self.l1 else d * d
+
+    def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:
+        """out, ref: N x F x T x 2 -> N"""
+        from .objf import EPSILON
+        loss = self._dist(out[..., 0], ref[..., 0]) + self._dist(out[..., 1], ref[..., 1])
+        if self.add_magnitude_loss:
+            out_mag = th.sqrt(out[..., 0]**2 + out[..., 1]**2 + EPSILON)
+            ref_mag = th.sqrt(ref[..., 0]**2 + ref[..., 1]**2 + EPSILON)
+            loss = loss + self._dist(out_mag, ref_mag)
+        return th.sum(loss.mean(-1), -1)
+
+    def forward(self, egs: Dict) -> Dict:
+        mix, ref = egs["mix"], egs["ref"]
+        out = self.nnet(mix)
+        if isinstance(out, th.Tensor):
+            out, ref = [out], [ref]
+        ref = [self.ctx(r, return_polar=False) for r in ref]
+        loss = hybrid_permu_objf(out, ref, self.objf, weight=self.weight, permute=self.permute,
+                                 permu_num_spks=self.num_spks)
+        return {"loss": th.mean(loss)}
+
+
+class ComplexMaskingTask(ComplexMappingTask):
+    """Complex ratio masks: distance after masking, or to the compressed ideal mask.
+    aps/task/sse.py:755-841 ("sse@complex_masking")"""
+
+    def __init__(self, nnet: nn.Module, num_spks: int = 2, weight: Optional[str] = None, permute: bool = True,
+                 compress_param=(10, 0.1, -100), compress_masks: bool = False, objf: str = "L2") -> None:
+        super(ComplexMaskingTask, self).__init__(nnet, num_spks=num_spks, weight=weight, permute=permute, objf=objf,
+                                                 add_magnitude_loss=False)
+        self.k, self.c, self.lower_bound = compress_param
+        self.compress_masks = compress_masks
+
+    def _compress_mask(self, mix_stft: th.Tensor, ref: th.Tensor) -> th.Tensor:
+        """compressed complex ratio mask in [-k, k] (sse.py:783-796)"""
+        from .objf import EPSILON
+        ref_stft = self.ctx(ref, return_polar=False)
+        denominator = th.sum(mix_stft**2, -1) + EPSILON
+        real = mix_stft[..., 0] * ref_stft[..., 0] + mix_stft[..., 1] * ref_stft[..., 1]
+        imag = mix_stft[..., 0] * ref_stft[..., 1] - mix_stft[..., 1] * ref_stft[..., 0]
+        # as written in the reference: [N, F, T, 2] / [N, F, T] only broadcasts for special shapes and raises otherwise
+        crm = th.stack([real, imag], -1) / denominator
+        exp = th.exp(-self.c * th.clamp_min(crm, self.lower_bound))
+        return self.k * (1 - exp) / (1 + exp)
+
+    @staticmethod
+    def _complex_tf_mask(mix_stft: th.Tensor, mask: th.Tensor) -> th.Tensor:
+        real = mix_stft[..., 0] * mask[..., 0] - mix_stft[..., 1] * mask[..., 1]
+        imag = mix_stft[..., 0] * mask[..., 1] + mix_stft[..., 1] * mask[..., 0]
+        return th.stack([real, imag], -1)
+
+    def forward(self, egs: Dict) -> Dict:
+        ref = egs["ref"]
+        out = self.nnet(egs["mix"])
+        if isinstance(out, th.Tensor):
+            out, ref = [out], [ref]
+        mix = self.ctx(egs["mix"], return_polar=False)
+        if self.compress_masks:
+            ref = [self._compress_mask(mix, r) for r in ref]
+        else:
+            ref = [self.ctx(r, return_polar=False) for r in ref]
+            out = [self._complex_tf_mask(mix, o) for o in out]
+        loss = hybrid_permu_objf(out, ref, self.objf, weight=self.weight, permute=self.permute,
+                                 permu_num_spks=self.num_spks)
+        return {"loss": th.mean(loss)}

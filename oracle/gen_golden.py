@@ -110,6 +110,57 @@ def freqsa_cases():
     save("freqsa_0", dict(N=N, S=S, enh=enh_kw, cfgs={k: [v[0], v[1]] for k, v in cfgs.items()}), **arrays)
 
 
+def timesa_cases():
+    """Time-domain spectral-approximation and complex mapping / masking tasks (aps/task/sse.py:458-841, row f1) of the
+    live reference, with stub networks that return fixed waveforms / spectra / masks."""
+    import torch.nn as nn
+    from aps.task.sse import ComplexMappingTask, ComplexMaskingTask, LinearTimeSaTask, MelTimeSaTask
+    from aps.transform import EnhTransform
+    th.set_num_threads(4)
+    g = th.Generator().manual_seed(2700)
+    N, S = 4, 4000
+    enh_kw = dict(feats="spectrogram-log-cmvn", frame_len=512, frame_hop=256, window="sqrthann", center=True)
+    enh = EnhTransform(**enh_kw)
+    refs = [0.1 * th.randn(N, S, generator=g) for _ in range(2)]
+    mix = refs[0] + refs[1] + 0.01 * th.randn(N, S, generator=g)
+    ests = [refs[k] + 0.03 * th.randn(N, S, generator=g) for k in range(2)]
+    ests[0][1::2], ests[1][1::2] = ests[1][1::2].clone(), ests[0][1::2].clone()
+    T = int(enh.num_frames(th.tensor([S]))[0])
+    spec = [0.5 * th.randn(N, 257, T, 2, generator=g) for _ in range(2)]       # "network" spectra / complex masks
+
+    class Stub(nn.Module):
+        def __init__(self, out):
+            super().__init__()
+            self.enh_transform = enh
+            self.out = out
+
+        def forward(self, mix):
+            return [o.clone() for o in self.out]                               # TimeSaTask pre-emphasises in place
+
+    arrays = {"mix": mix, "ref0": refs[0], "ref1": refs[1], "est0": ests[0], "est1": ests[1], "spec0": spec[0],
+              "spec1": spec[1]}
+    cfgs = {
+        "tlin_l2": ("time_linear", dict()),
+        "tlin_l1_center": ("time_linear", dict(objf="L1", center=True, window="hann", frame_len=400, frame_hop=160)),
+        "tmel_log": ("time_mel", dict(mel_log=True, mel_scale=5, num_mels=40, permute=False)),
+        "cmap_l1_mag": ("complex_mapping", dict()),
+        "cmap_l2": ("complex_mapping", dict(objf="L2", add_magnitude_loss=False)),
+        "cmask": ("complex_masking", dict()),
+    }
+    table = {"time_linear": (LinearTimeSaTask, ests), "time_mel": (MelTimeSaTask, ests),
+             "complex_mapping": (ComplexMappingTask, spec), "complex_masking": (ComplexMaskingTask, spec)}
+    with th.no_grad():
+        for name, (kind, kw) in cfgs.items():
+            cls, out = table[kind]
+            egs = {"mix": mix.clone(), "ref": [r.clone() for r in refs]}
+            arrays["loss_" + name] = cls(Stub(out), **kw)(egs)["loss"]
+        # pre-emphasis lives in TimeSaTask only (the registered subclasses do not expose it): set it on the instance
+        task = LinearTimeSaTask(Stub(ests))
+        task.pre_emphasis = 0.97
+        arrays["loss_tlin_preemph"] = task({"mix": mix.clone(), "ref": [r.clone() for r in refs]})["loss"]
+    save("timesa_0", dict(N=N, S=S, enh=enh_kw, cfgs={k: [v[0], v[1]] for k, v in cfgs.items()}), **arrays)
+
+
 def norm_cases():
     """Per-utterance normalisations over time: TCN with cLN / gLN / IN (tcn.py:75-88) and the transformer
     encoder behind LinearProj(norm="LN") (proj.py:30-56, component.py:86-114)."""
@@ -242,7 +293,8 @@ def main():
         return objf_cases()
     if "--only-freqsa" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
-        return freqsa_cases()
+        freqsa_cases()
+        return timesa_cases()
     from aps.transform import AsrTransform, EnhTransform
     from aps.transform.utils import STFT, iSTFT
     th.set_num_threads(4)
@@ -416,6 +468,7 @@ def main():
         save(f"dccrn_{i}", dict(enh=ekw, net=nkw), **arrays)
     objf_cases()
     freqsa_cases()
+    timesa_cases()
     norm_cases()
     time_tcn_cases()
     reference_fixture_cases()

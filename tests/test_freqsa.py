@@ -1,5 +1,6 @@
-"""Frequency-domain spectral-approximation tasks (row f1: aps/task/sse.py:207-455, "sse@freq_linear_sa",
-"sse@freq_mel_sa") against values of the live reference (tests/golden/freqsa_0.npz, oracle/gen_golden.py).
+"""Spectral-approximation and complex mapping / masking tasks (row f1: aps/task/sse.py:207-841, "sse@freq_linear_sa",
+"sse@freq_mel_sa", "sse@time_linear_sa", "sse@time_mel_sa", "sse@complex_mapping", "sse@complex_masking") against values
+of the live reference (tests/golden/freqsa_0.npz, timesa_0.npz, oracle/gen_golden.py).
 
 The CPU test drives the task shells with the oracle's STFT as context (host logic: reference magnitude, masking,
 distances, permutations); the GPU test uses the real EnhTransform context (fused polar STFT kernel)."""
@@ -13,14 +14,15 @@ from oracle import transform as O
 FLOAT_TOL = 1e-4
 
 
-class _OracleCtx:
+class _OracleCtx(nn.Module):
     """forward_stft context on the CPU: the oracle's dense-DFT STFT with the golden's framing"""
 
     def __init__(self, kw):
-        self.K, self.w = O.dft_kernel(kw["frame_len"], O.window(kw["window"], kw["frame_len"]))
-        self.hop, self.center = kw["frame_hop"], kw["center"]
+        super().__init__()
+        self.K, self.w = O.dft_kernel(kw.get("frame_len", 512), O.window(kw.get("window", "sqrthann"), kw.get("frame_len", 512)))
+        self.hop, self.center = kw.get("frame_hop", 256), kw.get("center", False)
 
-    def __call__(self, wav, return_polar=False):
+    def forward(self, wav, return_polar=False):
         return O.stft_dense(wav, self.K, self.w, self.hop, center=self.center, polar=return_polar)
 
 
@@ -83,3 +85,57 @@ def test_freqsa_gpu_vs_reference():
     kw, g = load_golden("freqsa_0")
     dev = th.device("cuda", 0)
     _run(kw, g, EnhTransform(**kw["enh"]).to(dev), dev)
+
+
+# ---- time-domain SA + complex mapping / masking ---------------------------------------------------------------------
+def _run_timesa(kw, g, dev, oracle_ctx):
+    from aps_b200 import task as T
+    table = {"time_linear": (T.LinearTimeSaTask, "est"), "time_mel": (T.MelTimeSaTask, "est"),
+             "complex_mapping": (T.ComplexMappingTask, "spec"), "complex_masking": (T.ComplexMaskingTask, "spec")}
+    if oracle_ctx:
+        enh = _EnhShim(_OracleCtx(kw["enh"]))
+    else:
+        from aps_b200.transform import EnhTransform
+        enh = EnhTransform(**kw["enh"]).to(dev)
+    egs = lambda: {"mix": g["mix"].clone().to(dev), "ref": [g["ref0"].clone().to(dev), g["ref1"].clone().to(dev)]}
+
+    def check(task, name):
+        if oracle_ctx and isinstance(task, T.sse.TimeSaTask):
+            task.ctx = _OracleCtx(name[1])                      # the task's own framing arguments
+        task = task.to(dev)
+        with th.no_grad():
+            loss = task(egs())["loss"]
+        want = g["loss_" + name[0]]
+        assert abs(float(loss) - float(want)) / abs(float(want)) < FLOAT_TOL, f"{name[0]}: {float(loss)} vs {float(want)}"
+
+    for name, (kind, cfg) in kw["cfgs"].items():
+        cls, key = table[kind]
+        out = [g[key + "0"].to(dev), g[key + "1"].to(dev)]
+        check(cls(_Stub(enh, out), **cfg), (name, cfg))
+    task = T.LinearTimeSaTask(_Stub(enh, [g["est0"].to(dev), g["est1"].to(dev)]))
+    task.pre_emphasis = 0.97
+    before = g["ref0"].clone()
+    check(task, ("tlin_preemph", {}))
+    assert th.equal(before, g["ref0"])                          # unlike the reference, the inputs are left alone
+
+
+def test_timesa_host_logic_vs_reference():
+    kw, g = load_golden("timesa_0")
+    _run_timesa(kw, g, th.device("cpu"), oracle_ctx=True)
+
+
+def test_complex_masking_compressed_path_raises_like_the_reference():
+    """sse.py:783-796 divides [N, F, T, 2] by [N, F, T]: a broadcast error for ordinary shapes, reproduced."""
+    from aps_b200.task import ComplexMaskingTask
+    kw, g = load_golden("timesa_0")
+    task = ComplexMaskingTask(_Stub(_EnhShim(_OracleCtx(kw["enh"])), [g["spec0"], g["spec1"]]), compress_masks=True)
+    with pytest.raises(RuntimeError):
+        task({"mix": g["mix"], "ref": [g["ref0"], g["ref1"]]})
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the same shells pass on the CPU "
+                                        "with the oracle STFT and the sibling FreqSa GPU test passed on a B200")
+def test_timesa_gpu_vs_reference():
+    kw, g = load_golden("timesa_0")
+    _run_timesa(kw, g, th.device("cuda", 0), oracle_ctx=False)
