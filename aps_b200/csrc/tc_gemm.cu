@@ -12,14 +12,14 @@
 // (aps_b200_tf32_split); ACTIVATIONS ARE SPLIT INSIDE THIS KERNEL by the A-producer warps, so no hi/lo or im2col copy
 // of an activation is ever written to HBM.
 //
-// One persistent CTA per SM (320 threads) walks 128 x BN output tiles; roles:
+// One persistent CTA per SM (320 threads, 448 for convolution gathers on 64/128-wide tiles) walks 128 x BN output tiles; roles:
 //   warp 0    : TMA producer for W_hi / W_lo tiles (BN rows x BK floats, swizzled), mbarrier tx
 //   warp 1    : allocates TMEM (2 x BN columns: double-buffered accumulator) and issues the UMMAs
 //   warps 2-5 : epilogue — tcgen05.ld of the finished accumulator while the NEXT tile's MMAs run into the other
 //               buffer; 32x32 transposes through shared memory, bias / activation / GLU / affine / residual, coalesced
 //               128-byte row stores
-//   warps 6-9 : A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
-//               taps), hi/lo split in registers, st.shared into the same 128-byte-swizzled K-major layout TMA would
+//   warps 6-9 (6-13): A producers — coalesced float4 gathers of the fp32 activation (rows, im2col patches or transposed-conv
+//               taps), hi/lo split in registers (integer rounding: sm_100a emulates cvt.rna.tf32), st.shared into the same 128-byte-swizzled K-major layout TMA would
 //               write, fence.proxy.async, mbarrier arrive
 // Replaces the cuBLAS / cuDNN calls behind F.linear, 1x1 convolutions and Conv2d / ConvTranspose2d of the reference
 // (aps/asr/transformer/impl.py:62-83, :388-393, :454-475; aps/asr/base/component.py:251-307;
