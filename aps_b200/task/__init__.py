@@ -1,7 +1,7 @@
 from .objf import pair_objf_matrix, sisnr_objf, snr_objf, permu_invarint_objf, multiple_objf, hybrid_permu_objf
-from .sse import (SisnrTask, SnrTask, LinearFreqSaTask, MelFreqSaTask, LinearTimeSaTask, MelTimeSaTask,
+from .sse import (SisnrTask, SnrTask, WaTask, LinearFreqSaTask, MelFreqSaTask, LinearTimeSaTask, MelTimeSaTask,
                   ComplexMappingTask, ComplexMaskingTask)
 
 __all__ = ["pair_objf_matrix", "sisnr_objf", "snr_objf", "permu_invarint_objf", "multiple_objf", "hybrid_permu_objf",
-           "SisnrTask", "SnrTask", "LinearFreqSaTask", "MelFreqSaTask", "LinearTimeSaTask", "MelTimeSaTask",
+           "SisnrTask", "SnrTask", "WaTask", "LinearFreqSaTask", "MelFreqSaTask", "LinearTimeSaTask", "MelTimeSaTask",
            "ComplexMappingTask", "ComplexMaskingTask"]

@@ -86,6 +86,23 @@ class SnrTask(TimeDomainTask):
         return self.fused_objf()(out, ref)
 
 
+class WaTask(TimeDomainTask):
+    """L1 / L2 distance between waveforms (summed over samples).  aps/task/sse.py:170-204 ("sse@wa")"""
+
+    def __init__(self, nnet: nn.Module, objf: str = "L1", num_spks: int = 2, permute: bool = True,
+                 weight: Optional[str] = None) -> None:
+        super(WaTask, self).__init__(nnet, num_spks=num_spks, permute=permute, weight=weight,
+                                     description="Using L1/L2 loss on waveform for training")
+        self.l1 = objf == "L1"
+
+    def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:
+        d = out - ref
+        return (d.abs() if self.l1 else d * d).sum(-1)
+
+    def fused_objf(self):
+        return self.objf                       # a plain callable: the PIT helpers evaluate it pair by pair
+
+
 class FreqSaTask(Task):
     """Frequency-domain spectral approximation (to be inherited).  aps/task/sse.py:207-311.
 

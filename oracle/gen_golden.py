@@ -155,6 +155,9 @@ def timesa_cases():
             egs = {"mix": mix.clone(), "ref": [r.clone() for r in refs]}
             arrays["loss_" + name] = cls(Stub(out), **kw)(egs)["loss"]
         # pre-emphasis lives in TimeSaTask only (the registered subclasses do not expose it): set it on the instance
+        from aps.task.sse import WaTask
+        for objf in ("L1", "L2"):
+            arrays["loss_wa_" + objf] = WaTask(Stub(ests), objf=objf)({"mix": mix, "ref": refs})["loss"]
         task = LinearTimeSaTask(Stub(ests))
         task.pre_emphasis = 0.97
         arrays["loss_tlin_preemph"] = task({"mix": mix.clone(), "ref": [r.clone() for r in refs]})["loss"]

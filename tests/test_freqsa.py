@@ -119,6 +119,16 @@ def _run_timesa(kw, g, dev, oracle_ctx):
     assert th.equal(before, g["ref0"])                          # unlike the reference, the inputs are left alone
 
 
+def test_wa_task_vs_reference():
+    """sse@wa is plain tensor arithmetic (no kernel of ours involved), so it is checked on the CPU."""
+    from aps_b200.task import WaTask
+    kw, g = load_golden("timesa_0")
+    for objf in ("L1", "L2"):
+        task = WaTask(_Stub(None, [g["est0"], g["est1"]]), objf=objf)
+        loss = task({"mix": g["mix"], "ref": [g["ref0"], g["ref1"]]})["loss"]
+        assert rel_err(loss, g["loss_wa_" + objf]) < 1e-5
+
+
 def test_timesa_host_logic_vs_reference():
     kw, g = load_golden("timesa_0")
     _run_timesa(kw, g, th.device("cpu"), oracle_ctx=True)
