@@ -124,7 +124,8 @@ def lstmp_pair(mods, xs):
     engine, then one fused recurrence + cell-update launch per frame for all of them together (csrc/lstm.cu), exact
     fp32.  APS_B200_LSTM=cudnn: torch.nn.LSTM (library), kept for A/B only — cuDNN would run the recurrent GEMMs as
     single-pass TF32 by default (torch.backends.cudnn.allow_tf32): off unless APS_B200_LSTM_TF32=1."""
-    if LSTM_ENGINE == "cudnn":
+    # hidden sizes that are not a multiple of 4 (no 16-byte rows for the kernel's copies) stay on the library as well
+    if LSTM_ENGINE == "cudnn" or any(m.lstm.hidden_size % 4 for m in mods):
         with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
             outs = [m.lstm(x)[0] for m, x in zip(mods, xs)]
     else:
