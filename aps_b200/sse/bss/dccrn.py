@@ -236,7 +236,7 @@ class DCCRN(nn.Module):
                                 cache=self._splits)
             if i + 1 != L:
                 skips.append(x)
-        # ---- complex LSTM bottleneck (cuDNN): features ordered (channel, frequency) like dccrn.py:41-50 ------
+        # ---- complex LSTM bottleneck (csrc/lstm.cu): features ordered (channel, frequency) like dccrn.py:41-50 ------
         N, Fq, T, C2 = x.shape
         Cc = C2 // 2
         hr = x[..., :Cc].permute(0, 2, 3, 1).reshape(N, T, Cc * Fq)
