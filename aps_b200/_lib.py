@@ -167,7 +167,12 @@ def last_error() -> str:
     return buf.value.decode("utf-8", "replace")
 
 
+CALLS = 0          # C-ABI launch calls made so far (each is at least one kernel launch); read by bench.py
+
+
 def check(rc: int) -> None:
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise RuntimeError(f"aps_b200: {last_error()} (code {rc})")
 

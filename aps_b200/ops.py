@@ -58,6 +58,28 @@ class SplitCache:
         self._items.clear()
 
 
+# bench.py's kernel leg: when set to a list, every tensor-core GEMM launch appends (kind, flops, start event, end event)
+PROFILE = None
+
+
+class _Timed:
+    """CUDA events on the launching stream around one GEMM launch (only while ops.PROFILE is a list)."""
+
+    def __init__(self, kind: str, flops: float, dev):
+        self.kind, self.flops, self.dev = kind, flops, dev
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            self.e0.record(th.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(th.cuda.current_stream(self.dev))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
 def _tc_ok(x: th.Tensor, w: th.Tensor, M: int, K: int, N: int) -> bool:
     return (GEMM_ENGINE == "tc" and K % 4 == 0 and K >= 32 and M >= 64 and N >= 32 and x.stride(0) % 4 == 0
             and w.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and w.stride(1) == 1)
@@ -86,7 +108,7 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
     e = _epilogue(bias, act, alpha, slope, leaky, residual, beta, post)
     if _tc_ok(x, weight, M, K, N):
         w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
-        with th.cuda.device(dev):
+        with th.cuda.device(dev), _Timed("linear", 2.0 * M * K * N, dev):
             _lib.check(_lib.load().aps_b200_linear_tc_fwd(x.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
                                                           w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(),
                                                           out.stride(0), _lib.stream_ptr(dev)))
@@ -114,7 +136,7 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
         # tensor-core path: implicit im2col + TF32 split by the kernel's producer warps
         w2 = weight.view(Cout, K)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
-        with th.cuda.device(dev):
+        with th.cuda.device(dev), _Timed("conv2d", 2.0 * M * K * Cout, dev):
             _lib.check(_lib.load().aps_b200_conv2d_nhwc_tc_fwd(x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(),
                                                                w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
                                                                padding[0], padding[1], dilation[0], dilation[1], e,
