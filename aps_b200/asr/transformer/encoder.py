@@ -322,20 +322,31 @@ class TransformerEncoder(nn.Module):
         self._packs = None
         self._splits = ops.SplitCache()
         self._graphs = {}
+        self._guard = ops.PackGuard(self)
+        self._fast = False
         self.use_graphs = os.environ.get("APS_B200_GRAPHS", "1") != "0"
         self.register_load_state_dict_post_hook(lambda m, k: m._drop_packs())
 
-    # ---- repacked weights (BatchNorm folding, layout changes); rebuilt after load_state_dict / .to() ------
+    # ---- repacked weights (BatchNorm folding, layout changes) ----------------------------------------------
+    # Rebuilt after load_state_dict / .to() and whenever a parameter or buffer was updated in place since they were
+    # built (ops.PackGuard: EMA / optimizer steps, a load_state_dict on a sub-module) — the captured CUDA graphs and the
+    # TF32 splits they read go with them, so a replay can never see stale weights.
     def _drop_packs(self):
         self._packs = None
         self._splits.clear()
         self._graphs.clear()
+        self._guard.reset()
+
+    def refresh_packs(self):
+        """Drop every derived copy of the weights (call after writing parameters through `.data`)."""
+        self._drop_packs()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
         if hasattr(self, "_splits"):
             self._splits.clear()
             self._graphs.clear()
+            self._guard.reset()
         return super()._apply(fn, *a, **k)
 
     @staticmethod
@@ -389,6 +400,45 @@ class TransformerEncoder(nn.Module):
     def _lin(self, x, w, b=None, **kw):
         return ops.linear(x, w, b, cache=self._splits, **kw)
 
+    # ---- activations travel as PAIRS (x, x_lo) ----------------------------------------------------------------
+    # x_lo is the TF32 "lo" companion of x (ops.linear): a tensor-core GEMM whose input has one loads both operand sides
+    # by TMA and needs no gather / split warps.  Every kernel of the stack that feeds a GEMM writes the companion of its
+    # output for free (GEMM / LayerNorm / attention / depthwise-conv epilogues); x_lo is None on the generic path
+    # (SIMT engine, widths that are not multiples of 128), where everything below degrades to the plain kernels.
+    def _lin2(self, xp, w, b=None, **kw):
+        return ops.linear(xp[0], w, b, cache=self._splits, x_lo=xp[1], **kw)
+
+    def _ln2(self, norm, x, residual=None, alpha=1.0, bias=None):
+        """(y, y_lo) with y = LN(alpha * (sum of the split-K slices of x + bias) + residual); norm None: no LN."""
+        if self._fast:
+            g, b, eps = (norm.weight.detach(), norm.bias.detach(), norm.eps) if norm is not None else (None, None, 0.0)
+            return ops.layernorm2(x, g, b, eps, bias=bias, residual=residual, alpha=alpha, normalize=norm is not None)
+        assert x.dim() == 2 and bias is None and norm is not None
+        return ops.layernorm(x, norm.weight.detach(), norm.bias.detach(), norm.eps, residual=residual, alpha=alpha), None
+
+    def _ksplit(self, K: int, N: int, M: int) -> int:
+        """K slices of the skinny GEMMs (d_ff -> d_model, front projection): 25 row tiles x 5 slices fill the machine at
+        the BASELINE size.  A function of (K, N) only — never of M — so a row's result does not depend on the batch."""
+        if not self._fast or M < 64 or N > 256 or K < 1024:
+            return 1
+        return 5 if K <= 2560 else 8
+
+    def _second(self, hp, lin, residual, alpha, norm):
+        """(y, y_lo): y = [LN](alpha * (h @ W.T + b) + residual) for the second Linear of an FFN."""
+        w, b = lin.weight.detach(), lin.bias.detach()
+        ks = self._ksplit(w.shape[1], w.shape[0], hp[0].shape[0])
+        if ks > 1 and hp[1] is not None:
+            parts = ops.linear(hp[0], w, None, cache=self._splits, x_lo=hp[1], ksplit=ks)
+            return self._ln2(norm, parts, residual=residual, alpha=alpha, bias=b)
+        if norm is None:
+            return self._lin2(hp, w, b, alpha=alpha, residual=residual), None
+        return self._ln2(norm, self._lin2(hp, w, b), residual=residual, alpha=alpha)
+
+    def _ffn(self, seq, xp, act):
+        """first Linear + activation of an FFN -> pair"""
+        r = self._lin2(xp, seq[0].weight.detach(), seq[0].bias.detach(), act=act, want_lo=self._fast)
+        return r if self._fast else (r, None)
+
     # ---- pieces ---------------------------------------------------------------------------------------------
     def _front_lens(self, lens: Optional[th.Tensor]) -> Optional[th.Tensor]:
         """Lengths after the projection front (integer exact, the reference's own rule)."""
@@ -398,100 +448,110 @@ class TransformerEncoder(nn.Module):
         return lens
 
     def _front(self, x: th.Tensor, pk):
+        """-> (rows pair, N, T): token rows [N*T, D] after the projection front."""
         if self.proj is None:
-            return x
+            N, T, _ = x.shape
+            return (ops.rows2d(x), None), N, T
         if isinstance(self.proj, LinearProj):
             N, T, Fi = x.shape
             if pk["lin_ln"] is None:
-                y = self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"], act="relu")
-            else:
-                g, b, eps = pk["lin_ln"]
-                y = ops.utt_norm(self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"]), N, T, g, b, eps, relu=True,
-                                 inplace=True)
-            return y.view(N, T, -1)
+                y = self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"], act="relu", want_lo=self._fast)
+                return (y if self._fast else (y, None)), N, T
+            g, b, eps = pk["lin_ln"]
+            y = ops.utt_norm(self._lin(ops.rows2d(x), pk["lin_w"], pk["lin_b"]), N, T, g, b, eps, relu=True,
+                             inplace=True)
+            return (y, None), N, T
         x4 = x[:, None] if x.dim() == 3 else x                      # N x C x T x F
         nhwc = x4.permute(0, 2, 3, 1).contiguous()
-        for (w, b, stride, padding), blk in zip(pk["convs"], self.proj.conv.enc_layers):
-            nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu", cache=self._splits)
+        lo = None
+        nconv = len(pk["convs"])
+        for i, ((w, b, stride, padding), blk) in enumerate(zip(pk["convs"], self.proj.conv.enc_layers)):
+            last = i + 1 == nconv and "front_w" in pk and self._fast
+            nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu", cache=self._splits, want_lo=last)
+            if last:
+                nhwc, lo = nhwc
         N, T, Fq, C = nhwc.shape
         flat = nhwc.view(N * T, Fq * C)
         if "front_w" in pk:
-            flat = self._lin(flat, pk["front_w"], pk["front_b"])
-        else:   # no output projection: restore the reference's channel-major feature order
-            flat = nhwc.permute(0, 1, 3, 2).reshape(N * T, C * Fq)
-        return flat.view(N, T, -1)
+            flo = lo.view(N * T, Fq * C) if lo is not None else None
+            w, b = pk["front_w"], pk["front_b"]
+            ks = self._ksplit(w.shape[1], w.shape[0], N * T)
+            if ks > 1 and flo is not None:
+                parts = ops.linear(flat, w, None, cache=self._splits, x_lo=flo, ksplit=ks)
+                return self._ln2(None, parts, bias=b), N, T
+            y = ops.linear(flat, w, b, cache=self._splits, x_lo=flo, want_lo=self._fast)
+            return (y if self._fast else (y, None)), N, T
+        # no output projection: restore the reference's channel-major feature order
+        return (nhwc.permute(0, 1, 3, 2).reshape(N * T, C * Fq), None), N, T
 
-    def _attention(self, a, x, res, N, T, inj, kpm, amask):
-        """res + SelfAttention(x) with the parameters of container `a`."""
-        qkv = self._lin(x, a.in_proj_weight.detach(), a.in_proj_bias.detach())
+    def _attention(self, a, xp, res, N, T, inj, kpm, amask):
+        """res + SelfAttention(x) with the parameters of container `a` (plain tensor)."""
+        qkv = self._lin2(xp, a.in_proj_weight.detach(), a.in_proj_bias.detach())
+        lo = self._fast
         if self.pose_type == "rel":
-            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=1, pos=inj, kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask)
+            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=1, pos=inj, kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask, want_lo=lo)
         elif self.pose_type == "xl":
             pos = self._lin(inj, a.rel_proj.weight.detach())
             ctx = ops.mhsa(qkv, N, T, self.nhead, mode=2, pos=pos, rel_u=a.rel_u.detach().contiguous(),
                            rel_v=a.rel_v.detach().contiguous(), kpm=kpm, kpm_fill=MIN_F32, attn_mask=amask,
-                           qpos_is_value=True)
+                           qpos_is_value=True, want_lo=lo)
         else:
-            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=0, kpm=kpm, kpm_fill=float("-inf"), attn_mask=amask)
-        return self._lin(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach(), residual=res)
+            ctx = ops.mhsa(qkv, N, T, self.nhead, mode=0, kpm=kpm, kpm_fill=float("-inf"), attn_mask=amask, want_lo=lo)
+        cp = ctx if lo else (ctx, None)
+        return self._lin2(cp, a.out_proj.weight.detach(), a.out_proj.bias.detach(), residual=res)
 
-    def _ffn_out(self, seq, x, act):
-        h = self._lin(x, seq[0].weight.detach(), seq[0].bias.detach(), act=act)
-        return h, seq[3]
-
-    @staticmethod
-    def _ln(norm, x, residual=None, alpha=1.0):
-        return ops.layernorm(x, norm.weight.detach(), norm.bias.detach(), norm.eps, residual=residual, alpha=alpha)
-
-    def _xfmr_layer(self, lay, pk, x, N, T, inj, kpm, amask):
+    def _xfmr_layer(self, lay, pk, xp, N, T, inj, kpm, amask):
         act = lay.activation
         if lay.pre_norm:
-            x = self._attention(lay.self_attn, self._ln(lay.norm1, x), x, N, T, inj, kpm, amask)
-            h, l2 = self._ffn_out(lay.feedforward, self._ln(lay.norm2, x), act)
-            return self._lin(h, l2.weight.detach(), l2.bias.detach(), residual=x)
-        x = self._ln(lay.norm1, self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask))
-        h, l2 = self._ffn_out(lay.feedforward, x, act)
-        return self._ln(lay.norm2, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x)
+            x = self._attention(lay.self_attn, self._ln2(lay.norm1, xp[0]), xp[0], N, T, inj, kpm, amask)
+            hp = self._ffn(lay.feedforward, self._ln2(lay.norm2, x), act)
+            return self._second(hp, lay.feedforward[3], x, 1.0, None)
+        xp = self._ln2(lay.norm1, self._attention(lay.self_attn, xp, xp[0], N, T, inj, kpm, amask))
+        hp = self._ffn(lay.feedforward, xp, act)
+        return self._second(hp, lay.feedforward[3], xp[0], 1.0, lay.norm2)
 
-    def _conv_module(self, lay, d, u, x, N, T):
-        g = self._lin(u, d["pw1_w"], d["pw1_b"], act="glu")
+    def _conv_module(self, lay, d, up, res, N, T):
+        """conv(u) + res (plain tensor)"""
+        g = self._lin2(up, d["pw1_w"], d["pw1_b"], act="glu")
         K = lay.kernel_size
         c = ops.dwconv1d(g, N, T, d["dw_w"], d["dw_b"], dilation=1, left_pad=(K - 1) if lay.padding else (K - 1) // 2,
-                         act=lay.activation)
-        return self._lin(c, d["pw2_w"], d["pw2_b"], residual=x)                # conv(u) + x
+                         act=lay.activation, want_lo=self._fast)
+        return self._lin2(c if self._fast else (c, None), d["pw2_w"], d["pw2_b"], residual=res)
 
-    def _cfmr_layer(self, lay, d, x, N, T, inj, kpm, amask):
+    def _cfmr_layer(self, lay, d, xp, N, T, inj, kpm, amask):
         act, mac = lay.activation, lay.macaron_factor
-        if lay.feedforward1 is not None:
-            if lay.pre_norm:
-                h, l2 = self._ffn_out(lay.feedforward1, self._ln(lay.norm_ffn1, x), act)
-                x = self._lin(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
-            else:
-                h, l2 = self._ffn_out(lay.feedforward1, x, act)
-                x = self._ln(lay.norm_ffn1, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
         if lay.pre_norm:
-            x = self._attention(lay.self_attn, self._ln(lay.norm_attn, x), x, N, T, inj, kpm, amask)
-            x = self._conv_module(lay, d, self._ln(lay.norm_conv, x), x, N, T)
-            h, l2 = self._ffn_out(lay.feedforward2, self._ln(lay.norm_ffn2, x), act)
-            return self._lin(h, l2.weight.detach(), l2.bias.detach(), alpha=mac, residual=x)
-        x = self._attention(lay.self_attn, x, x, N, T, inj, kpm, amask)
-        x = self._conv_module(lay, d, self._ln(lay.norm_attn, x), x, N, T)       # impl.py:536 reuses norm_attn
-        x = self._ln(lay.norm_conv, x)
-        h, l2 = self._ffn_out(lay.feedforward2, x, act)
-        return self._ln(lay.norm_ffn2, self._lin(h, l2.weight.detach(), l2.bias.detach()), residual=x, alpha=mac)
+            x = xp[0]
+            if lay.feedforward1 is not None:
+                hp = self._ffn(lay.feedforward1, self._ln2(lay.norm_ffn1, x), act)
+                x = self._second(hp, lay.feedforward1[3], x, mac, None)[0]
+            x = self._attention(lay.self_attn, self._ln2(lay.norm_attn, x), x, N, T, inj, kpm, amask)
+            x = self._conv_module(lay, d, self._ln2(lay.norm_conv, x), x, N, T)
+            hp = self._ffn(lay.feedforward2, self._ln2(lay.norm_ffn2, x), act)
+            return self._second(hp, lay.feedforward2[3], x, mac, None)
+        if lay.feedforward1 is not None:
+            hp = self._ffn(lay.feedforward1, xp, act)
+            xp = self._second(hp, lay.feedforward1[3], xp[0], mac, lay.norm_ffn1)
+        x = self._attention(lay.self_attn, xp, xp[0], N, T, inj, kpm, amask)
+        x = self._conv_module(lay, d, self._ln2(lay.norm_attn, x), x, N, T)       # impl.py:536 reuses norm_attn
+        xp = self._ln2(lay.norm_conv, x)
+        hp = self._ffn(lay.feedforward2, xp, act)
+        return self._second(hp, lay.feedforward2[3], xp[0], mac, lay.norm_ffn2)
 
     # ---- forward --------------------------------------------------------------------------------------------
     def _run(self, x: th.Tensor, lens_dev: Optional[th.Tensor]) -> th.Tensor:
         """Device-only part of the forward (safe to capture in a CUDA graph): x N x Ti x F -> N x To x D."""
         pk, dev = self._packs, x.device
-        x = self._front(x, pk)
-        N, T, D = x.shape
+        xp, N, T = self._front(x, pk)
+        D = xp[0].shape[-1]
         kpm = None
         if lens_dev is not None:
             kpm = (th.arange(T, device=dev)[None, :] >= lens_dev[:, None]).to(th.uint8).contiguous()
         inj = None
         if self.pose_type == "abs":
-            x = x * self.pose.factor + self.pose.encode(th.arange(0, T, 1.0, device=dev))
+            x3 = xp[0].view(N, T, D) * self.pose.factor + self.pose.encode(th.arange(0, T, 1.0, device=dev))
+            rows = x3.reshape(N * T, D).contiguous()
+            xp = (rows, ops.lo_companion(rows) if self._fast else None)
         elif self.pose_type == "rel":
             inj = self.pose.encode(th.arange(-T + 1, T, device=dev)).contiguous()
         else:
@@ -499,16 +559,20 @@ class TransformerEncoder(nn.Module):
         amask = None
         if self.lctx != -1 or self.rctx != -1:
             amask = _context_mask(T, self.chunk_size, self.lctx, self.rctx, dev).contiguous()
-        rows = x.reshape(N * T, D).contiguous()
+        if not xp[0].is_contiguous():
+            xp = (xp[0].contiguous(), None)
+        if self._fast and xp[1] is None:
+            xp = (xp[0], ops.lo_companion(xp[0]))
         for lay, d in zip(self.encoder.layers, pk["layers"]):
             if isinstance(lay, ConformerLayer):
-                rows = self._cfmr_layer(lay, d, rows, N, T, inj, kpm, amask)
+                xp = self._cfmr_layer(lay, d, xp, N, T, inj, kpm, amask)
             else:
-                rows = self._xfmr_layer(lay, d, rows, N, T, inj, kpm, amask)
+                xp = self._xfmr_layer(lay, d, xp, N, T, inj, kpm, amask)
         if self.encoder.norm is not None:
-            rows = self._ln(self.encoder.norm, rows)
+            xp = self._ln2(self.encoder.norm, xp[0])
+        rows = xp[0]
         if self.outp is not None:
-            rows = self._lin(rows, self.outp.weight.detach(), self.outp.bias.detach())
+            rows = self._lin2(xp, self.outp.weight.detach(), self.outp.bias.detach())
         return rows.view(N, T, -1)
 
     def _run_graphed(self, x: th.Tensor, lens_dev: Optional[th.Tensor]) -> th.Tensor:
@@ -546,11 +610,15 @@ class TransformerEncoder(nn.Module):
         if self.training:
             raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
         dev = _lib.require_cuda(inp_pad, "encoder input")
-        if self._packs is None or self._packs["dev"] != dev:
+        if self._packs is None or self._packs["dev"] != dev or self._guard.stale():
             if next(self.parameters()).device != dev:
                 raise RuntimeError(f"encoder parameters on {next(self.parameters()).device}, input on {dev}")
+            self._drop_packs()
             self._packs = self._build_packs(dev)
-            self._graphs.clear()
+            self._guard.mark()
+        # pair mode: tensor-core engine and a model width the fused LayerNorm / reduce kernel takes
+        self._fast = (ops.GEMM_ENGINE == "tc" and ops.layernorm2_ok(self.att_dim)
+                      and os.environ.get("APS_B200_ENC_PAIRS", "1") != "0")
         x = inp_pad.detach().float()
         out_len = self._front_lens(inp_len)
         lens_dev = None

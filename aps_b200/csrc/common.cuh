@@ -28,4 +28,16 @@ int num_sms();
 // reference trainer's guard, aps/trainer/ddp.py:146, keeps working through the Python shell)
 #define APSB_LAUNCH_CHECK() APSB_CUDA(cudaGetLastError())
 
+// Function attributes (opt-in dynamic shared memory) and occupancy answers are PER DEVICE: launchers keep one slot per
+// device index (the Python layer supports several GPUs per process).  Concurrent first calls from two host threads may
+// both set the attribute — the calls are idempotent, so the race is benign.
+struct LaunchCache {
+    int smem_set = -1, occ_smem = -1, occ = 1;
+};
+inline LaunchCache& launch_cache(LaunchCache (&slots)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return slots[dev & 63];
+}
+
 }  // namespace apsb

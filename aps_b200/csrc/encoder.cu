@@ -54,6 +54,85 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// LayerNorm that also finishes a split-K GEMM: v = alpha * (sum_p x[p] + bias) + res, y = LN(v) * gamma + beta, and
+// writes the TF32 "lo" companion of y for a TMA-fed tensor-core consumer (tc_gemm.cu MODE 3).  One warp per row,
+// 16-byte vector traffic, the row stays in registers between the statistics and the normalisation (D <= 1024,
+// D % 128 == 0: the encoder widths); `gamma == nullptr` with `do_norm == 0` makes it a plain reduce + bias + residual.
+__device__ __forceinline__ float ln_tf32_lo(float x) {
+    const float l = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+}
+
+template <int VPL>   // float4 vectors per lane: D = 128 * VPL
+__global__ void __launch_bounds__(256) layernorm2_kernel(const float* __restrict__ x, long long ldx, int nparts,
+                                                         long long part_stride, const float* __restrict__ bias,
+                                                         const float* __restrict__ res, long long ldr, float alpha,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, int do_norm, long long M, float* __restrict__ out,
+                                                         float* __restrict__ out_lo, long long ldo) {
+    const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    constexpr int D = 128 * VPL;
+    float4 v[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int d = 4 * lane + 128 * j;
+        float4 a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + d));
+        for (int p = 1; p < nparts; ++p) {                 // fixed order: deterministic
+            const float4 b = __ldg(reinterpret_cast<const float4*>(x + p * part_stride + m * ldx + d));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + d));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (res) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(res + m * ldr + d));
+            a.x = fmaf(alpha, a.x, r.x); a.y = fmaf(alpha, a.y, r.y); a.z = fmaf(alpha, a.z, r.z); a.w = fmaf(alpha, a.w, r.w);
+        } else {
+            a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+        }
+        v[j] = a;
+    }
+    if (do_norm) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float inv = rsqrtf(q / (float)D + eps);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int d = 4 * lane + 128 * j;
+            float4 y = make_float4((v[j].x - mean) * inv, (v[j].y - mean) * inv, (v[j].z - mean) * inv, (v[j].w - mean) * inv);
+            if (gamma) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + d));
+                const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                y.x = fmaf(y.x, g.x, b.x); y.y = fmaf(y.y, g.y, b.y); y.z = fmaf(y.z, g.z, b.z); y.w = fmaf(y.w, g.w, b.w);
+            }
+            v[j] = y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int d = 4 * lane + 128 * j;
+        *reinterpret_cast<float4*>(out + m * ldo + d) = v[j];
+        if (out_lo)
+            *reinterpret_cast<float4*>(out_lo + m * ldo + d) =
+                make_float4(ln_tf32_lo(v[j].x), ln_tf32_lo(v[j].y), ln_tf32_lo(v[j].z), ln_tf32_lo(v[j].w));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct DwParams {
     const float* x;
@@ -62,7 +141,7 @@ struct DwParams {
     const float* bias;   // [D] or nullptr
     int N, T, D, Kw, dil, lpad;   // out[t] = sum_k w[k] * x[t - lpad + k*dil]
     long long sn, st;    // row(n, t) = n*sn + t*st
-    Epilogue e;
+    Epilogue e;          // e.out_lo: optional TF32 "lo" companion of the output (V == 4 path)
 };
 
 // thread = (row, group of V channels); rows are walked with 32-bit arithmetic (64-bit divisions per element made the
@@ -106,8 +185,14 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(const __grid_constant__ D
             if (p.e.res) v = fmaf(p.e.beta, __ldg(p.e.res + m * p.e.ldres + d + j), v);
             o[j] = v;
         }
-        if (V == 4) *reinterpret_cast<float4*>(p.e.out + m * p.e.ldo + d) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
-        else p.e.out[m * p.e.ldo + d] = o[0];
+        if (V == 4) {
+            *reinterpret_cast<float4*>(p.e.out + m * p.e.ldo + d) = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+            if (p.e.out_lo)
+                *reinterpret_cast<float4*>(p.e.out_lo + m * p.e.ldo + d) =
+                    make_float4(ln_tf32_lo(o[0]), ln_tf32_lo(o[1 % V]), ln_tf32_lo(o[2 % V]), ln_tf32_lo(o[3 % V]));
+        } else {
+            p.e.out[m * p.e.ldo + d] = o[0];
+        }
     }
 }
 
@@ -130,6 +215,7 @@ struct AttnParams {
     const float* amask;  // [L, L] additive mask or nullptr
     float scale;         // 1/sqrt(dh)
     float* out;          // rows (n, t), columns h*dh + d
+    float* out_lo;       // optional TF32 "lo" companion of out
     long long ldo;
 };
 
@@ -248,7 +334,11 @@ __global__ void __launch_bounds__(kAttnWarps * 32) mhsa_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < (DH + 31) / 32; ++c) {
             const int d = lane + 32 * c;
-            if (d < DH) o[d] = (lrun > 0.f) ? acc[c] * inv : NAN;
+            if (d < DH) {
+                const float y = (lrun > 0.f) ? acc[c] * inv : NAN;
+                o[d] = y;
+                if (p.out_lo) p.out_lo[(n * p.sn + i * p.st) * p.ldo + h * DH + d] = ln_tf32_lo(y);
+            }
         }
     }
 }
@@ -267,10 +357,37 @@ extern "C" int aps_b200_layernorm_fwd(const float* x, int64_t ld_x, const float*
     return 0;
 }
 
-extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
-                                     int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
-                                     int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
-                                     int64_t ld_out, void* stream) {
+extern "C" int aps_b200_layernorm2_fwd(const float* x, int64_t ld_x, int32_t num_parts, int64_t part_stride,
+                                       const float* bias, const float* residual, int64_t ld_residual, float alpha,
+                                       const float* gamma, const float* beta, float eps, int32_t normalize,
+                                       int64_t rows, int64_t dim, float* out, float* out_lo, int64_t ld_out,
+                                       void* stream) {
+    APSB_CHECK_ARG(x && out && rows > 0 && dim > 0 && ld_x >= dim && ld_out >= dim && num_parts >= 1, "bad arguments");
+    APSB_CHECK_ARG(dim % 128 == 0 && dim <= 1024, "layernorm2: width %lld is not a multiple of 128 up to 1024", (long long)dim);
+    const uintptr_t al = (uintptr_t)x | (uintptr_t)out | (uintptr_t)out_lo | (uintptr_t)bias | (uintptr_t)residual |
+                         (uintptr_t)gamma | (uintptr_t)beta;
+    APSB_CHECK_ARG((al & 15) == 0 && (ld_x & 3) == 0 && (ld_out & 3) == 0 && (ld_residual & 3) == 0 && (part_stride & 3) == 0,
+                   "layernorm2: operands must be 16-byte aligned");
+    APSB_CHECK_ARG(num_parts == 1 || part_stride >= rows * ld_x, "layernorm2: part_stride too small");
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define APSB_LN2(V)                                                                                                    \
+    case V:                                                                                                            \
+        layernorm2_kernel<V><<<grid, 256, 0, st>>>(x, ld_x, num_parts, part_stride, bias, residual, ld_residual, alpha, \
+                                                   gamma, beta, eps, normalize, rows, out, out_lo, ld_out);           \
+        break;
+    switch ((int)(dim / 128)) {
+        APSB_LN2(1) APSB_LN2(2) APSB_LN2(3) APSB_LN2(4) APSB_LN2(5) APSB_LN2(6) APSB_LN2(7) APSB_LN2(8)
+    }
+#undef APSB_LN2
+    APSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int dwconv1d_impl(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
+                         int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
+                         int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
+                         float* out_lo, int64_t ld_out, void* stream) {
     APSB_CHECK_ARG(x && weight_kd && epi && out, "null pointer argument");
     APSB_CHECK_ARG(batch > 0 && num_frames > 0 && channels > 0 && kernel > 0 && dilation > 0 && left_pad >= 0,
                    "bad shape");
@@ -282,6 +399,7 @@ extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch
     p.e.bias = nullptr; p.e.act = epi->act; p.e.alpha = epi->alpha; p.e.slope = epi->prelu_slope;
     p.e.slope_stride = epi->prelu_per_channel ? 1 : 0; p.e.leak = epi->leaky_slope;
     p.e.res = epi->residual; p.e.ldres = epi->ld_residual; p.e.beta = epi->beta; p.e.out = out; p.e.ldo = ld_out;
+    p.e.out_lo = out_lo;
     p.e.post_scale = epi->post_scale; p.e.post_shift = epi->post_shift;
     APSB_CHECK_ARG(!epi->post_scale == !epi->post_shift, "post_scale and post_shift come together");
     APSB_CHECK_ARG(epi->act != ACT_PRELU || epi->prelu_slope, "PReLU slope missing");
@@ -289,6 +407,7 @@ extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch
     APSB_CHECK_ARG(rows < (1LL << 31), "too many rows (%lld)", rows);
     const bool vec = (channels & 3) == 0 && (ld_x & 3) == 0 && (ld_out & 3) == 0 && ((uintptr_t)x & 15) == 0 &&
                      ((uintptr_t)out & 15) == 0 && ((uintptr_t)weight_kd & 15) == 0;
+    APSB_CHECK_ARG(!out_lo || (vec && ((uintptr_t)out_lo & 15) == 0), "dwconv: a lo companion needs the 16-byte aligned path");
     const long long groups = vec ? channels / 4 : channels;
     const long long rows_per_block = groups >= 256 ? 1 : 256 / groups;
     const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
@@ -298,7 +417,23 @@ extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch
     return 0;
 }
 
-extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_t ld_out, void* stream) {
+extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
+                                     int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
+                                     int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
+                                     int64_t ld_out, void* stream) {
+    return dwconv1d_impl(x, ld_x, batch, num_frames, channels, stride_n, stride_t, weight_kd, bias, kernel, dilation,
+                         left_pad, epi, out, nullptr, ld_out, stream);
+}
+
+extern "C" int aps_b200_dwconv1d2_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
+                                      int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
+                                      int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
+                                      float* out_lo, int64_t ld_out, void* stream) {
+    return dwconv1d_impl(x, ld_x, batch, num_frames, channels, stride_n, stride_t, weight_kd, bias, kernel, dilation,
+                         left_pad, epi, out, out_lo, ld_out, stream);
+}
+
+static int mhsa_impl(const aps_b200_attn_desc* d, float* out, float* out_lo, int64_t ld_out, void* stream) {
     APSB_CHECK_ARG(d && out && d->q && d->k && d->v, "null pointer argument");
     APSB_CHECK_ARG(d->batch > 0 && d->length > 0 && d->heads > 0, "bad shape");
     APSB_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "unknown attention mode %d", d->mode);
@@ -312,7 +447,7 @@ extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_
     p.N = (int)d->batch; p.L = (int)d->length; p.H = (int)d->heads; p.dh = (int)d->head_dim; p.mode = d->mode;
     p.pos = d->pos; p.ldpos = d->ld_pos; p.rel_u = d->rel_u; p.rel_v = d->rel_v;
     p.kpm = d->key_padding_mask; p.kpm_fill = d->padding_fill; p.amask = d->attn_mask;
-    p.scale = d->scale; p.out = out; p.ldo = ld_out;
+    p.scale = d->scale; p.out = out; p.out_lo = out_lo; p.ldo = ld_out;
     dim3 grid((unsigned)((p.L + kAttnWarps - 1) / kAttnWarps), (unsigned)p.H, (unsigned)p.N);
     cudaStream_t st = (cudaStream_t)stream;
     switch (p.dh) {
@@ -322,4 +457,12 @@ extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_
     }
     APSB_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int aps_b200_mhsa_fwd(const aps_b200_attn_desc* d, float* out, int64_t ld_out, void* stream) {
+    return mhsa_impl(d, out, nullptr, ld_out, stream);
+}
+
+extern "C" int aps_b200_mhsa2_fwd(const aps_b200_attn_desc* d, float* out, float* out_lo, int64_t ld_out, void* stream) {
+    return mhsa_impl(d, out, out_lo, ld_out, stream);
 }

@@ -479,18 +479,19 @@ static int launch_frontend(FrontendParams& p, cudaStream_t st) {
     APSB_CHECK_ARG(p.total_chunks < (1LL << 31), "frontend: too many chunks (%lld)", p.total_chunks);
     p.tma_ok = (((uintptr_t)p.wav & 15) == 0 && (p.ld & 3) == 0 && (((long long)TC * p.hop) & 3) == 0 &&
                 (p.pad & 3) == 0 && !g_disable_tma) ? 1 : 0;
-    static int smem_set = -1, occ_smem = -1, occ_cached = 1;  // per instantiation; one GPU per process
-    if (L.total > smem_set) {
+    static LaunchCache slots[64];                             // per instantiation and device
+    LaunchCache& lc = launch_cache(slots);
+    if (L.total > lc.smem_set) {
         APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        smem_set = L.total;
+        lc.smem_set = L.total;
     }
-    if (L.total != occ_smem) {
+    if (L.total != lc.occ_smem) {
         int o = 0;
         APSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, L.total));
-        occ_cached = o < 1 ? 1 : o;
-        occ_smem = L.total;
+        lc.occ = o < 1 ? 1 : o;
+        lc.occ_smem = L.total;
     }
-    const int occ = occ_cached;
+    const int occ = lc.occ;
     long long grid = (long long)num_sms() * occ;
     if (grid > p.total_chunks) grid = p.total_chunks;
     kern<<<(unsigned)grid, kThreads, L.total, st>>>(p);

@@ -108,6 +108,77 @@ __global__ void __launch_bounds__(256) conv2d_narrow_kernel(const __grid_constan
     }
 }
 
+// 3x3 convolution of a 1- or 2-channel image (conv2d front of the encoder: [N, T, 80] -> 256 channels; first DCCRN
+// encoder layer: stacked re/im).  The layer is a pure WRITE-bandwidth problem (521 MB of output for 16 MB of input at
+// B = 64), so everything is arranged around issuing as few instructions per stored float4 as possible: a thread owns 4
+// output channels for its whole life and keeps their 9 * CIN * 4 weights and the bias in REGISTERS; a block walks
+// output rows (nb, oh) — one division per row, none per position — and the lanes of a warp share the position, so the
+// 9 * CIN input loads are warp-uniform L1 hits.  ~70 instructions per 4 outputs instead of the ~130 (+ a run-time
+// activation switch) of conv2d_narrow_kernel, which measured 547 us against an 85 us write bound.
+template <int CIN, int ACT>
+__global__ void __launch_bounds__(256) conv2d_thin3x3_kernel(const __grid_constant__ NarrowConvParams p) {
+    constexpr int K = 9 * CIN;
+    const unsigned groups = (unsigned)p.Cout >> 2;                // power of two <= 256 (host check)
+    const unsigned ppb = 256u / groups;                           // position lanes of the block
+    const unsigned g = threadIdx.x & (groups - 1), pl = threadIdx.x / groups;
+    float4 w[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float* wp = p.w + (long long)(4 * g) * K + k;
+        w[k] = make_float4(__ldg(wp), __ldg(wp + K), __ldg(wp + 2 * K), __ldg(wp + 3 * K));
+    }
+    const float4 b = p.e.bias ? __ldg(reinterpret_cast<const float4*>(p.e.bias) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned rows = (unsigned)(p.M / p.OW);                 // Nb * OH
+    const float alpha = p.e.alpha, leak = p.e.leak;
+    for (unsigned row = blockIdx.x; row < rows; row += gridDim.x) {
+        const unsigned nb = row / (unsigned)p.OH, oh = row - nb * (unsigned)p.OH;
+        const int ih0 = (int)oh * p.sh - p.ph;
+        const float* img = p.x + (long long)nb * p.H * p.W * CIN;
+        const float* r[3];
+        bool rv[3];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = ih0 + kh;
+            rv[kh] = ih >= 0 && ih < p.H;
+            r[kh] = img + (long long)(rv[kh] ? ih : 0) * p.W * CIN;
+        }
+        // pointers walk with the position lane: the loads below use immediate offsets (no 64-bit address arithmetic per load)
+        const long long xstep = (long long)ppb * p.sw * CIN;
+        const float* px0 = r[0] + ((long long)pl * p.sw - p.pw) * CIN;
+        const float* px1 = r[1] + ((long long)pl * p.sw - p.pw) * CIN;
+        const float* px2 = r[2] + ((long long)pl * p.sw - p.pw) * CIN;
+        float* op = p.e.out + ((long long)row * p.OW + pl) * p.e.ldo + 4 * g;
+        const long long ostep = (long long)ppb * p.e.ldo;
+        int iw0 = (int)pl * p.sw - p.pw;
+        for (unsigned ow = pl; ow < (unsigned)p.OW; ow += ppb, px0 += xstep, px1 += xstep, px2 += xstep, op += ostep, iw0 += (int)ppb * p.sw) {
+            float4 a = b;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* px = kh == 0 ? px0 : (kh == 1 ? px1 : px2);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const bool ok = rv[kh] && (unsigned)(iw0 + kw) < (unsigned)p.W;
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float xv = ok ? __ldg(px + kw * CIN + c) : 0.f;
+                        const float4 wv = w[(kh * 3 + kw) * CIN + c];
+                        a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y);
+                        a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
+                    }
+                }
+            }
+            if (ACT == ACT_RELU) {
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            } else if (ACT == ACT_LEAKY) {
+                a.x = a.x >= 0.f ? a.x : a.x * leak; a.y = a.y >= 0.f ? a.y : a.y * leak;
+                a.z = a.z >= 0.f ? a.z : a.z * leak; a.w = a.w >= 0.f ? a.w : a.w * leak;
+            }
+            a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+            *reinterpret_cast<float4*>(op) = a;
+        }
+    }
+}
+
 // Transposed convolution with very few OUTPUT channels (<= 8): the last DCCRN decoder layer maps 64 channels to
 // 2 * num_spks (dccrn.py:133-147).  On the GEMM engine such a layer pays for a 64-column tile and is bound by the
 // operand gather (6.9 ms at B = 128 x 4 s for 1.2 GB of traffic); here 8 lanes share one output pixel, each reads
@@ -414,6 +485,24 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
         const unsigned grid = (unsigned)(blocks < (long long)num_sms() * 16 ? blocks : (long long)num_sms() * 16);
         const size_t smem = (size_t)K * cg * 16;
         cudaStream_t st = (cudaStream_t)stream;
+        // 3x3, 1 or 2 input channels, Cout / 4 a power of two, plain bias + {none, relu, leaky}: weights-in-registers kernel
+        const bool thin = kernel_h == 3 && kernel_w == 3 && dil_h == 1 && dil_w == 1 && (in_channels == 1 || in_channels == 2) &&
+                          (ncols & 3) == 0 && cg <= 256 && (cg & (cg - 1)) == 0 && !epi->post_scale &&
+                          (e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LEAKY) && (e.ldo & 3) == 0 &&
+                          ((uintptr_t)out & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) && !getenv("APS_B200_NO_THIN_CONV");
+        if (thin) {
+            const long long rows = batch * OH;
+            const unsigned tg = (unsigned)(rows < (long long)num_sms() * 3 ? rows : (long long)num_sms() * 3);
+#define APSB_THIN(CI, A) conv2d_thin3x3_kernel<CI, A><<<tg, 256, 0, st>>>(c)
+            if (in_channels == 1) {
+                if (e.act == ACT_RELU) APSB_THIN(1, ACT_RELU); else if (e.act == ACT_LEAKY) APSB_THIN(1, ACT_LEAKY); else APSB_THIN(1, ACT_NONE);
+            } else {
+                if (e.act == ACT_RELU) APSB_THIN(2, ACT_RELU); else if (e.act == ACT_LEAKY) APSB_THIN(2, ACT_LEAKY); else APSB_THIN(2, ACT_NONE);
+            }
+#undef APSB_THIN
+            APSB_LAUNCH_CHECK();
+            return 0;
+        }
         if (kernel_h == 3 && kernel_w == 3 && in_channels == 1) conv2d_narrow_kernel<3, 3, 1><<<grid, 256, smem, st>>>(c);
         else if (kernel_h == 3 && kernel_w == 3 && in_channels == 2) conv2d_narrow_kernel<3, 3, 2><<<grid, 256, smem, st>>>(c);
         else conv2d_narrow_kernel<0, 0, 0><<<grid, 256, smem, st>>>(c);

@@ -34,6 +34,7 @@ struct Epilogue {
     float beta;
     float* out;
     long long ldo;
+    float* out_lo;         // tensor-core engine only: optional TF32 "lo" companion of `out` (same leading dimension)
     int dbg_nobias;        // tuning builds only: skip the bias loads of the tensor-core epilogue
 };
 

@@ -179,18 +179,19 @@ static int launch_istft(IstftParams& p, cudaStream_t st) {
     p.TC = TC;
     p.chunks_per_row = (p.T + TC - 1) / TC;
     p.total_chunks = p.rows * p.chunks_per_row;
-    static int smem_set = -1, occ_smem = -1, occ_cached = 1;
-    if (L.total > smem_set) {
+    static LaunchCache slots[64];                             // per instantiation and device
+    LaunchCache& lc = launch_cache(slots);
+    if (L.total > lc.smem_set) {
         APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        smem_set = L.total;
+        lc.smem_set = L.total;
     }
-    if (L.total != occ_smem) {
+    if (L.total != lc.occ_smem) {
         int o = 0;
         APSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kIThreads, L.total));
-        occ_cached = o < 1 ? 1 : o;
-        occ_smem = L.total;
+        lc.occ = o < 1 ? 1 : o;
+        lc.occ_smem = L.total;
     }
-    long long grid = (long long)num_sms() * occ_cached;
+    long long grid = (long long)num_sms() * lc.occ;
     if (grid > p.total_chunks) grid = p.total_chunks;
     kern<<<(unsigned)grid, kIThreads, L.total, st>>>(p);
     APSB_LAUNCH_CHECK();

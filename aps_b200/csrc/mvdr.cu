@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) covar_kernel(const __grid_constant__ Cova
     const float* xr = p.x.re + n * p.x.sn + f * p.x.sf;
     const float* xi = p.x.im + n * p.x.sn + f * p.x.sf;
     const int tvalid = p.lens ? (int)min((long long)p.T, p.lens[n]) : p.T;
-    const bool packed = (p.x.im == p.x.re + 1) && (p.x.st == 2);
+    // interleaved (re, im) pairs are read as float2: needs an 8-byte aligned base and even outer strides as well
+    const bool packed = (p.x.im == p.x.re + 1) && (p.x.st == 2) && ((reinterpret_cast<uintptr_t>(p.x.re) & 7) == 0) &&
+                        (((p.x.sn | p.x.sc | p.x.sf) & 1) == 0);
     const float inv_s = p.max_s ? 1.0f : 0.f;  // flag only
     const float ds = p.max_s ? (p.max_s[item] + p.norm_eps) : 1.f;
     const float dn = (p.mask_n && p.max_n) ? (p.max_n[item] + p.norm_eps) : 1.f;
@@ -340,7 +342,9 @@ __global__ void __launch_bounds__(256) beamform_kernel(const __grid_constant__ B
     const int n = (int)(item / p.F), f = (int)(item - (long long)n * p.F);
     const float* xr = p.x.re + n * p.x.sn + f * p.x.sf;
     const float* xi = p.x.im + n * p.x.sn + f * p.x.sf;
-    const bool packed = (p.x.im == p.x.re + 1) && (p.x.st == 2);
+    // interleaved (re, im) pairs are read as float2: needs an 8-byte aligned base and even outer strides as well
+    const bool packed = (p.x.im == p.x.re + 1) && (p.x.st == 2) && ((reinterpret_cast<uintptr_t>(p.x.re) & 7) == 0) &&
+                        (((p.x.sn | p.x.sc | p.x.sf) & 1) == 0);
     float wr[C], wi[C];
     const float2* pw = reinterpret_cast<const float2*>(p.w) + item * C;
 #pragma unroll

@@ -35,14 +35,15 @@ template <int K> __device__ __forceinline__ void accumulate(PairSums<K>& a, cons
     }
 }
 
-// grid (chunks, batch): CTA (c, n) reduces samples [c*span, (c+1)*span) of utterance n and writes its
+// grid (chunks * batch): CTA (c, n) = (blockIdx.x % chunks, blockIdx.x / chunks) reduces samples [c*span, (c+1)*span) of utterance n and writes its
 // PairSums to partials[n][c][:] (fixed order -> deterministic finalisation, no atomics).
 template <int K, bool VEC>
 __global__ void __launch_bounds__(kObjfThreads) pair_sums_kernel(aps_b200_signal_list est, aps_b200_signal_list ref,
-                                                               int64_t num_samples, int64_t span,
+                                                               int64_t num_samples, int64_t span, int chunks,
                                                                double* __restrict__ partials) {
-    const int64_t n = blockIdx.y;
-    const int64_t begin = (int64_t)blockIdx.x * span;
+    const int64_t n = blockIdx.x / (unsigned)chunks;          // batch folded into gridDim.x: no 65535 limit on N
+    const int64_t chunk = blockIdx.x - (unsigned)n * (unsigned)chunks;
+    const int64_t begin = chunk * span;
     const int64_t end = min(begin + span, num_samples);
     const float* xp[K];
     const float* sp[K];
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kObjfThreads) pair_sums_kernel(aps_b200_signal
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kObjfThreads / 32; ++w) v += red[w][threadIdx.x];
-        partials[(n * gridDim.x + blockIdx.x) * PairSums<K>::kCount + threadIdx.x] = v;
+        partials[(n * chunks + chunk) * PairSums<K>::kCount + threadIdx.x] = v;
     }
 }
 
@@ -174,11 +175,11 @@ static int launch_objf(const aps_b200_signal_list& est, const aps_b200_signal_li
         vec = vec && (reinterpret_cast<uintptr_t>(ref.ptr[k]) % 16 == 0) && ref.ld[k] % 4 == 0;
     }
     vec = vec && num_samples % 4 == 0;
-    dim3 grid(chunks, (unsigned)batch);
+    const unsigned grid = (unsigned)(batch * chunks);
     if (vec)
-        pair_sums_kernel<K, true><<<grid, kObjfThreads, 0, st>>>(est, ref, num_samples, span, ws);
+        pair_sums_kernel<K, true><<<grid, kObjfThreads, 0, st>>>(est, ref, num_samples, span, chunks, ws);
     else
-        pair_sums_kernel<K, false><<<grid, kObjfThreads, 0, st>>>(est, ref, num_samples, span, ws);
+        pair_sums_kernel<K, false><<<grid, kObjfThreads, 0, st>>>(est, ref, num_samples, span, chunks, ws);
     APSB_LAUNCH_CHECK();
     const int64_t total = batch * K * K;
     pair_objf_kernel<K><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws, batch, chunks, num_samples, d, out);
@@ -201,7 +202,7 @@ extern "C" int aps_b200_pair_objf_fwd(const aps_b200_signal_list* est, const aps
     APSB_CHECK_ARG(est->count == ref->count, "pair_objf: %d estimates vs %d references", est->count, ref->count);
     APSB_CHECK_ARG(est->count >= 1 && est->count <= APS_B200_MAX_SIGNALS, "pair_objf: 1..%d signals supported, got %d",
                    APS_B200_MAX_SIGNALS, est->count);
-    APSB_CHECK_ARG(batch > 0 && batch <= 65535 && num_samples > 0, "pair_objf: bad shape %lld x %lld", (long long)batch,
+    APSB_CHECK_ARG(batch > 0 && batch < (1LL << 20) && num_samples > 0, "pair_objf: bad shape %lld x %lld", (long long)batch,
                    (long long)num_samples);
     APSB_CHECK_ARG(desc->kind == 0 || desc->kind == 1, "pair_objf: unknown objective %d", desc->kind);
     APSB_CHECK_ARG(workspace_bytes >= aps_b200_pair_objf_workspace_bytes(batch, num_samples, est->count),

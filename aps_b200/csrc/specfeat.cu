@@ -149,10 +149,11 @@ static int launch_specfeat(SpecFeatParams& p, cudaStream_t st) {
     p.ft.mel_in_smem = (p.ft.M * p.ft.mel_stride * 4 <= 48 * 1024) ? 1 : 0;
     const int smem = (kSTC * (p.F | 1) + 2 * p.ft.M + 40 + (p.ft.mel_in_smem ? p.ft.M * p.ft.mel_stride : 0)) * 4 + 16;
     APSB_CHECK_ARG(smem <= 227 * 1024, "specfeat: %d bins need too much shared memory", p.F);
-    static int smem_set = -1;
-    if (smem > smem_set) {
+    static LaunchCache slots[64];                             // per instantiation and device
+    LaunchCache& lc = launch_cache(slots);
+    if (smem > lc.smem_set) {
         APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
+        lc.smem_set = smem;
     }
     p.chunks_per_row = (p.T + kSTC - 1) / kSTC;
     p.total_chunks = p.rows * p.chunks_per_row;

@@ -4,6 +4,11 @@
 //       linear rows         A(m, k) = x[m*ld + k]
 //       conv2d (NHWC)       implicit im2col,  m -> (nb, oh, ow), k -> (kh, kw, c)
 //       conv_transpose2d    implicit gather,  oh = ih*sh - ph + kh
+//       linear rows + lo    (MODE 3) the producer of x also wrote its companion xl = rn_tf32(x - trunc_tf32(x)): the tensor
+//                           core reads an fp32 operand as TF32 by DROPPING the low 13 mantissa bits, so the raw x tile IS
+//                           the "hi" operand and x = trunc(x) + xl holds to 2^-21; both tiles arrive by TMA and the kernel
+//                           has no gather / split warps at all.  Optional split-K (partial tiles, reduced by the
+//                           LayerNorm / reduce kernel) for the skinny [3200 x 2048] x [2048 x 256] shapes.
 //
 // Precision: the tensor core reads fp32 shared-memory operands as TF32 (10-bit mantissa).  Every operand is split into
 // hi = rn_tf32(x) and lo = rn_tf32(x - hi) and the product is rebuilt as hi*hi + hi*lo + lo*hi in the fp32 TMEM
@@ -45,8 +50,10 @@ constexpr int TC_BM = 128;
 #ifndef APSB_TC_PW_LINEAR
 #define APSB_TC_PW_LINEAR 4
 #endif
+// MODE 3 (linear layer whose activation comes with its TF32 "lo" companion, see below) has NO producer warps: the TMA
+// warp loads the A tiles as well.
 template <int BN, int MODE> struct TcRoles {
-    static constexpr int PW = BN > 128 ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR);
+    static constexpr int PW = MODE == 3 ? 0 : (BN > 128 ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
     static constexpr int PRODUCERS = PW * 32;
     static constexpr int THREADS = (6 + PW) * 32;
 };
@@ -152,6 +159,16 @@ __device__ __forceinline__ float rn_tf32(float v) {
     return __uint_as_float(u);
 }
 
+// "lo" companion of an activation the NEXT tensor-core GEMM will read raw (MODE 3): the tensor core truncates x to
+// trunc(x) = bits & ~0x1fff; lo = rn_tf32(x - trunc(x)) (the subtraction is exact; integer rounding as in the producers)
+__device__ __forceinline__ float tf32_lo(float x) {
+    const float l = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float4 tf32_lo4(const float4& v) {
+    return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
+
 // Activation resolved at compile time (a run-time switch inside the unrolled element loops would replicate tanhf / erff
 // dozens of times: the epilogue is instruction-issue bound, one warp per scheduler).
 template <int ACT>
@@ -172,7 +189,7 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
 template <int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue_vec(const uint32_t (&r)[32], const float4 (&res)[8], const Epilogue& e,
                                                 const float* __restrict__ cv, int c0, int n0, int N, bool row_ok,
-                                                float* __restrict__ orow) {
+                                                float* __restrict__ orow, float* __restrict__ olow) {
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
         const int n = n0 + 4 * q4;
@@ -190,7 +207,10 @@ __device__ __forceinline__ void tc_epilogue_vec(const uint32_t (&r)[32], const f
             o.y = fmaf(e.beta, res[q4].y, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 1]) + b4.y, sl4.y), ps4.y, pt4.y) * e.alpha);
             o.z = fmaf(e.beta, res[q4].z, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 2]) + b4.z, sl4.z), ps4.z, pt4.z) * e.alpha);
             o.w = fmaf(e.beta, res[q4].w, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 3]) + b4.w, sl4.w), ps4.w, pt4.w) * e.alpha);
-            if (row_ok) *reinterpret_cast<float4*>(orow + 4 * q4) = o;
+            if (row_ok) {
+                *reinterpret_cast<float4*>(orow + 4 * q4) = o;
+                if (olow) *reinterpret_cast<float4*>(olow + 4 * q4) = tf32_lo4(o);   // companion for a MODE 3 consumer
+            }
         }
     }
 }
@@ -277,6 +297,8 @@ struct TcParams {
     AGather a;
     Epilogue e;
     int epi_vec;                 // output / residual rows are 16-byte aligned and N % 4 == 0 (N % 8 for GLU)
+    int ksplit;                  // MODE 3: the K range is cut into `ksplit` slices, slice s -> out + s * split_stride
+    long long split_stride;      //         (raw partial sums; bias / activation / residual happen in the reducing kernel)
     int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
     unsigned long long* trace;   // debug builds (-DAPSB_TC_TRACE): [0] = event counter, then (event << 48 | clock) words
 };
@@ -322,6 +344,7 @@ template <int BN> struct TcCfg {
 template <int BN, int MODE>
 __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                   const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                    const __grid_constant__ TcParams p) {
     using C = TcCfg<BN>;
     constexpr int S = C::STAGES, BK = C::BK, SWZ = C::SWZ, A_BYTES = C::A_BYTES;
@@ -348,14 +371,34 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     // into L1 (the tex->L2 sector traffic of a 3x3 convolution drops towards a third).
     // MODE (0 linear, 1 conv2d, 2 conv_transpose2d) is a template parameter: each instantiation carries only its own
     // gather code — the producers are instruction-fetch bound when their per-k-block code does not fit the L0 i-cache.
-    const int num_kh = MODE == 0 ? 1 : p.a.KH;
-    const int num_kw = MODE == 0 ? 1 : p.a.KW;
-    const int kb_per_tap = MODE == 0 ? (p.K + BK - 1) / BK : p.a.Cin / BK;
+    constexpr bool LIN = MODE == 0 || MODE == 3;
+    const int num_kh = LIN ? 1 : p.a.KH;
+    const int num_kw = LIN ? 1 : p.a.KW;
+    const int kb_per_tap = LIN ? (p.K + BK - 1) / BK : p.a.Cin / BK;
     // The channel blocks are walked in groups of 32 channels whatever BK is (SUB = 2 half-blocks for BK = 16), so the
     // order of the k-steps — and with it every rounding — does not depend on the tile width: a row's result is bit
     // identical for any batch size / sharding (tests: "batch-shard invariance").
-    constexpr int SUB = MODE == 0 ? 1 : 32 / BK;
-    const int cb32_per_tap = MODE == 0 ? kb_per_tap : p.a.Cin / 32;
+    constexpr int SUB = LIN ? 1 : 32 / BK;
+    const int cb32_per_tap = LIN ? kb_per_tap : p.a.Cin / 32;
+    // MODE 3 work item: (row block, column block, K slice)
+    struct TileIdx { int m_blk, n_blk, ks, kb0, kb1; };
+    auto decode3 = [&](unsigned tile) {
+        TileIdx t;
+        unsigned t2 = tile;
+        t.ks = 0;
+        if (p.ksplit > 1) {
+            t2 = tile / (unsigned)p.ksplit;
+            t.ks = (int)(tile - t2 * (unsigned)p.ksplit);
+        }
+        t.m_blk = (int)(t2 / (unsigned)p.tiles_n);
+        t.n_blk = (int)(t2 - (unsigned)t.m_blk * (unsigned)p.tiles_n);
+        // slice boundaries in units of 32 k (whatever BK is): a row's rounding does not depend on the tile width
+        const int groups = (p.K + 31) / 32;
+        t.kb0 = (int)((long long)t.ks * groups / p.ksplit) * (32 / BK);
+        t.kb1 = (int)((long long)(t.ks + 1) * groups / p.ksplit) * (32 / BK);
+        if (t.kb1 > kb_per_tap) t.kb1 = kb_per_tap;
+        return t;
+    };
     auto tile_class = [&](unsigned tile) {
         const unsigned m_first = (tile / (unsigned)p.tiles_n) * TC_BM;
         const unsigned m_last = m_first + TC_BM - 1 < (unsigned)p.M ? m_first + TC_BM - 1 : (unsigned)p.M - 1;
@@ -369,11 +412,15 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     if (warp == WARP_TMA && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        if (MODE == 3) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
+        }
     }
     if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                tc_mbar_init(full_a + s, TcRoles<BN, MODE>::PW);
+                tc_mbar_init(full_a + s, MODE == 3 ? 1 : TcRoles<BN, MODE>::PW);
                 tc_mbar_init(full_b + s, 1);
                 tc_mbar_init(empty + s, 1);
             }
@@ -397,7 +444,27 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
 
     if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
-        if (lane == 0) {
+        if (MODE == 3) {
+            // operands of both sides by TMA: [A (raw x = hi) | A lo | W hi | W lo] per stage, one mbarrier transaction
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                    const TileIdx t = decode3(tile);
+                    for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+                        const int s = it % S;
+                        const uint32_t ph = (it / S) & 1;
+                        tc_mbar_wait_parked(empty + s, ph ^ 1);
+                        uint8_t* st = base + s * C::STAGE_BYTES;
+                        tc_mbar_expect_tx(full_b + s, 2 * A_BYTES + 2 * C::B_BYTES);
+                        tc_tma_load_2d(&tmA, full_b + s, st, kb * BK, t.m_blk * TC_BM);
+                        tc_tma_load_2d(&tmAlo, full_b + s, st + A_BYTES, kb * BK, t.m_blk * TC_BM);
+                        tc_tma_load_2d(&tmB, full_b + s, st + 2 * A_BYTES, kb * BK, t.n_blk * BN);
+                        tc_tma_load_2d(&tmBlo, full_b + s, st + 2 * A_BYTES + C::B_BYTES, kb * BK, t.n_blk * BN);
+                        TC_TR(1);
+                    }
+                }
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int n_blk = (int)(tile % (unsigned)p.tiles_n);
@@ -440,6 +507,28 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 const int cls = tile_class(tile);
                 uint32_t first = 1;
+                if (MODE == 3) {
+                    const TileIdx t = decode3(tile);
+                    for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
+                        const int s = it % S;
+                        const uint32_t ph = (it / S) & 1;
+                        tc_mbar_wait(full_b + s, ph);
+                        tc_fence_after();
+                        TC_TR(2);
+                        const uint32_t sa = s_u32(base + s * C::STAGE_BYTES);
+                        const uint32_t sal = sa + A_BYTES, sb = sa + 2 * A_BYTES, sbl = sb + C::B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint64_t da = tc_smem_desc<SWZ>(sa + k * 32), dal = tc_smem_desc<SWZ>(sal + k * 32);
+                            const uint64_t db = tc_smem_desc<SWZ>(sb + k * 32), dbl = tc_smem_desc<SWZ>(sbl + k * 32);
+                            tc_mma_tf32(d_tmem, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                            tc_mma_tf32(d_tmem, da, dbl, idesc, 1);
+                            tc_mma_tf32(d_tmem, dal, db, idesc, 1);
+                        }
+                        first = 0;
+                        tc_commit(empty + s);
+                    }
+                } else
                 for (int kh = 0; kh < num_kh; ++kh) {
                   if (!tc_kh_valid(p.a, cls, kh)) continue;
                   for (int j = 0; j < kb_per_tap * num_kw; ++j, ++it) {
@@ -479,8 +568,14 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
         for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
-            const int n_blk = (int)(tile % (unsigned)p.tiles_n);
-            const unsigned m_blk = tile / (unsigned)p.tiles_n;
+            int n_blk = (int)(tile % (unsigned)p.tiles_n);
+            unsigned m_blk = tile / (unsigned)p.tiles_n;
+            float* eout = e.out;                   // split-K: slice ks of the partial-sum workspace
+            if (MODE == 3) {
+                const TileIdx t = decode3(tile);
+                n_blk = t.n_blk; m_blk = (unsigned)t.m_blk;
+                eout += (long long)t.ks * p.split_stride;
+            }
             const uint32_t buf = tcount & 1;
             const long long m0 = (long long)m_blk * TC_BM + q * 32;
             const int ncols = min(BN, p.N - n_blk * BN);
@@ -556,7 +651,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 if (p.epi_vec) {
                     if (glu) {
                         // columns (2j, 2j+1) of the lane's row -> output column j; 16 outputs = 4 vector stores
-                        float* orow = e.out + mrow * e.ldo + (n0 >> 1);
+                        float* orow = eout + mrow * e.ldo + (n0 >> 1);
 #pragma unroll
                         for (int q4 = 0; q4 < 4; ++q4) {
                             const int n = n0 + 8 * q4;
@@ -585,9 +680,10 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             }
                         }
                     } else {
-                        float* orow = e.out + mrow * e.ldo + n0;
+                        float* orow = eout + mrow * e.ldo + n0;
+                        float* olow = e.out_lo ? e.out_lo + mrow * e.ldo + n0 : nullptr;
 #define TC_EPI_CASE(A) \
-    case A: tc_epilogue_vec<A, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow); break;
+    case A: tc_epilogue_vec<A, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow, olow); break;
                         switch (e.act) {
                             TC_EPI_CASE(ACT_RELU)
                             TC_EPI_CASE(ACT_SWISH)
@@ -596,7 +692,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             TC_EPI_CASE(ACT_PRELU)
                             TC_EPI_CASE(ACT_LEAKY)
                             TC_EPI_CASE(ACT_GELU)
-                            default: tc_epilogue_vec<ACT_NONE, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow);
+                            default: tc_epilogue_vec<ACT_NONE, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow, olow);
                         }
 #undef TC_EPI_CASE
                     }
@@ -618,7 +714,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                                 const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
                                 float o = e.alpha * (v * (1.f / (1.f + __expf(-g))));
                                 if (e.res) o = fmaf(e.beta, __ldg(e.res + m * e.ldres + no), o);
-                                e.out[m * e.ldo + no] = o;
+                                eout[m * e.ldo + no] = o;
                             }
                         }
                     } else {
@@ -643,7 +739,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             if (nok) {
                                 const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
                                 if (e.res) v = fmaf(e.beta, __ldg(e.res + m * e.ldres + n), v);
-                                e.out[m * e.ldo + n] = v;
+                                eout[m * e.ldo + n] = v;
                             }
                         }
                     }
@@ -652,7 +748,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             }
             if (threadIdx.x == 64) TC_TR(6);
         }
-    } else {
+    } else if constexpr (MODE != 3) {
         // ================= A producers (warps 6..9) =================
         // thread -> 16-byte chunk c of rows rg, rg + RSTEP, ...: a warp instruction reads whole SWZ-byte row segments.
         // The gather for k-block i+1 is issued BEFORE block i is split and stored, so the L2 round trip is hidden.
@@ -1016,7 +1112,8 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
 }
 
 template <int BN, int MODE>
-static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const TcParams& p, long long grid, cudaStream_t st) {
+static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const CUtensorMap& tA, const CUtensorMap& tAl,
+                          const TcParams& p, long long grid, cudaStream_t st) {
     using C = TcCfg<BN>;
     static bool attr_done[64] = {false};       // function attributes are per device (one context per GPU)
     int dev = 0;
@@ -1029,22 +1126,31 @@ static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const T
                                        (C::SMEM + 1024) * 100 / (228 * 1024) + 1));
         attr = true;
     }
-    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TcRoles<BN, MODE>::THREADS, C::SMEM, st>>>(tB, tBl, p);
+    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TcRoles<BN, MODE>::THREADS, C::SMEM, st>>>(tB, tBl, tA, tAl, p);
     APSB_LAUNCH_CHECK();
     return 0;
 }
 
+// `xlo` != nullptr selects MODE 3 (A tiles by TMA from x / xlo); `ksplit` > 1 cuts K into slices (MODE 3 only)
 template <int BN>
 static int launch_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, int M, int N, int K,
-                     const Epilogue& e, cudaStream_t st) {
+                     const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
+                     long long split_stride = 0) {
     using C = TcCfg<BN>;
-    CUtensorMap tB, tBl;
+    CUtensorMap tB, tBl, tA, tAl;
     if (int rc = make_map(&tB, W, N, K, ldw, BN, C::BK)) return rc;
     if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN, C::BK)) return rc;
+    tA = tB; tAl = tBl;
+    if (xlo) {
+        if (int rc = make_map(&tA, a.x, M, K, a.ld, TC_BM, C::BK)) return rc;
+        if (int rc = make_map(&tAl, xlo, M, K, a.ld, TC_BM, C::BK)) return rc;
+    }
     TcParams p{};
     p.M = M; p.N = N; p.K = K;
     p.tiles_n = (N + BN - 1) / BN;
-    const long long tiles = (long long)((M + TC_BM - 1) / TC_BM) * p.tiles_n;
+    p.ksplit = xlo ? (ksplit < 1 ? 1 : ksplit) : 1;
+    p.split_stride = split_stride;
+    const long long tiles = (long long)((M + TC_BM - 1) / TC_BM) * p.tiles_n * p.ksplit;
     APSB_CHECK_ARG(tiles < (1LL << 31) - 1024, "too many output tiles (%lld)", tiles);
     p.tiles = (unsigned)tiles;
     p.a = a; p.e = e;
@@ -1056,6 +1162,7 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
         if (e.post_scale) v = v && ((uintptr_t)e.post_scale & 15) == 0 && ((uintptr_t)e.post_shift & 15) == 0;
         if (e.act == ACT_PRELU && e.slope_stride) v = v && ((uintptr_t)e.slope & 15) == 0;
         p.epi_vec = v ? 1 : 0;
+        APSB_CHECK_ARG(!e.out_lo || v, "a lo companion needs the vector epilogue (16-byte aligned bias / residual / output rows)");
     }
 #ifdef APSB_TC_TRACE
     p.trace = g_tc_trace;
@@ -1063,9 +1170,10 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     p.e.dbg_nobias = (p.dbg & 128) ? 1 : 0;
 #endif
     const long long grid = tiles < num_sms() ? tiles : num_sms();
-    if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, p, grid, st);
-    if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, p, grid, st);
-    return launch_tc_mode<BN, 2>(tB, tBl, p, grid, st);
+    if (xlo) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, grid, st);
+    if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, grid, st);
+    if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, grid, st);
+    return launch_tc_mode<BN, 2>(tB, tBl, tA, tAl, p, grid, st);
 }
 
 // Tile width from a small cost model fitted to B200 measurements (profiles/r01_tc_gemm_v2_microbench.txt, cycles):
@@ -1073,27 +1181,33 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
 // pipeline refill), the epilogue ~4000 cycles per 32 columns and overlaps the next tile's main loop; tiles run in
 // waves of one per SM.
 static int run_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, long long M, long long N,
-                  long long K, const Epilogue& e, cudaStream_t st) {
+                  long long K, const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
+                  long long split_stride = 0) {
     const long long tm = (M + TC_BM - 1) / TC_BM;
+    const long long K0 = K;
     const int sms = num_sms();
     const char* fe = getenv("APS_B200_TC_BN");                    // tuning / test aid: force the tile width
     int bn = fe ? atoi(fe) : 0;
     if (bn != 64 && bn != 128 && bn != 256) {
         const int cand[3] = {256, 128, 64};
-        const double per_k[3] = {87.0, 64.0, 53.0};
+        // cycles per unit of k in the main loop: gather-fed tiles are bound by the producer warps (~the same time per
+        // k-block whatever the width), TMA-fed tiles (MODE 3) by the MMAs and the shared-memory operand traffic
+        const double per_k_gather[3] = {87.0, 64.0, 53.0}, per_k_tma[3] = {60.0, 36.0, 26.0};
+        const double* per_k = xlo ? per_k_tma : per_k_gather;
+        if (ksplit > 1) K = (K + ksplit - 1) / ksplit;
         double best = 0.0;
         for (int i = 0; i < 3; ++i) {
             if (cand[i] > 64 && N <= cand[i] / 2) continue;       // more than half of the tile would be padding
-            const long long tiles = tm * ((N + cand[i] - 1) / cand[i]);
+            const long long tiles = tm * ((N + cand[i] - 1) / cand[i]) * (ksplit > 1 ? ksplit : 1);
             const double waves = (double)((tiles + sms - 1) / sms);
             const double main_c = (double)K * per_k[i] + 5000.0, epi_c = 4000.0 * (cand[i] / 32);
             const double t = main_c + (waves - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
             if (bn == 0 || t < best) { best = t; bn = cand[i]; }
         }
     }
-    if (bn == 256) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
-    if (bn == 128) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
-    return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st);
+    if (bn == 256) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
+    if (bn == 128) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
+    return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
 }
 
 static int fill_tc_epilogue(Epilogue& e, const aps_b200_epilogue* epi, long long N, float* out, long long ld_out) {
@@ -1162,6 +1276,40 @@ extern "C" int aps_b200_linear_tc_fwd(const float* x, int64_t rows, int64_t in_f
     return run_tc(a, weight_hi, weight_lo, ld_w, rows, out_features, in_features, e, (cudaStream_t)stream);
 }
 
+// Linear layer with the optional extras of the encoder stack: `x_lo` (companion of x: the kernel then loads both
+// operand sides by TMA and runs without gather warps), `out_lo` (write the companion of the result for the next layer),
+// `ksplit` > 1 (needs x_lo; slice s of K accumulates into out + s * split_stride as RAW partial sums — the epilogue must
+// then be empty and aps_b200_layernorm2_fwd / the caller reduces the slices).
+extern "C" int aps_b200_linear_tc2_fwd(const float* x, const float* x_lo, int64_t rows, int64_t in_features, int64_t ld_x,
+                                       const float* weight_hi, const float* weight_lo, int64_t ld_w,
+                                       int64_t out_features, const aps_b200_epilogue* epi, float* out, float* out_lo,
+                                       int64_t ld_out, int32_t ksplit, int64_t split_stride, void* stream) {
+    APSB_CHECK_ARG(x, "null pointer argument");
+    APSB_CHECK_ARG(rows > 0 && in_features > 0 && out_features > 0 && ld_x >= in_features, "bad shape");
+    APSB_CHECK_ARG(rows < (1LL << 31) && out_features < (1LL << 31) && in_features < (1LL << 31), "shape too large");
+    APSB_CHECK_ARG((ld_x & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x_lo & 15) == 0,
+                   "the tensor-core path needs 16-byte aligned activation rows");
+    if (int rc = check_weights(weight_hi, weight_lo, ld_w, in_features)) return rc;
+    Epilogue e{};
+    if (int rc = fill_tc_epilogue(e, epi, out_features, out, ld_out)) return rc;
+    e.out_lo = out_lo;
+    if (out_lo)
+        APSB_CHECK_ARG(((uintptr_t)out_lo & 15) == 0 && ((uintptr_t)out & 15) == 0 && (ld_out & 3) == 0 &&
+                           (out_features & 3) == 0 && epi->act != ACT_GLU,
+                       "a lo companion needs 16-byte aligned output rows and no GLU");
+    if (ksplit > 1) {
+        APSB_CHECK_ARG(x_lo, "split-K needs the lo companion of x (TMA-fed mode)");
+        APSB_CHECK_ARG(!epi->bias && epi->act == ACT_NONE && !epi->residual && !epi->post_scale && epi->alpha == 1.f && !out_lo,
+                       "split-K writes raw partial sums: the epilogue must be empty");
+        APSB_CHECK_ARG(split_stride >= rows * ld_out, "split_stride too small");
+        APSB_CHECK_ARG(ksplit <= (in_features + 31) / 32, "ksplit %d: every slice needs at least one 32-wide k group", ksplit);
+    }
+    AGather a{};
+    a.mode = 0; a.x = x; a.ld = ld_x;
+    return run_tc(a, weight_hi, weight_lo, ld_w, rows, out_features, in_features, e, (cudaStream_t)stream, x_lo,
+                  ksplit < 1 ? 1 : ksplit, split_stride);
+}
+
 static int conv_geometry(AGather& a, const float* x, int64_t batch, int64_t height, int64_t width,
                          int64_t in_channels, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,
                          int pad_w) {
@@ -1178,11 +1326,11 @@ static int conv_geometry(AGather& a, const float* x, int64_t batch, int64_t heig
     return 0;
 }
 
-extern "C" int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
-                                           int64_t in_channels, const float* weight_hi, const float* weight_lo,
-                                           int64_t out_channels, int kernel_h, int kernel_w, int stride_h,
-                                           int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                                           const aps_b200_epilogue* epi, float* out, void* stream) {
+static int conv2d_tc_impl(const float* x, int64_t batch, int64_t height, int64_t width,
+                          int64_t in_channels, const float* weight_hi, const float* weight_lo,
+                          int64_t out_channels, int kernel_h, int kernel_w, int stride_h,
+                          int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                          const aps_b200_epilogue* epi, float* out, float* out_lo, void* stream) {
     AGather a{};
     if (int rc = conv_geometry(a, x, batch, height, width, in_channels, kernel_h, kernel_w, stride_h, stride_w, pad_h,
                                pad_w))
@@ -1199,7 +1347,30 @@ extern "C" int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_
     Epilogue e{};
     const int64_t ncols = (epi && epi->act == ACT_GLU) ? out_channels / 2 : out_channels;
     if (int rc = fill_tc_epilogue(e, epi, out_channels, out, ncols)) return rc;
+    e.out_lo = out_lo;
+    if (out_lo)
+        APSB_CHECK_ARG(((uintptr_t)out_lo & 15) == 0 && ((uintptr_t)out & 15) == 0 && (out_channels & 3) == 0 &&
+                           epi->act != ACT_GLU, "a lo companion needs 16-byte aligned output rows and no GLU");
     return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream);
+}
+
+extern "C" int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                           int64_t in_channels, const float* weight_hi, const float* weight_lo,
+                                           int64_t out_channels, int kernel_h, int kernel_w, int stride_h,
+                                           int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                           const aps_b200_epilogue* epi, float* out, void* stream) {
+    return conv2d_tc_impl(x, batch, height, width, in_channels, weight_hi, weight_lo, out_channels, kernel_h, kernel_w,
+                          stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, epi, out, nullptr, stream);
+}
+
+/* as above, and also writes the TF32 "lo" companion of the output (same shape) for a TMA-fed linear consumer */
+extern "C" int aps_b200_conv2d_nhwc_tc2_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                            int64_t in_channels, const float* weight_hi, const float* weight_lo,
+                                            int64_t out_channels, int kernel_h, int kernel_w, int stride_h,
+                                            int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                            const aps_b200_epilogue* epi, float* out, float* out_lo, void* stream) {
+    return conv2d_tc_impl(x, batch, height, width, in_channels, weight_hi, weight_lo, out_channels, kernel_h, kernel_w,
+                          stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, epi, out, out_lo, stream);
 }
 
 extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float* x_skip, int64_t batch, int64_t height,

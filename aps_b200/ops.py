@@ -80,6 +80,34 @@ class _Timed:
         return False
 
 
+class PackGuard:
+    """Detects in-place updates of the parameters / buffers that derived weight copies were built from (BatchNorm
+    folded into convolutions, GLU-interleaved rows, NHWC filter order, TF32 hi/lo splits, captured CUDA graphs).
+
+    `stale()` compares the sum of the tensors' version counters (bumped by every in-place op: optimizer / EMA updates
+    `p.mul_().add_()`, `p.copy_()`, a `load_state_dict` on a SUB-module) and their storage addresses with the values
+    seen when the copies were built.  Writes through `.data` (`p.data.copy_(...)`) do not touch the version counter of
+    `p`; after such a write call the owning module's `refresh_packs()`."""
+
+    def __init__(self, module):
+        self.module, self.tensors, self.key = module, None, None
+
+    def _key(self):
+        ts = self.tensors
+        return (sum(t._version for t in ts), sum(t.data_ptr() for t in ts) & 0xFFFFFFFFFFFF, len(ts))
+
+    def mark(self):
+        import itertools
+        self.tensors = list(itertools.chain(self.module.parameters(), self.module.buffers()))
+        self.key = self._key()
+
+    def stale(self) -> bool:
+        return self.tensors is None or self._key() != self.key
+
+    def reset(self):
+        self.tensors, self.key = None, None
+
+
 def _tc_ok(x: th.Tensor, w: th.Tensor, M: int, K: int, N: int) -> bool:
     return (GEMM_ENGINE == "tc" and K % 4 == 0 and K >= 32 and M >= 64 and N >= 32 and x.stride(0) % 4 == 0
             and w.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and w.stride(1) == 1)
@@ -97,31 +125,59 @@ def rows2d(x: th.Tensor) -> th.Tensor:
 
 def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, act: str = "none", alpha: float = 1.0,
            slope=None, leaky: float = 0.0, residual: Optional[th.Tensor] = None, beta: float = 1.0,
-           out: Optional[th.Tensor] = None, post=None, cache: Optional["SplitCache"] = None) -> th.Tensor:
-    """out[m, :] = alpha * act(x[m, :] @ weight.T + bias) + beta * residual[m, :]   (x: [M, K], weight: [N, K])"""
+           out: Optional[th.Tensor] = None, post=None, cache: Optional["SplitCache"] = None,
+           x_lo: Optional[th.Tensor] = None, want_lo: bool = False, ksplit: int = 1):
+    """out[m, :] = alpha * act(x[m, :] @ weight.T + bias) + beta * residual[m, :]   (x: [M, K], weight: [N, K])
+
+    Tensor-core extras (encoder stack): `x_lo` = the TF32 lo companion of x (see `lo_companion`) — the kernel then loads
+    both operand sides by TMA; `want_lo` -> returns (out, out_lo); `ksplit` > 1 (needs x_lo, empty epilogue) -> returns
+    the RAW partial sums [ksplit, M, N] that `layernorm2` reduces."""
     dev = _lib.require_cuda(x, "linear input")
     M, K = x.shape
     N = weight.shape[0]
     ncol = N // 2 if act == "glu" else N
+    tc = _tc_ok(x, weight, M, K, N)
+    if x_lo is not None and not (tc and x_lo.shape == x.shape and x_lo.stride() == x.stride()):
+        x_lo = None
+    if ksplit > 1:
+        if x_lo is None:
+            raise RuntimeError("ops.linear: split-K needs the tensor-core path and the lo companion of x")
+        parts = th.empty((ksplit, M, N), dtype=th.float32, device=dev)
+        w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
+        e = _epilogue()
+        with th.cuda.device(dev), _Timed("linear", 2.0 * M * K * N, dev):
+            _lib.check(_lib.load().aps_b200_linear_tc2_fwd(x.data_ptr(), x_lo.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
+                                                           w_lo.data_ptr(), w_hi.stride(0), N, e, parts.data_ptr(), 0,
+                                                           N, ksplit, M * N, _lib.stream_ptr(dev)))
+        return parts
     if out is None:
         out = th.empty((M, ncol), dtype=th.float32, device=dev)
     e = _epilogue(bias, act, alpha, slope, leaky, residual, beta, post)
-    if _tc_ok(x, weight, M, K, N):
+    if tc:
         w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
+        lo = th.empty_like(out) if want_lo else None
         with th.cuda.device(dev), _Timed("linear", 2.0 * M * K * N, dev):
-            _lib.check(_lib.load().aps_b200_linear_tc_fwd(x.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
-                                                          w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(),
-                                                          out.stride(0), _lib.stream_ptr(dev)))
-        return out
+            if x_lo is None and lo is None:
+                _lib.check(_lib.load().aps_b200_linear_tc_fwd(x.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
+                                                              w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(),
+                                                              out.stride(0), _lib.stream_ptr(dev)))
+            else:
+                _lib.check(_lib.load().aps_b200_linear_tc2_fwd(x.data_ptr(), _lib.ptr(x_lo), M, K, x.stride(0),
+                                                               w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e,
+                                                               out.data_ptr(), _lib.ptr(lo), out.stride(0), 1, 0,
+                                                               _lib.stream_ptr(dev)))
+        return (out, lo) if want_lo else out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
                                                    N, e, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
-    return out
+    return (out, None) if want_lo else out
 
 
 def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
-                act: str = "none", slope=None, leaky: float = 0.0, cache: Optional["SplitCache"] = None) -> th.Tensor:
-    """x [B, H, W, Cin] contiguous, weight [Cout, KH, KW, Cin] contiguous -> [B, OH, OW, Cout]."""
+                act: str = "none", slope=None, leaky: float = 0.0, cache: Optional["SplitCache"] = None,
+                want_lo: bool = False):
+    """x [B, H, W, Cin] contiguous, weight [Cout, KH, KW, Cin] contiguous -> [B, OH, OW, Cout]
+    (`want_lo`: -> (out, TF32 lo companion or None when the layer does not run on the tensor-core engine))."""
     dev = _lib.require_cuda(x, "conv input")
     B, H, W, Cin = x.shape
     Cout, KH, KW, _ = weight.shape
@@ -136,17 +192,18 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
         # tensor-core path: implicit im2col + TF32 split by the kernel's producer warps
         w2 = weight.view(Cout, K)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
+        lo = th.empty_like(out) if (want_lo and act != "glu" and Cout % 4 == 0) else None
         with th.cuda.device(dev), _Timed("conv2d", 2.0 * M * K * Cout, dev):
-            _lib.check(_lib.load().aps_b200_conv2d_nhwc_tc_fwd(x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(),
-                                                               w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
-                                                               padding[0], padding[1], dilation[0], dilation[1], e,
-                                                               out.data_ptr(), _lib.stream_ptr(dev)))
-        return out
+            _lib.check(_lib.load().aps_b200_conv2d_nhwc_tc2_fwd(x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(),
+                                                                w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
+                                                                padding[0], padding[1], dilation[0], dilation[1], e,
+                                                                out.data_ptr(), _lib.ptr(lo), _lib.stream_ptr(dev)))
+        return (out, lo) if want_lo else out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv2d_nhwc_fwd(x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW,
                                                         stride[0], stride[1], padding[0], padding[1], dilation[0],
                                                         dilation[1], e, out.data_ptr(), _lib.stream_ptr(dev)))
-    return out
+    return (out, None) if want_lo else out
 
 
 def cat_complex(a: th.Tensor, b: th.Tensor) -> th.Tensor:
@@ -230,6 +287,37 @@ def layernorm(x: th.Tensor, gamma, beta, eps: float = 1e-5, residual: Optional[t
     return out
 
 
+def layernorm2(x: th.Tensor, gamma, beta, eps: float = 1e-5, bias=None, residual: Optional[th.Tensor] = None,
+               alpha: float = 1.0, normalize: bool = True, want_lo: bool = True):
+    """v = alpha * (sum_p x[p] + bias) + residual; y = LN(v) * gamma + beta (or v when not `normalize`).
+    x: [M, D] or the split-K partial sums [P, M, D] of `linear(..., ksplit=P)`; D % 128 == 0, D <= 1024.
+    -> (y, TF32 lo companion of y or None)."""
+    dev = _lib.require_cuda(x, "layernorm input")
+    parts = x.shape[0] if x.dim() == 3 else 1
+    M, D = x.shape[-2], x.shape[-1]
+    out = th.empty((M, D), dtype=th.float32, device=dev)
+    lo = th.empty_like(out) if want_lo else None
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_layernorm2_fwd(x.data_ptr(), x.stride(-2), parts, x.stride(0) if x.dim() == 3 else 0,
+                                                       _lib.ptr(bias), _lib.ptr(residual),
+                                                       residual.stride(0) if residual is not None else 0, float(alpha),
+                                                       _lib.ptr(gamma), _lib.ptr(beta), float(eps), int(normalize), M, D,
+                                                       out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.stream_ptr(dev)))
+    return out, lo
+
+
+def lo_companion(x: th.Tensor) -> th.Tensor:
+    """rn_tf32(x - trunc_tf32(x)) for a tensor that no kernel epilogue produced (e.g. the input features): what a
+    TMA-fed tensor-core GEMM needs next to the raw x.  Plain device tensor ops (integer view arithmetic)."""
+    xi = x.contiguous().view(th.int32)
+    lo = x - (xi & -8192).view(th.float32)
+    return ((lo.view(th.int32) + 4096) & -8192).view(th.float32)
+
+
+def layernorm2_ok(D: int) -> bool:
+    return D % 128 == 0 and D <= 1024
+
+
 def utt_norm(x: th.Tensor, N: int, T: int, gamma=None, beta=None, eps: float = 1e-5, per_channel: bool = False,
              relu: bool = False, stride_n: Optional[int] = None, stride_t: int = 1, inplace: bool = False) -> th.Tensor:
     """Per-utterance normalisation over time of token rows [N*T, C] (row(n, t) = n*stride_n + t*stride_t):
@@ -306,25 +394,28 @@ def lstm(x: th.Tensor, lstm_mod, cache: Optional[dict] = None) -> th.Tensor:
 
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
              stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
-             residual=None, post=None) -> th.Tensor:
-    """Depthwise conv over time on token rows [N*T, D] (row(n, t) = n*stride_n + t*stride_t)."""
+             residual=None, post=None, want_lo: bool = False):
+    """Depthwise conv over time on token rows [N*T, D] (row(n, t) = n*stride_n + t*stride_t);
+    `want_lo` -> (out, TF32 lo companion)."""
     dev = _lib.require_cuda(x, "dwconv input")
     D = x.shape[1]
     Kw = weight_kd.shape[0]
     out = th.empty_like(x)
+    lo = th.empty_like(x) if want_lo else None
     e = _epilogue(None, act, 1.0, slope, 0.0, residual, 1.0, post)
     with th.cuda.device(dev):
-        _lib.check(_lib.load().aps_b200_dwconv1d_fwd(x.data_ptr(), x.stride(0), N, T, D,
-                                                     T if stride_n is None else stride_n, stride_t,
-                                                     weight_kd.data_ptr(), _lib.ptr(bias), Kw, dilation, left_pad, e,
-                                                     out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
-    return out
+        _lib.check(_lib.load().aps_b200_dwconv1d2_fwd(x.data_ptr(), x.stride(0), N, T, D,
+                                                      T if stride_n is None else stride_n, stride_t,
+                                                      weight_kd.data_ptr(), _lib.ptr(bias), Kw, dilation, left_pad, e,
+                                                      out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.stream_ptr(dev)))
+    return (out, lo) if want_lo else out
 
 
 def mhsa(qkv: th.Tensor, N: int, L: int, H: int, mode: int = 0, pos: Optional[th.Tensor] = None,
          rel_u=None, rel_v=None, kpm: Optional[th.Tensor] = None, kpm_fill: float = float("-inf"),
-         attn_mask: Optional[th.Tensor] = None, qpos_is_value: bool = False) -> th.Tensor:
-    """Self-attention on the packed projection qkv [N*L, 3E] (rows batch-major) -> context [N*L, E]."""
+         attn_mask: Optional[th.Tensor] = None, qpos_is_value: bool = False, want_lo: bool = False):
+    """Self-attention on the packed projection qkv [N*L, 3E] (rows batch-major) -> context [N*L, E]
+    (`want_lo` -> (context, TF32 lo companion))."""
     dev = _lib.require_cuda(qkv, "attention input")
     E = qkv.shape[1] // 3
     dh = E // H
@@ -344,6 +435,7 @@ def mhsa(qkv: th.Tensor, N: int, L: int, H: int, mode: int = 0, pos: Optional[th
     d.padding_fill = kpm_fill
     d.attn_mask = _lib.ptr(attn_mask)
     d.scale = 1.0 / dh**0.5
+    lo = th.empty_like(out) if want_lo else None
     with th.cuda.device(dev):
-        _lib.check(_lib.load().aps_b200_mhsa_fwd(d, out.data_ptr(), out.stride(0), _lib.stream_ptr(dev)))
-    return out
+        _lib.check(_lib.load().aps_b200_mhsa2_fwd(d, out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.stream_ptr(dev)))
+    return (out, lo) if want_lo else out

@@ -203,16 +203,23 @@ class DCCRN(nn.Module):
         self.num_spks, self.connection, self.share_decoder = num_spks, connection, share_decoder
         self._packs = None
         self._splits = ops.SplitCache()
+        self._guard = ops.PackGuard(self)
         self.register_load_state_dict_post_hook(lambda m, k: m._reset())
 
     def _reset(self):
         self._packs = None
         self._splits.clear()
+        self._guard.reset()
+
+    def refresh_packs(self):
+        """Drop every derived copy of the weights (call after writing parameters through `.data`)."""
+        self._reset()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
         if hasattr(self, "_splits"):
             self._splits.clear()
+            self._guard.reset()
         return super()._apply(fn, *a, **k)
 
     def _build_packs(self):
@@ -225,8 +232,10 @@ class DCCRN(nn.Module):
     def _mask_nhwc(self, packed: th.Tensor) -> th.Tensor:
         if self.training:
             raise RuntimeError("aps_b200.DCCRN implements the inference forward only: call .eval()")
-        if self._packs is None:
+        if self._packs is None or self._guard.stale():       # also catches in-place parameter updates (ops.PackGuard)
+            self._reset()
             self._packs = self._build_packs()
+            self._guard.mark()
         pk = self._packs
         x = packed
         skips = []

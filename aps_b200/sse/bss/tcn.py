@@ -192,16 +192,23 @@ class FreqConvTasNet(nn.Module):
         self.num_spks, self.num_bins = num_spks, num_bins
         self._packs = None
         self._splits = ops.SplitCache()
+        self._guard = ops.PackGuard(self)
         self.register_load_state_dict_post_hook(lambda m, k: m._reset())
 
     def _reset(self):
         self._packs = None
         self._splits.clear()
+        self._guard.reset()
+
+    def refresh_packs(self):
+        """Drop every derived copy of the weights (call after writing parameters through `.data`)."""
+        self._reset()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
         if hasattr(self, "_splits"):
             self._splits.clear()
+            self._guard.reset()
         return super()._apply(fn, *a, **k)
 
     def _lin(self, x, w, b=None, **kw):
@@ -222,8 +229,10 @@ class FreqConvTasNet(nn.Module):
         dev = _lib.require_cuda(feats, "mask network input")
         if feats.dim() != 3:
             raise RuntimeError(f"expect N x T x F features, got {feats.dim()}D")
-        if self._packs is None:
+        if self._packs is None or self._guard.stale():       # also catches in-place parameter updates (ops.PackGuard)
+            self._reset()
             self._packs = self._build_packs()
+            self._guard.mark()
         pk = self._packs
         N, T, Fi = feats.shape
         rows = ops.rows2d(feats.detach().float())
@@ -304,16 +313,23 @@ class TimeConvTasNet(nn.Module):
         self.num_spks, self.mixture_consistency, self.L = num_spks, mixture_consistency, L
         self._packs = None
         self._splits = ops.SplitCache()
+        self._guard = ops.PackGuard(self)
         self.register_load_state_dict_post_hook(lambda m, k: m._reset())
 
     def _reset(self):
         self._packs = None
         self._splits.clear()
+        self._guard.reset()
+
+    def refresh_packs(self):
+        """Drop every derived copy of the weights (call after writing parameters through `.data`)."""
+        self._reset()
 
     def _apply(self, fn, *a, **k):
         self._packs = None
         if hasattr(self, "_splits"):
             self._splits.clear()
+            self._guard.reset()
         return super()._apply(fn, *a, **k)
 
     def _lin(self, x, w, b=None, **kw):
@@ -336,8 +352,10 @@ class TimeConvTasNet(nn.Module):
         if self.training:
             raise RuntimeError("aps_b200.TimeConvTasNet implements the inference forward only: call .eval()")
         dev = _lib.require_cuda(mix, "mixture")
-        if self._packs is None:
+        if self._packs is None or self._guard.stale():       # also catches in-place parameter updates (ops.PackGuard)
+            self._reset()
             self._packs = self._build_packs()
+            self._guard.mark()
         pk = self._packs
         mix = mix.detach().float().contiguous()
         Nb, S = mix.shape

@@ -53,6 +53,12 @@ def pair_objf_matrix(est: Sequence[th.Tensor], ref: Sequence[th.Tensor], kind: i
         if x.shape != est[0].shape:
             raise RuntimeError("Dimention mismatch when calculate " + f"si-snr, {x.shape} vs {est[0].shape}")
     dev = _lib.require_cuda(est[0], "separated signal")
+    if th.is_grad_enabled() and any(x.requires_grad for x in est):
+        # the kernels compute the VALUE of the objective (the forward hot path); returning a loss without an autograd
+        # graph to a training loop would silently train nothing
+        raise RuntimeError("aps_b200 fused Si-SNR / SNR / PIT objectives are inference-only (no autograd graph): the "
+                           "separated signals require grad; evaluate under torch.no_grad() or use the reference task "
+                           "for training")
     est = [_rows(x) for x in est]
     ref = [_rows(_check_dev(s, dev)) for s in ref]
     N, S = est[0].shape

@@ -375,6 +375,27 @@ class CmvnTransform(_Layer):
         return (f"norm_mean={self.norm_mean}, norm_var={self.norm_var}, per_band={self.per_band}, "
                 f"gcmvn_stats={self.gcmvn}, eps={self.eps:.3e}")
 
+    def global_stats(self, dev: th.device, dim: int):
+        """(gmean, gstd) as the kernel reads them: float32, contiguous, on `dev`, `dim` values each.  Statistics loaded
+        with `th.load` keep their saved dtype (the reference works in float64 through type promotion, asr.py:576-585),
+        so a converted copy is cached and rebuilt when the parameters change; a length that does not match the
+        feature dimension raises the reference's broadcast error instead of reading out of bounds."""
+        key = (self.gmean._version, self.gstd._version, self.gmean.data_ptr(), self.gstd.data_ptr(), str(dev))
+        hit = getattr(self, "_gstats", None)
+        if hit is None or hit[0] != key:
+            for name, t in (("gmean", self.gmean), ("gstd", self.gstd)):
+                if t.device != dev:
+                    raise RuntimeError(f"cmvn {name} lives on {t.device}, input on {dev}: move the module first")
+            m = self.gmean.detach().reshape(-1).to(th.float32).contiguous()
+            v = self.gstd.detach().reshape(-1).to(th.float32).contiguous()
+            hit = self._gstats = (key, m, v)
+        _, m, v = hit
+        for name, t in (("gmean", m), ("gstd", v)):
+            if t.numel() != dim:
+                raise RuntimeError(f"The size of tensor a ({dim}) must match the size of tensor b ({t.numel()}) at "
+                                   f"non-singleton dimension 2 (cmvn {name})")
+        return m, v
+
     def dim_scale(self) -> int:
         return 1
 
@@ -517,8 +538,9 @@ class DeltaTransform(_Layer):
 
 # ------------------------------------------------------------------------------------ fused execution
 def _feat_desc(power: float, mel: Optional[MelTransform], log: Optional[LogTransform],
-               cmvn: Optional[CmvnTransform], dev: th.device):
-    """Build the `aps_b200_feat_desc` for a [Power][Mel][Log][Cmvn] tail; returns (desc, allband_cmvn)."""
+               cmvn: Optional[CmvnTransform], dev: th.device, feat_dim: int):
+    """Build the `aps_b200_feat_desc` for a [Power][Mel][Log][Cmvn] tail; returns (desc, allband_cmvn).
+    `feat_dim`: width of the feature rows the tail produces (num_mels, or the number of STFT bins)."""
     d = _lib.FeatDesc()
     d.power = int(power)
     keep = []
@@ -537,7 +559,9 @@ def _feat_desc(power: float, mel: Optional[MelTransform], log: Optional[LogTrans
         d.norm_mean, d.norm_var, d.cmvn_eps = int(cmvn.norm_mean), int(cmvn.norm_var), float(cmvn.eps)
         if cmvn.gmean is not None:
             d.cmvn_mode = 2
-            d.gmean, d.gstd = cmvn.gmean.data_ptr(), cmvn.gstd.data_ptr()
+            gm, gs = cmvn.global_stats(dev, feat_dim)
+            d.gmean, d.gstd = gm.data_ptr(), gs.data_ptr()
+            keep += [gm, gs]
         elif cmvn.per_band:
             d.cmvn_mode = 1
         else:
@@ -592,14 +616,14 @@ def fused_wave_features(spec: SpectrogramTransform, wav: th.Tensor, tail, rescal
     if x.stride(-1) != 1:
         x = x.contiguous()
     sd = spec.stft_desc(dev, rescale=rescale, utt_preemph=utt_preemph)
-    fd, allband = _feat_desc(power, mel, log, cmvn, dev)
+    D = mel.num_mels if mel is not None else spec.num_bins
+    fd, allband = _feat_desc(power, mel, log, cmvn, dev, D)
     if nan_count is not None and allband is None:
         fd.nan_count = nan_count.data_ptr()
     lib = _lib.load()
     T = lib.aps_b200_num_frames(S, sd.frame_width, sd.hop, sd.center_pad)
     if T < 1:
         raise RuntimeError(f"STFT: {S} samples are too few for one frame of {sd.frame_width}")
-    D = mel.num_mels if mel is not None else spec.num_bins
     out = th.empty((rows, T, D), dtype=th.float32, device=dev)
     with th.cuda.device(dev):
         _lib.check(lib.aps_b200_feats_fwd(x.data_ptr(), rows, S, x.stride(0), sd, fd, out.data_ptr(),
@@ -627,8 +651,10 @@ def fused_spec_features(packed: th.Tensor, ref_channel: int, tail, extra_cols: i
         ref = ref_channel
     else:
         raise RuntimeError(f"expect a packed STFT N x (C) x F x T x 2, got {x.dim()}D")
-    fd, allband = _feat_desc(power, mel, log, cmvn, dev)
     D = mel.num_mels if mel is not None else F
+    if mel is not None and mel.filters.shape[-1] != F:
+        raise RuntimeError(f"mel filters expect {mel.filters.shape[-1]} bins, the packed STFT has {F}")
+    fd, allband = _feat_desc(power, mel, log, cmvn, dev, D)
     out = th.empty((N, T, D + extra_cols), dtype=th.float32, device=dev)
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_spec_feats_fwd(x.data_ptr(), N, C, ref, F, T, mag_eps, fd, out.data_ptr(),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define APS_B200_ABI_VERSION 4
+#define APS_B200_ABI_VERSION 5
 
 /* library / device ------------------------------------------------------------------------ */
 int aps_b200_abi_version(void);
@@ -219,6 +219,22 @@ int aps_b200_linear_tc_fwd(const float* x, int64_t rows, int64_t in_features, in
                            const float* weight_hi, const float* weight_lo, int64_t ld_w,
                            int64_t out_features, const aps_b200_epilogue* epi, float* out,
                            int64_t ld_out, void* stream);
+/* Encoder-stack variant of aps_b200_linear_tc_fwd (same reference call sites).  The tensor core reads an fp32 operand
+ * as TF32 by dropping the low 13 mantissa bits, so an activation x can be fed RAW as its own "hi" part when its
+ * companion  x_lo = rn_tf32(x - trunc_tf32(x))  exists: with x_lo != NULL both operand sides are loaded by TMA and the
+ * kernel runs without gather / split warps.  out_lo != NULL makes the epilogue write the companion of the result for
+ * the next layer (same leading dimension as out).  ksplit > 1 (needs x_lo) cuts K into slices whose RAW partial sums go
+ * to out + s * split_stride (epilogue must be empty); aps_b200_layernorm2_fwd reduces them.                         */
+int aps_b200_linear_tc2_fwd(const float* x, const float* x_lo, int64_t rows, int64_t in_features, int64_t ld_x,
+                            const float* weight_hi, const float* weight_lo, int64_t ld_w,
+                            int64_t out_features, const aps_b200_epilogue* epi, float* out, float* out_lo,
+                            int64_t ld_out, int32_t ksplit, int64_t split_stride, void* stream);
+/* aps_b200_conv2d_nhwc_tc_fwd that also writes the lo companion of its output */
+int aps_b200_conv2d_nhwc_tc2_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
+                                 int64_t in_channels, const float* weight_hi, const float* weight_lo,
+                                 int64_t out_channels, int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                 int pad_h, int pad_w, int dil_h, int dil_w, const aps_b200_epilogue* epi,
+                                 float* out, float* out_lo, void* stream);
 /* Conv2d as an implicit GEMM (same geometry / layouts as aps_b200_conv2d_nhwc_fwd; weight_hi / weight_lo are
  * the split [Cout, KH*KW*Cin] filter): aps/asr/base/component.py:251-307, aps/sse/enh/dcunet.py:24-45      */
 int aps_b200_conv2d_nhwc_tc_fwd(const float* x, int64_t batch, int64_t height, int64_t width,
@@ -278,6 +294,16 @@ int aps_b200_layernorm_fwd(const float* x, int64_t ld_x, const float* residual, 
                            float alpha, const float* gamma, const float* beta, float eps,
                            int64_t rows, int64_t dim, float* out, int64_t ld_out, void* stream);
 
+/* LayerNorm that also finishes a split-K tensor-core GEMM (aps_b200_linear_tc2_fwd, ksplit = num_parts):
+ *   v = alpha * (sum_p x[p * part_stride + ...] + bias) + residual;  out = normalize ? LN(v) * gamma + beta : v
+ * and, when out_lo != NULL, the TF32 lo companion of out.  dim % 128 == 0, dim <= 1024, 16-byte aligned operands.
+ * Same reference lines as aps_b200_layernorm_fwd plus the second Linear of the feed-forward modules
+ * (aps/asr/transformer/impl.py:388-393, :499-541).                                                       */
+int aps_b200_layernorm2_fwd(const float* x, int64_t ld_x, int32_t num_parts, int64_t part_stride,
+                            const float* bias, const float* residual, int64_t ld_residual, float alpha,
+                            const float* gamma, const float* beta, float eps, int32_t normalize,
+                            int64_t rows, int64_t dim, float* out, float* out_lo, int64_t ld_out, void* stream);
+
 /* Depthwise 1-D convolution over time: out[n, t, d] = epi(bias[d] + sum_k w[k, d] * x[n, t - left_pad
  * + k*dilation, d]) (zeros outside [0, T)); `weight_kd` is [kernel, channels] (tap-major).
  * Replaces the grouped nn.Conv1d (+ eval BatchNorm1d folded by the caller + activation) of
@@ -287,6 +313,12 @@ int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t n
                           const float* weight_kd, const float* bias, int kernel, int dilation,
                           int left_pad, const aps_b200_epilogue* epi, float* out, int64_t ld_out,
                           void* stream);
+/* ... and the TF32 lo companion of the output (channels % 4 == 0, 16-byte aligned rows) */
+int aps_b200_dwconv1d2_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames,
+                           int64_t channels, int64_t stride_n, int64_t stride_t,
+                           const float* weight_kd, const float* bias, int kernel, int dilation,
+                           int left_pad, const aps_b200_epilogue* epi, float* out, float* out_lo,
+                           int64_t ld_out, void* stream);
 
 /* Multi-head self-attention, softmax((q.k + pos_term) * scale [masked]) . v per (batch, head).
  * mode 0: no position term (aps/asr/transformer/impl.py:120-131 / torch MHA);
@@ -310,6 +342,8 @@ typedef struct aps_b200_attn_desc {
     float scale;
 } aps_b200_attn_desc;
 int aps_b200_mhsa_fwd(const aps_b200_attn_desc* desc, float* out, int64_t ld_out, void* stream);
+/* ... and the TF32 lo companion of the context rows */
+int aps_b200_mhsa2_fwd(const aps_b200_attn_desc* desc, float* out, float* out_lo, int64_t ld_out, void* stream);
 
 /* Per-utterance normalisation over time of token rows, row(n, t) = n*stride_n + t*stride_t:
  * per_channel = 0: statistics over (channels, frames) of each utterance — nn.GroupNorm(1, C), i.e. "cLN"

@@ -322,3 +322,76 @@ def test_c4_conformer_full_size_subset_vs_oracle(engine, monkeypatch):
     assert rel_err(y[rows], o) < FLOAT_TOL
     alone, _ = dev_net(x[rows].to(DEV), lens[rows].to(DEV))
     assert th.equal(alone, y[rows])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bn", ["", "64", "128", "256"])
+def test_tensor_core_tma_fed_linear_and_lo_companion(monkeypatch, bn):
+    """MODE 3 of the GEMM engine: the activation is fed RAW (the tensor core truncates it to TF32) next to its lo
+    companion, both by TMA.  Error against fp64 stays at the fp32 level; the companion a kernel writes is bit-identical
+    to ops.lo_companion of its output."""
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    monkeypatch.setenv("APS_B200_TC_BN", bn)
+    th.manual_seed(3)
+    for (M, K, N) in ((128, 32, 64), (3200, 256, 2048), (3200, 2048, 256), (333, 96, 200), (700, 2304, 256), (3200, 256, 768)):
+        x, w, b = th.randn(M, K, device=DEV), th.randn(N, K, device=DEV) / K**0.5, th.randn(N, device=DEV)
+        r = th.randn(M, N, device=DEV)
+        xl = ops.lo_companion(x)
+        hi = (x.view(th.int32) & -8192).view(th.float32)
+        assert float((hi.double() + xl.double() - x.double()).abs().max() / x.abs().max()) < 2.0**-20
+        ref = x.double() @ w.double().t() + b.double()
+        y, yl = ops.linear(x, w, b, x_lo=xl, want_lo=True)
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) < 3e-5, (M, K, N)
+        assert th.equal(yl, ops.lo_companion(y))
+        y2 = ops.linear(x, w, b, act="swish", alpha=0.5, residual=r, x_lo=xl)
+        ref2 = 0.5 * ref * th.sigmoid(ref) + r.double()
+        assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) < 3e-5, (M, K, N)
+        if N % 2 == 0:
+            y3 = ops.linear(x, w, b, act="glu", x_lo=xl)
+            ref3 = ref[:, 0::2] * th.sigmoid(ref[:, 1::2])
+            assert float((y3.double() - ref3).abs().max() / ref3.abs().max()) < 3e-5, (M, K, N)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ksplit", [2, 5, 8])
+def test_split_k_linear_reduced_by_layernorm2(monkeypatch, ksplit):
+    """Skinny GEMM (d_ff -> d_model) cut into K slices whose raw partial sums are reduced by the LayerNorm kernel:
+    LN(alpha * (x @ W.T + b) + res) against fp64; rows are bit-identical whatever the batch (slices depend on K only)."""
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    th.manual_seed(4)
+    for (M, K, N) in ((3200, 2048, 256), (3200, 2560, 256), (200, 1024, 128)):
+        x, w, b = th.randn(M, K, device=DEV), th.randn(N, K, device=DEV) / K**0.5, th.randn(N, device=DEV)
+        r, g, be = th.randn(M, N, device=DEV), th.rand(N, device=DEV) + 0.5, th.randn(N, device=DEV)
+        xl = ops.lo_companion(x)
+        parts = ops.linear(x, w, None, x_lo=xl, ksplit=ksplit)
+        assert parts.shape == (ksplit, M, N)
+        v = 0.5 * (x.double() @ w.double().t() + b.double()) + r.double()
+        y, yl = ops.layernorm2(parts, g, be, 1e-5, bias=b, residual=r, alpha=0.5)
+        ref = th.nn.functional.layer_norm(v, (N,), g.double(), be.double(), 1e-5)
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) < 3e-5, (M, K, N)
+        assert th.equal(yl, ops.lo_companion(y))
+        y0, _ = ops.layernorm2(parts, None, None, 0.0, bias=b, residual=r, alpha=0.5, normalize=False)
+        assert float((y0.double() - v).abs().max() / v.abs().max()) < 3e-5
+        # a sub-batch gives bit-identical rows
+        sub = ops.linear(x[:128].contiguous(), w, None, x_lo=xl[:128].contiguous(), ksplit=ksplit)
+        assert th.equal(sub, parts[:, :128])
+
+
+@pytest.mark.gpu
+def test_lo_companions_of_attention_and_depthwise_conv():
+    from aps_b200 import ops
+    th.manual_seed(5)
+    N, L, H, E = 4, 50, 4, 256
+    qkv = th.randn(N * L, 3 * E, device=DEV)
+    pos = th.randn(2 * L - 1, E // H, device=DEV)
+    ctx, lo = ops.mhsa(qkv, N, L, H, mode=1, pos=pos, kpm_fill=-3.4e38, want_lo=True)
+    assert th.equal(ctx, ops.mhsa(qkv, N, L, H, mode=1, pos=pos, kpm_fill=-3.4e38)) and th.equal(lo, ops.lo_companion(ctx))
+    x = th.randn(N * L, E, device=DEV)
+    w, b = th.randn(15, E, device=DEV), th.randn(E, device=DEV)
+    c, cl = ops.dwconv1d(x, N, L, w, b, left_pad=7, act="swish", want_lo=True)
+    assert th.equal(c, ops.dwconv1d(x, N, L, w, b, left_pad=7, act="swish")) and th.equal(cl, ops.lo_companion(c))
+    y, yl = ops.conv2d_nhwc(th.randn(2, 20, 12, 32, device=DEV), th.randn(64, 3, 3, 32, device=DEV) / 17, None, stride=(2, 2),
+                            padding=(1, 1), act="relu", want_lo=True)
+    assert yl is not None and th.equal(yl, ops.lo_companion(y))

@@ -112,3 +112,60 @@ def test_layer_forwards_equal_reference_on_cpu():
     assert th.equal(a.src_sr, r.src_sr) and th.equal(a.dst_sr, r.dst_sr)
     for cm in (dict(), dict(per_band=False), dict(norm_mean=False)):
         assert rel_err(A.CmvnTransform(**cm)(x), R.CmvnTransform(**cm)(x)) < 1e-6
+
+
+def test_pack_guard_detects_in_place_updates():
+    """derived weight copies (BN folding, TF32 splits, CUDA graphs) must be rebuilt after in-place parameter
+    updates, not only after a top-level load_state_dict: the guard sees EMA-style updates, copy_ and a sub-module
+    load_state_dict (all bump the version counter)."""
+    import copy
+    import time
+
+    from aps_b200 import ops
+    from aps_b200.asr.transformer import TransformerEncoder
+    cfg = dict(arch="cfmr", input_size=80, num_layers=2, proj="conv2d", proj_kwargs=dict(conv_channels=32, num_layers=2),
+               pose="rel", pose_kwargs=dict(lradius=8, rradius=8),
+               arch_kwargs=dict(att_dim=64, nhead=4, feedforward_dim=128, kernel_size=7, pre_norm=False))
+    net = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+    g = net._guard
+    assert g.stale()                     # nothing built yet
+    g.mark()
+    assert not g.stale()
+    with th.no_grad():
+        net.encoder.layers[0].norm_ffn1.weight.mul_(0.999).add_(0.001)          # EMA-style update
+    assert g.stale()
+    g.mark()
+    with th.no_grad():
+        net.proj.conv.enc_layers[0].norm.norm.running_mean.copy_(th.ones(32))     # buffer update
+    assert g.stale()
+    g.mark()
+    net.proj.load_state_dict(copy.deepcopy(net.proj.state_dict()))                # sub-module load
+    assert g.stale()
+    net._drop_packs()
+    assert g.stale() and net._packs is None
+    g.mark()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        g.stale()
+    assert (time.perf_counter() - t0) / 100 < 2e-3      # cheap enough to run on every forward
+
+
+def test_global_cmvn_stats_are_validated_before_the_kernel_sees_them():
+    """ADVICE r1: gcmvn statistics keep their saved dtype (float64 from `th.load`) and may not match the feature width;
+    the kernel must get a float32 copy of the right length or the reference's broadcast error — never a raw pointer."""
+    import torch.nn as nn
+
+    from aps_b200.transform.asr import CmvnTransform
+    c = CmvnTransform(gcmvn="/nonexistent/cmvn.pt", dim=8)
+    c.gmean = nn.Parameter(th.arange(8, dtype=th.float64), requires_grad=False)
+    c.gstd = nn.Parameter(th.full((8,), 2.0, dtype=th.float64), requires_grad=False)
+    dev = th.device("cpu")
+    m, s = c.global_stats(dev, 8)
+    assert m.dtype == th.float32 and s.dtype == th.float32 and m.is_contiguous()
+    assert th.equal(m, th.arange(8, dtype=th.float32)) and th.equal(s, th.full((8,), 2.0))
+    assert c.global_stats(dev, 8)[0] is m                       # cached
+    with th.no_grad():
+        c.gmean.add_(1.0)
+    assert th.equal(c.global_stats(dev, 8)[0], th.arange(1, 9, dtype=th.float32))   # rebuilt after an in-place update
+    with pytest.raises(RuntimeError, match="must match the size"):
+        c.global_stats(dev, 80)
