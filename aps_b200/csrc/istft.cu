@@ -31,7 +31,7 @@ struct IstftParams {
     float eps;
     const float* window;  // [width]
     const float2* tables; // inverse tables
-    int TC, halo, chunks_per_row;
+    int TC, halo, chunks_per_row, nf_log2;
     long long total_chunks;
 };
 
@@ -83,6 +83,14 @@ __global__ void __launch_bounds__(kIThreads) istft_kernel(const __grid_constant_
         sm_ptw[i] = make_float2(p.scale * t.x, p.scale * t.y);
     }
 
+    // Round-2 structure (ncu r02a: 195 us, long-scoreboard 3.3 / issue, 25 % warps active): the frame count of a chunk
+    // (NF = TC + halo) is a POWER OF TWO and a multiple of the lane groups, so (a) the tile index splits with shifts
+    // instead of an emulated division per element and a bin's NF frames are one aligned-size run, (b) the inverse
+    // FFTs take exactly NF / NGROUPS full passes (TC = 16 + 1 halo frame used to cost a second pass for one frame),
+    // (c) eight independent 8-byte loads per thread are in flight before the first is consumed, and (d) the overlap-add
+    // indexes samples relative to the chunk in 32-bit arithmetic (the 64-bit divisions per output sample are gone).
+    const int lg = p.nf_log2;
+    const unsigned total = (unsigned)(NC + 1) << lg;
     for (long long chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         const long long row = chunk / p.chunks_per_row;
         const int c = (int)(chunk - row * p.chunks_per_row);
@@ -99,26 +107,36 @@ __global__ void __launch_bounds__(kIThreads) istft_kernel(const __grid_constant_
         __syncthreads();
         // ---- load the [bin][frame] tile -----------------------------------------------------------
         const float2* sp = reinterpret_cast<const float2*>(p.spec) + row * (long long)(NC + 1) * p.T;
-        for (int idx = tid; idx < (NC + 1) * nfr; idx += kIThreads) {
-            const int k = idx / nfr, f = idx - k * nfr;
-            const int t = f0 + f;
-            float2 X = make_float2(0.f, 0.f);
-            if (t >= 0) {
-                X = __ldg(sp + (long long)k * p.T + t);
+        for (unsigned base = tid; base < total; base += kIThreads * 8) {
+            float2 X[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned idx = base + u * kIThreads;
+                const int k = (int)(idx >> lg), f = (int)(idx & ((1u << lg) - 1u));
+                const int t = f0 + f;
+                X[u] = (idx < total && t >= 0 && t < f_hi) ? __ldg(sp + (unsigned)k * (unsigned)p.T + (unsigned)t)
+                                                           : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned idx = base + u * kIThreads;
+                if (idx >= total) break;
+                const int k = (int)(idx >> lg), f = (int)(idx & ((1u << lg) - 1u));
+                float2 v = X[u];
                 if (p.polar) {
                     float sn, cs;
-                    sincosf(X.y, &sn, &cs);
-                    X = make_float2(X.x * cs, X.x * sn);
+                    sincosf(v.y, &sn, &cs);
+                    v = make_float2(v.x * cs, v.x * sn);
                 }
-                if (k == 0 || k == NC) X.y = 0.f;  // a C2R transform ignores Im of DC / Nyquist
+                if (k == 0 || k == NC) v.y = 0.f;      // a C2R transform ignores Im of DC / Nyquist
+                sm_tile[k * ts + f] = v;
             }
-            sm_tile[k * ts + f] = X;
         }
         __syncthreads();
 
-        // ---- inverse transform of every frame ------------------------------------------------------
-        const int nfr_round = (nfr + NGROUPS - 1) / NGROUPS * NGROUPS;
-        for (int f = group; f < nfr_round; f += NGROUPS) {
+        // ---- inverse transform of every frame (NF is a multiple of NGROUPS) ------------------------
+        for (int f = group; f < NF; f += NGROUPS) {
+            if (f - group >= nfr) break;               // whole pass beyond the chunk's frames (warp-uniform)
             const int fe = min(f, nfr - 1);
             float2 v[16];
 #pragma unroll
@@ -144,18 +162,21 @@ __global__ void __launch_bounds__(kIThreads) istft_kernel(const __grid_constant_
 
         // ---- deterministic overlap-add + de-normalisation ------------------------------------------
         float* o = p.out + row * p.S_out;
-        for (long long s = s_beg + tid; s < s_end; s += kIThreads) {
-            const long long so = s - p.pad;
+        const int j_end = (int)(s_end - s_beg);
+        const int t_last = p.T - 1 - tb;               // last existing frame, relative to tb
+        for (int j = tid; j < j_end; j += kIThreads) {
+            const long long so = s_beg + j - p.pad;
             if (so < 0 || so >= p.S_out) continue;
-            // frames t with t*hop <= s < t*hop + width
-            int t_hi = (int)min((long long)(p.T - 1), s / p.hop);
-            long long lo = s - p.width + 1;
-            int t_lo = lo <= 0 ? 0 : (int)((lo + p.hop - 1) / p.hop);
+            // frames tr (relative to tb) with tr*hop <= j < tr*hop + width, clipped to the frames that exist
+            const int tr_hi = min(t_last, (int)((unsigned)j / (unsigned)p.hop));
+            const int lo = j - p.width + 1;
+            int tr_lo = lo <= 0 ? -(int)((unsigned)(-lo) / (unsigned)p.hop) : (int)(((unsigned)lo + (unsigned)p.hop - 1u) / (unsigned)p.hop);
+            tr_lo = max(tr_lo, -min(tb, p.halo));
             float acc = 0.f, den = 0.f;
-            for (int t = t_lo; t <= t_hi; ++t) {
-                const int n = (int)(s - (long long)t * p.hop);
+            for (int tr = tr_lo; tr <= tr_hi; ++tr) {
+                const int n = j - tr * p.hop;
                 const float w = sm_win[n];
-                acc += sm_fb[(t - f0) * fs + n];
+                acc += sm_fb[(tr + p.halo) * fs + n];
                 den = fmaf(w, w, den);
             }
             o[so] = acc / (den + p.eps);
@@ -168,12 +189,14 @@ static int launch_istft(IstftParams& p, cudaStream_t st) {
     auto kern = istft_kernel<NC>;
     constexpr int NGROUPS = kIThreads / FFTPlan<NC>::G;
     p.halo = (p.width - 1) / p.hop;
-    int TC = max(NGROUPS, 16);
-    ISmem L = make_ilayout<NC>(p.nfft, TC + p.halo);
-    while (L.total > 110 * 1024 && TC > 4) {
-        TC /= 2;
-        L = make_ilayout<NC>(p.nfft, TC + p.halo);
-    }
+    // frames per chunk: a power of two, a multiple of the lane groups, large enough to own at least one hop
+    int NF = NGROUPS < 16 ? 16 : NGROUPS;
+    while (NF - p.halo < 1 || (NF - p.halo) * 4 < NF) NF *= 2;          // keep the halo re-computation below 3/4
+    APSB_CHECK_ARG(NF <= 4096, "istft: hop %d is too small for a window of %d samples", p.hop, p.width);
+    int TC = NF - p.halo;
+    ISmem L = make_ilayout<NC>(p.nfft, NF);
+    p.nf_log2 = 0;
+    while ((1 << p.nf_log2) < NF) ++p.nf_log2;
     APSB_CHECK_ARG(L.total <= 227 * 1024, "istft: shared memory need %d B exceeds 227 KB (hop %d too small?)", L.total,
                    p.hop);
     p.TC = TC;

@@ -182,37 +182,17 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
     return v;
 }
 
-// 32 accumulator columns of one row (lane = row, the native TMEM layout): everything is 16-byte vector traffic on the
-// lane's own row — 8 LDG.128 of the residual (prefetched by the caller), 8 STG.128 — and the per-column vectors
-// (bias, post scale / shift, PReLU slope) come from the warp's shared-memory copy `cv` (staged while the main loop of
-// the tile was still running): [bias | scale | shift | slope], BN floats each, column index relative to the tile.
-template <int ACT, int BN>
-__device__ __forceinline__ void tc_epilogue_vec(const uint32_t (&r)[32], const float4 (&res)[8], const Epilogue& e,
-                                                const float* __restrict__ cv, int c0, int n0, int N, bool row_ok,
-                                                float* __restrict__ orow, float* __restrict__ olow) {
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-        const int n = n0 + 4 * q4;
-        if (n < N) {                                  // N % 4 == 0 on this path
-            const float4 b4 = *reinterpret_cast<const float4*>(cv + c0 + 4 * q4);
-            float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
-            if (e.post_scale) {
-                ps4 = *reinterpret_cast<const float4*>(cv + BN + c0 + 4 * q4);
-                pt4 = *reinterpret_cast<const float4*>(cv + 2 * BN + c0 + 4 * q4);
-            }
-            if (ACT == ACT_PRELU) sl4 = *reinterpret_cast<const float4*>(cv + 3 * BN + c0 + 4 * q4);
-            float4 o;
-            o.x = fmaf(e.beta, res[q4].x, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 0]) + b4.x, sl4.x), ps4.x, pt4.x) * e.alpha);
-            o.y = fmaf(e.beta, res[q4].y, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 1]) + b4.y, sl4.y), ps4.y, pt4.y) * e.alpha);
-            o.z = fmaf(e.beta, res[q4].z, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 2]) + b4.z, sl4.z), ps4.z, pt4.z) * e.alpha);
-            o.w = fmaf(e.beta, res[q4].w, fmaf(tc_act<ACT>(__uint_as_float(r[4 * q4 + 3]) + b4.w, sl4.w), ps4.w, pt4.w) * e.alpha);
-            if (row_ok) {
-                *reinterpret_cast<float4*>(orow + 4 * q4) = o;
-                if (olow) *reinterpret_cast<float4*>(olow + 4 * q4) = tf32_lo4(o);   // companion for a MODE 3 consumer
-            }
-        }
-    }
+// Epilogue arithmetic on 4 consecutive columns of one output row (after the shared-memory transpose, see the epilogue
+// warps): bias / activation / post affine / alpha / residual; the per-column vectors are the lane's own 4 columns.
+template <int ACT>
+__device__ __forceinline__ float4 tc_epilogue4(const float4& v, const float4& b4, const float4& ps4, const float4& pt4,
+                                               const float4& sl4, const float4& res, float alpha, float beta) {
+    float4 o;
+    o.x = fmaf(beta, res.x, fmaf(tc_act<ACT>(v.x + b4.x, sl4.x), ps4.x, pt4.x) * alpha);
+    o.y = fmaf(beta, res.y, fmaf(tc_act<ACT>(v.y + b4.y, sl4.y), ps4.y, pt4.y) * alpha);
+    o.z = fmaf(beta, res.z, fmaf(tc_act<ACT>(v.z + b4.z, sl4.z), ps4.z, pt4.z) * alpha);
+    o.w = fmaf(beta, res.w, fmaf(tc_act<ACT>(v.w + b4.w, sl4.w), ps4.w, pt4.w) * alpha);
+    return o;
 }
 
 // How the A operand is gathered (host-filled; see aps_b200_gemm_a_desc)
@@ -330,7 +310,7 @@ template <int BN> struct TcCfg {
     static constexpr int A_BYTES = TC_BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
+    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;      // per epilogue warp: a 32 x 32 block, rows padded to 36 floats
 #ifdef APSB_TC_TRACE
     static constexpr int TRACE_BYTES = 8 * 1024;
 #else
@@ -563,7 +543,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         // vector loads / stores on the lane's own row.  Fallback (e.g. N = 257 mask rows): the 32x32 block is transposed
         // through a padded shared tile so that lane = column and the scalar accesses are still 128-byte rows.
         const int q = warp & 3;
-        float* tile_s = epi_tiles + (warp - WARP_EPI0) * (32 * 33);
+        float* tile_s = epi_tiles + (warp - WARP_EPI0) * (32 * 36);
         const Epilogue& e = p.e;
         const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
@@ -588,34 +568,37 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             const bool row_ok = lane < rows;
 #endif
             const long long mrow = row_ok ? tc_out_row(p.a, (unsigned)(m0 + lane)) : 0;   // row of the output / residual matrices
-            // residual of the lane's row, one chunk ahead (vector path)
+            // Vector path: TMEM delivers lane = row.  Storing that way makes every STG.128 of a warp touch 32 different
+            // lines (32 LSU cycles per instruction — the epilogue, not the MMAs, bounded the K = 256 layers: r02b
+            // microbenchmark, +8 us for a second output).  The 32 x 32 block is therefore transposed through this warp's
+            // padded shared tile and lane (g = lane / 8, c = lane % 8) handles columns 4c..4c+3 of rows g, g+4, ..., g+28:
+            // a warp instruction reads / writes four full 128-byte row segments, the residual comes in coalesced, and a
+            // lane's bias / affine / slope columns are the same for all 8 rows (one 16-byte load per chunk).
+            const int er = lane >> 3, ec = (lane & 7) * 4;
+            int mr[8];                             // output row of (er + 4 i) (rows < 2^31), -1: beyond M
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                mr[i] = __shfl_sync(0xffffffffu, row_ok ? (int)mrow : -1, er + 4 * i);
             float4 res_nxt[8];
             auto fetch_res = [&](int ch, float4 (&dst)[8]) {
-                const int n0 = n_blk * BN + ch * 32;
-                const bool ok = p.epi_vec && e.res != nullptr && !glu && row_ok;
+                const int n = n_blk * BN + ch * 32 + ec;
+                const bool ok = p.epi_vec && e.res != nullptr && n < p.N;
+                const long long col = glu ? (n >> 1) : n;
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4)
-                    dst[q4] = (ok && n0 + 4 * q4 < p.N) ? __ldg(reinterpret_cast<const float4*>(e.res + mrow * e.ldres + n0) + q4)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            // Everything that does not depend on the accumulator happens BEFORE the wait, i.e. while the tile's main loop
-            // is still running: the first residual chunk is requested and the per-column vectors of the tile are staged
-            // into this warp's shared-memory area (the vector path does not use it as a transpose tile).
-            fetch_res(0, res_nxt);
-            if (p.epi_vec && !glu) {
-                __syncwarp();                      // the previous tile's reads of the staged vectors are done
-                for (int j = lane; j < BN; j += 32) {
-                    const int n = n_blk * BN + j;
-                    const bool ok = n < p.N;
-                    tile_s[j] = (e.bias && ok && !e.dbg_nobias) ? __ldg(e.bias + n) : 0.f;
-                    if (e.post_scale) {
-                        tile_s[BN + j] = ok ? __ldg(e.post_scale + n) : 1.f;
-                        tile_s[2 * BN + j] = ok ? __ldg(e.post_shift + n) : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && mr[i] >= 0) {
+                        if (glu) {
+                            const float2 t = __ldg(reinterpret_cast<const float2*>(e.res + (long long)mr[i] * e.ldres + col));
+                            dst[i].x = t.x; dst[i].y = t.y;
+                        } else {
+                            dst[i] = __ldg(reinterpret_cast<const float4*>(e.res + (long long)mr[i] * e.ldres + col));
+                        }
                     }
-                    if (e.act == ACT_PRELU) tile_s[3 * BN + j] = ok ? __ldg(e.slope + (long long)n * e.slope_stride) : 0.f;
                 }
-                __syncwarp();
-            }
+            };
+            // the first residual chunk is requested BEFORE the wait, i.e. while the tile's main loop is still running
+            fetch_res(0, res_nxt);
             if (lane == 0) tc_mbar_wait_parked(tmem_full + buf, (tcount >> 1) & 1);
             __syncwarp();
             tc_fence_after();
@@ -649,41 +632,51 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     if (threadIdx.x == 64) TC_TR(5);
                 }
                 if (p.epi_vec) {
-                    if (glu) {
-                        // columns (2j, 2j+1) of the lane's row -> output column j; 16 outputs = 4 vector stores
-                        float* orow = eout + mrow * e.ldo + (n0 >> 1);
+                    // ---- transpose: lane = row -> lane = (row group, 4 columns) ----
+                    __syncwarp();                  // the previous chunk's reads of the tile are done
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int n = n0 + 8 * q4;
-                            if (n < p.N) {         // N % 8 == 0 on this path
-                                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-                                if (e.bias) {
-                                    ba = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-                                    bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + 4));
-                                }
-                                auto gl = [&](uint32_t v, float bv, uint32_t g, float bg) {
-                                    return e.alpha * ((__uint_as_float(v) + bv) * (1.f / (1.f + __expf(-(__uint_as_float(g) + bg)))));
-                                };
-                                float4 o;
-                                o.x = gl(r[8 * q4 + 0], ba.x, r[8 * q4 + 1], ba.y);
-                                o.y = gl(r[8 * q4 + 2], ba.z, r[8 * q4 + 3], ba.w);
-                                o.z = gl(r[8 * q4 + 4], bb.x, r[8 * q4 + 5], bb.y);
-                                o.w = gl(r[8 * q4 + 6], bb.z, r[8 * q4 + 7], bb.w);
-                                if (row_ok) {
-                                    if (e.res) {
-                                        const float4 rv = __ldg(reinterpret_cast<const float4*>(e.res + mrow * e.ldres + (n0 >> 1)) + q4);
-                                        o.x = fmaf(e.beta, rv.x, o.x); o.y = fmaf(e.beta, rv.y, o.y);
-                                        o.z = fmaf(e.beta, rv.z, o.z); o.w = fmaf(e.beta, rv.w, o.w);
-                                    }
-                                    *reinterpret_cast<float4*>(orow + 4 * q4) = o;
-                                }
-                            }
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        *reinterpret_cast<uint4*>(tile_s + lane * 36 + 4 * j4) =
+                            make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                    __syncwarp();
+                    const int n = n0 + ec;
+                    const bool nok = n < p.N;      // N % 4 == 0 (N % 8 for GLU) on this path
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias && nok && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    if (glu) {
+                        // columns (2j, 2j+1) -> output column j: this lane's 4 columns give 2 outputs
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 v = *reinterpret_cast<const float4*>(tile_s + (er + 4 * i) * 36 + ec);
+                            float2 o;
+                            o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
+                            o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
+                            o.x = fmaf(e.beta, res_cur[i].x, o.x);
+                            o.y = fmaf(e.beta, res_cur[i].y, o.y);
+                            if (nok && mr[i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[i] * e.ldo + (n >> 1)) = o;
                         }
                     } else {
-                        float* orow = eout + mrow * e.ldo + n0;
-                        float* olow = e.out_lo ? e.out_lo + mrow * e.ldo + n0 : nullptr;
-#define TC_EPI_CASE(A) \
-    case A: tc_epilogue_vec<A, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow, olow); break;
+                        float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
+                        if (e.post_scale && nok) {
+                            ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                            pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                        }
+                        if (e.act == ACT_PRELU && nok) {
+                            if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                            else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+                        }
+#define TC_EPI_CASE(A)                                                                                                  \
+    case A:                                                                                                             \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                                                 \
+            const float4 v = *reinterpret_cast<const float4*>(tile_s + (er + 4 * i) * 36 + ec);                         \
+            const float4 o = tc_epilogue4<A>(v, b4, ps4, pt4, sl4, res_cur[i], e.alpha, e.beta);                        \
+            if (nok && mr[i] >= 0) {                                                                                    \
+                *reinterpret_cast<float4*>(eout + (long long)mr[i] * e.ldo + n) = o;                                               \
+                if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[i] * e.ldo + n) = tf32_lo4(o);                   \
+            }                                                                                                           \
+        }                                                                                                               \
+        break;
                         switch (e.act) {
                             TC_EPI_CASE(ACT_RELU)
                             TC_EPI_CASE(ACT_SWISH)
@@ -692,7 +685,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             TC_EPI_CASE(ACT_PRELU)
                             TC_EPI_CASE(ACT_LEAKY)
                             TC_EPI_CASE(ACT_GELU)
-                            default: tc_epilogue_vec<ACT_NONE, BN>(r, res_cur, e, tile_s, c0, n0, p.N, row_ok, orow, olow);
+                            default:
+                            TC_EPI_CASE(ACT_NONE)
                         }
 #undef TC_EPI_CASE
                     }

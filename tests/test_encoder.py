@@ -392,6 +392,6 @@ def test_lo_companions_of_attention_and_depthwise_conv():
     w, b = th.randn(15, E, device=DEV), th.randn(E, device=DEV)
     c, cl = ops.dwconv1d(x, N, L, w, b, left_pad=7, act="swish", want_lo=True)
     assert th.equal(c, ops.dwconv1d(x, N, L, w, b, left_pad=7, act="swish")) and th.equal(cl, ops.lo_companion(c))
-    y, yl = ops.conv2d_nhwc(th.randn(2, 20, 12, 32, device=DEV), th.randn(64, 3, 3, 32, device=DEV) / 17, None, stride=(2, 2),
-                            padding=(1, 1), act="relu", want_lo=True)
+    y, yl = ops.conv2d_nhwc(th.randn(4, 40, 24, 32, device=DEV), th.randn(64, 3, 3, 32, device=DEV) / 17, None, stride=(2, 2),
+                            padding=(1, 1), act="relu", want_lo=True)       # 960 output rows: tensor-core engine
     assert yl is not None and th.equal(yl, ops.lo_companion(y))
