@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace apsb {
 
@@ -25,6 +26,15 @@ int num_sms() {
         if (g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
+}
+
+bool pdl_enabled() {
+    static int state = -1;                 // read once: APS_B200_PDL=1 enables programmatic dependent launches
+    if (state < 0) {
+        const char* e = getenv("APS_B200_PDL");
+        state = (e && e[0] == '1') ? 1 : 0;
+    }
+    return state == 1;
 }
 
 }  // namespace apsb

@@ -40,4 +40,28 @@ inline LaunchCache& launch_cache(LaunchCache (&slots)[64]) {
     return slots[dev & 63];
 }
 
+// Programmatic dependent launch (PDL).  Kernels of the encoder stack call pdl_trigger() first thing — the NEXT kernel of the
+// stream (or graph) may then be scheduled as soon as SMs free up, instead of after this grid has drained — and pdl_wait()
+// before they touch anything a predecessor wrote or still reads: the launch latency, CTA start-up and (tensor-core GEMM)
+// mbarrier / TMEM / tensor-map set-up of kernel N+1 overlap the tail of kernel N.  Both instructions are no-ops for a
+// kernel launched without the attribute.  APS_B200_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace apsb

@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace apsb {
 
@@ -70,6 +71,8 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float eps, int do_norm, long long M, float* __restrict__ out,
                                                          float* __restrict__ out_lo, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (m >= M) return;
@@ -148,6 +151,8 @@ struct DwParams {
 // first version 6x slower than its HBM bound) and, when V == 4, 16-byte vector loads / stores.
 template <int V>
 __global__ void __launch_bounds__(256) dwconv1d_kernel(const __grid_constant__ DwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned groups = (unsigned)(p.D / V);                 // channel groups per row (D % V == 0)
     const unsigned rows_per_block = 256u / groups > 0 ? 256u / groups : 1u;
     const unsigned g = threadIdx.x % groups, rb = threadIdx.x / groups;
@@ -343,6 +348,210 @@ __global__ void __launch_bounds__(kAttnWarps * 32) mhsa_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-tiled attention (round 2).  ncu of mhsa_kernel at the BASELINE size (profiles/r02_ncu_enc_small.txt): LSU pipe
+// 63 %, 8.6 M shared-memory wavefronts — one LDS per FMA operand.  Here a CTA owns 64 queries of one (batch, head), walks
+// the keys in tiles of 64 with a streaming softmax, and every thread computes a 4 x 4 block of the 64 x 64 score tile from
+// 16-byte shared-memory reads (8 FMA per LDS instead of 0.5): query rows ty + 16a, key rows tx + 16b — for a fixed a / b the
+// rows read by the lanes of a quarter warp are consecutive, which is conflict free with 68-float rows.  The relative
+// position term q . R[j - i + L - 1] (the reference's pad / transpose skew, utils.py:14-39) needs rows
+// (tx - ty) + 16 (b - a) + 63 of the staged window of R: 7 distinct rows per thread.  P . V is tiled the same way
+// (queries ty + 16a, 4 head dims per thread).  Same arithmetic order per row whatever the batch.
+constexpr int kTQ = 64, kTK = 64;
+
+template <int DH>
+__global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int LD = DH + 4;              // floats per staged row: 16-byte aligned, conflict free for 8 consecutive rows
+    constexpr int C4 = DH / 4;
+    extern __shared__ float4 attn_smem4[];
+    float* sQ = reinterpret_cast<float*>(attn_smem4);
+    float* sK = sQ + kTQ * LD;
+    float* sV = sK + kTK * LD;
+    float* sR = sV + kTK * LD;              // kTQ + kTK rows (window of the position table), modes 1 / 2
+    float* sQp = sR + (p.mode ? (kTQ + kTK) * LD : 0);   // position query, mode 2 only (mode 1: the content query)
+    float* sS = sK;                         // the score / probability tile re-uses the key tile (rows of LD floats)
+    __shared__ float sMax[kTQ], sSum[kTQ], sCorr[kTQ];
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kTQ;
+    const int L = p.L;
+    // ---- queries of this CTA ----
+    for (int idx = tid; idx < kTQ * C4; idx += 256) {
+        const int r = idx / C4, c = (idx - r * C4) * 4;
+        const int ii = min(i0 + r, L - 1);
+        const long long row = (long long)n * p.sn + (long long)ii * p.st;
+        float4 qc = __ldg(reinterpret_cast<const float4*>(p.q + row * p.ldq + h * DH + c));
+        if (p.mode == 2) {
+            // reference xl path: content term uses (X + u), position term (X + v), X = the tensor passed as "query" to
+            // dot_att — which is VALUE in the reference (impl.py:369)
+            const float4 x = __ldg(reinterpret_cast<const float4*>(p.qpos + row * p.ldqp + h * DH + c));
+            const float4 u = __ldg(reinterpret_cast<const float4*>(p.rel_u + h * DH + c));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.rel_v + h * DH + c));
+            qc = make_float4(x.x + u.x, x.y + u.y, x.z + u.z, x.w + u.w);
+            *reinterpret_cast<float4*>(sQp + r * LD + c) = make_float4(x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w);
+        }
+        *reinterpret_cast<float4*>(sQ + r * LD + c) = qc;
+    }
+    if (tid < kTQ) { sMax[tid] = -INFINITY; sSum[tid] = 0.f; }
+    const float* sQq = p.mode == 2 ? sQp : sQ;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+
+    for (int j0 = 0; j0 < L; j0 += kTK) {
+        __syncthreads();                    // the previous tile's P . V is done with sV and sS
+        for (int idx = tid; idx < kTK * C4; idx += 256) {
+            const int r = idx / C4, c = (idx - r * C4) * 4;
+            const int jj = j0 + r;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (jj < L) {
+                const long long row = (long long)n * p.sn + (long long)jj * p.st;
+                kv = __ldg(reinterpret_cast<const float4*>(p.k + row * p.ldk + h * DH + c));
+                vv = __ldg(reinterpret_cast<const float4*>(p.v + row * p.ldv + h * DH + c));
+            }
+            *reinterpret_cast<float4*>(sK + r * LD + c) = kv;
+            *reinterpret_cast<float4*>(sV + r * LD + c) = vv;
+        }
+        if (p.mode) {
+            // window row w <-> table row x = j - i + L - 1 with w = (j - j0) - (i - i0) + kTQ - 1
+            const int x0 = j0 - i0 - (kTQ - 1) + L - 1;
+            for (int idx = tid; idx < (kTQ + kTK - 1) * C4; idx += 256) {
+                const int r = idx / C4, c = (idx - r * C4) * 4;
+                const int x = x0 + r;
+                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (x >= 0 && x < 2 * L - 1)
+                    pv = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)x * p.ldpos + (p.mode == 2 ? h * DH : 0) + c));
+                *reinterpret_cast<float4*>(sR + r * LD + c) = pv;
+            }
+        }
+        __syncthreads();
+        // ---- scores: s[a][b] = q[ty + 16a] . k[tx + 16b] (+ position term) ----
+        float s[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s[a][b] = 0.f;
+        const int wbase = tx - ty + (kTQ - 1) - 48;      // window row of (a, b): wbase + 16 (b - a + 3)
+#pragma unroll 2
+        for (int d = 0; d < DH; d += 4) {
+            float4 q4[4], k4[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) q4[a] = *reinterpret_cast<const float4*>(sQ + (ty + 16 * a) * LD + d);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) k4[b] = *reinterpret_cast<const float4*>(sK + (tx + 16 * b) * LD + d);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    s[a][b] = fmaf(q4[a].x, k4[b].x, fmaf(q4[a].y, k4[b].y, fmaf(q4[a].z, k4[b].z, fmaf(q4[a].w, k4[b].w, s[a][b]))));
+            if (p.mode) {
+                float4 r4[7];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    const int w = wbase + 16 * c;
+                    r4[c] = (w >= 0 && w < kTQ + kTK - 1) ? *reinterpret_cast<const float4*>(sR + w * LD + d)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (p.mode == 2) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) q4[a] = *reinterpret_cast<const float4*>(sQq + (ty + 16 * a) * LD + d);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float4 r = r4[b - a + 3];
+                        s[a][b] = fmaf(q4[a].x, r.x, fmaf(q4[a].y, r.y, fmaf(q4[a].z, r.z, fmaf(q4[a].w, r.w, s[a][b]))));
+                    }
+            }
+        }
+        __syncthreads();                    // every thread is done with the key tile: it becomes the score tile
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = i0 + ty + 16 * a;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = j0 + tx + 16 * b;
+                float v = -INFINITY;
+                if (i < L && j < L) {
+                    v = s[a][b] * p.scale;
+                    if (p.kpm && p.kpm[(long long)n * L + j]) v = p.kpm_fill;
+                    if (p.amask) v += __ldg(p.amask + (long long)i * L + j);
+                }
+                sS[(ty + 16 * a) * LD + tx + 16 * b] = v;
+            }
+        }
+        __syncthreads();
+        // ---- streaming softmax: warp w owns rows 8w .. 8w+7, lane = keys lane, lane + 32 ----
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = warp * 8 + rr;
+            const float v0 = sS[r * LD + lane], v1 = sS[r * LD + lane + 32];
+            float tmax = fmaxf(v0, v1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            const float mold = sMax[r];
+            const float mnew = fmaxf(mold, tmax);
+            const float p0 = (v0 == -INFINITY) ? 0.f : __expf(v0 - mnew);
+            const float p1 = (v1 == -INFINITY) ? 0.f : __expf(v1 - mnew);
+            float psum = p0 + p1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+            sS[r * LD + lane] = p0;
+            sS[r * LD + lane + 32] = p1;
+            if (lane == 0) {
+                const float corr = (mold == -INFINITY) ? 0.f : __expf(mold - mnew);
+                sCorr[r] = (mnew == -INFINITY) ? 1.f : corr;
+                if (mnew != -INFINITY) { sSum[r] = sSum[r] * corr + psum; sMax[r] = mnew; }
+            }
+        }
+        __syncthreads();
+        // ---- acc[a][c] += P[ty + 16a][:] . V[:][4tx + c] ----
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float corr = sCorr[ty + 16 * a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] *= corr;
+        }
+#pragma unroll 2
+        for (int j = 0; j < kTK; j += 4) {
+            float4 p4[4], v4[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) p4[a] = *reinterpret_cast<const float4*>(sS + (ty + 16 * a) * LD + j);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) v4[jj] = *reinterpret_cast<const float4*>(sV + (j + jj) * LD + 4 * tx);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                acc[a][0] = fmaf(p4[a].x, v4[0].x, fmaf(p4[a].y, v4[1].x, fmaf(p4[a].z, v4[2].x, fmaf(p4[a].w, v4[3].x, acc[a][0]))));
+                acc[a][1] = fmaf(p4[a].x, v4[0].y, fmaf(p4[a].y, v4[1].y, fmaf(p4[a].z, v4[2].y, fmaf(p4[a].w, v4[3].y, acc[a][1]))));
+                acc[a][2] = fmaf(p4[a].x, v4[0].z, fmaf(p4[a].y, v4[1].z, fmaf(p4[a].z, v4[2].z, fmaf(p4[a].w, v4[3].z, acc[a][2]))));
+                acc[a][3] = fmaf(p4[a].x, v4[0].w, fmaf(p4[a].y, v4[1].w, fmaf(p4[a].z, v4[2].w, fmaf(p4[a].w, v4[3].w, acc[a][3]))));
+            }
+        }
+    }
+    // ---- normalise and store (4 consecutive head dims per thread: 16-byte stores) ----
+    if (4 * tx < DH) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = i0 + ty + 16 * a;
+            if (i >= L) continue;
+            const float l = sSum[ty + 16 * a];
+            // a fully masked row (all -inf) gives NaN in the reference's softmax too
+            const float inv = 1.f / l;
+            float4 y = (l > 0.f) ? make_float4(acc[a][0] * inv, acc[a][1] * inv, acc[a][2] * inv, acc[a][3] * inv)
+                                 : make_float4(NAN, NAN, NAN, NAN);
+            const long long off = ((long long)n * p.sn + (long long)i * p.st) * p.ldo + h * DH + 4 * tx;
+            *reinterpret_cast<float4*>(p.out + off) = y;
+            if (p.out_lo)
+                *reinterpret_cast<float4*>(p.out_lo + off) =
+                    make_float4(ln_tf32_lo(y.x), ln_tf32_lo(y.y), ln_tf32_lo(y.z), ln_tf32_lo(y.w));
+        }
+    }
+}
+
 }  // namespace apsb
 
 using namespace apsb;
@@ -373,8 +582,9 @@ extern "C" int aps_b200_layernorm2_fwd(const float* x, int64_t ld_x, int32_t num
     cudaStream_t st = (cudaStream_t)stream;
 #define APSB_LN2(V)                                                                                                    \
     case V:                                                                                                            \
-        layernorm2_kernel<V><<<grid, 256, 0, st>>>(x, ld_x, num_parts, part_stride, bias, residual, ld_residual, alpha, \
-                                                   gamma, beta, eps, normalize, rows, out, out_lo, ld_out);           \
+        APSB_CUDA(launch_pdl(layernorm2_kernel<V>, dim3(grid), dim3(256), 0, st, x, (long long)ld_x, (int)num_parts,    \
+                             (long long)part_stride, bias, residual, (long long)ld_residual, alpha, gamma, beta, eps, \
+                             (int)normalize, (long long)rows, out, out_lo, (long long)ld_out));                       \
         break;
     switch ((int)(dim / 128)) {
         APSB_LN2(1) APSB_LN2(2) APSB_LN2(3) APSB_LN2(4) APSB_LN2(5) APSB_LN2(6) APSB_LN2(7) APSB_LN2(8)
@@ -411,8 +621,8 @@ static int dwconv1d_impl(const float* x, int64_t ld_x, int64_t batch, int64_t nu
     const long long groups = vec ? channels / 4 : channels;
     const long long rows_per_block = groups >= 256 ? 1 : 256 / groups;
     const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
-    if (vec) dwconv1d_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    else dwconv1d_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    if (vec) APSB_CUDA(launch_pdl(dwconv1d_kernel<4>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));
+    else APSB_CUDA(launch_pdl(dwconv1d_kernel<1>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p));
     APSB_LAUNCH_CHECK();
     return 0;
 }
@@ -448,8 +658,27 @@ static int mhsa_impl(const aps_b200_attn_desc* d, float* out, float* out_lo, int
     p.pos = d->pos; p.ldpos = d->ld_pos; p.rel_u = d->rel_u; p.rel_v = d->rel_v;
     p.kpm = d->key_padding_mask; p.kpm_fill = d->padding_fill; p.amask = d->attn_mask;
     p.scale = d->scale; p.out = out; p.out_lo = out_lo; p.ldo = ld_out;
-    dim3 grid((unsigned)((p.L + kAttnWarps - 1) / kAttnWarps), (unsigned)p.H, (unsigned)p.N);
     cudaStream_t st = (cudaStream_t)stream;
+    // register-tiled kernel: head dim 64, every operand row 16-byte aligned (APS_B200_MHSA=simple forces the other one)
+    const uintptr_t al = (uintptr_t)p.q | (uintptr_t)p.k | (uintptr_t)p.v | (uintptr_t)p.qpos | (uintptr_t)p.pos |
+                         (uintptr_t)p.rel_u | (uintptr_t)p.rel_v | (uintptr_t)out | (uintptr_t)out_lo;
+    const long long lds = p.ldq | p.ldk | p.ldv | p.ldqp | p.ldpos | p.ldo;
+    const char* force = getenv("APS_B200_MHSA");
+    if (p.dh == 64 && (al & 15) == 0 && (lds & 3) == 0 && !(force && force[0] == 's')) {
+        constexpr int LD = 64 + 4;
+        const int smem = (kTQ + 2 * kTK + (p.mode ? kTQ + kTK : 0) + (p.mode == 2 ? kTQ : 0)) * LD * 4;
+        static LaunchCache slots[64];
+        LaunchCache& lc = launch_cache(slots);
+        if (smem > lc.smem_set) {
+            APSB_CUDA(cudaFuncSetAttribute(mhsa_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            lc.smem_set = smem;
+        }
+        dim3 tg((unsigned)((p.L + kTQ - 1) / kTQ), (unsigned)p.H, (unsigned)p.N);
+        APSB_CUDA(launch_pdl(mhsa_tiled_kernel<64>, tg, dim3(256), (size_t)smem, st, p));
+        APSB_LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 grid((unsigned)((p.L + kAttnWarps - 1) / kAttnWarps), (unsigned)p.H, (unsigned)p.N);
     switch (p.dh) {
         case 32: mhsa_kernel<32><<<grid, kAttnWarps * 32, 0, st>>>(p); break;
         case 64: mhsa_kernel<64><<<grid, kAttnWarps * 32, 0, st>>>(p); break;

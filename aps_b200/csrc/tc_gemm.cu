@@ -344,6 +344,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
 #endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     // k-blocks are walked tap by tap (convolutions: a k-block never crosses a (kh, kw) tap since Cin % 32 == 0) so that
     // a transposed-convolution tile can skip the taps that are zero for its row class; a linear layer is one "tap"
     // Order inside a tile: kernel row kh (skippable), then channel block cb, then kw INNERMOST: the three kw taps of one
@@ -421,6 +422,9 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TR(9);
+    // PDL: everything above (mbarriers, TMEM allocation, tensor-map prefetch) may overlap the tail of the previous kernel;
+    // nothing below may start before that kernel has completed (activations, residuals, output buffers it still reads)
+    pdl_wait();
 
     if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
@@ -1120,7 +1124,8 @@ static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const C
                                        (C::SMEM + 1024) * 100 / (228 * 1024) + 1));
         attr = true;
     }
-    tc_gemm_kernel<BN, MODE><<<(unsigned)grid, TcRoles<BN, MODE>::THREADS, C::SMEM, st>>>(tB, tBl, tA, tAl, p);
+    APSB_CUDA(launch_pdl(tc_gemm_kernel<BN, MODE>, dim3((unsigned)grid), dim3(TcRoles<BN, MODE>::THREADS), C::SMEM, st, tB, tBl,
+                         tA, tAl, p));
     APSB_LAUNCH_CHECK();
     return 0;
 }

@@ -395,3 +395,36 @@ def test_lo_companions_of_attention_and_depthwise_conv():
     y, yl = ops.conv2d_nhwc(th.randn(4, 40, 24, 32, device=DEV), th.randn(64, 3, 3, 32, device=DEV) / 17, None, stride=(2, 2),
                             padding=(1, 1), act="relu", want_lo=True)       # 960 output rows: tensor-core engine
     assert yl is not None and th.equal(yl, ops.lo_companion(y))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [50, 64, 100, 131])
+def test_register_tiled_attention_matches_the_simple_kernel(monkeypatch, L):
+    """mhsa_tiled_kernel (head dim 64) against mhsa_kernel (one warp per query) for the three position modes, key padding
+    and additive masks, and against an fp64 torch evaluation of the abs mode."""
+    from aps_b200 import ops
+    th.manual_seed(6)
+    N, H, E = 3, 4, 256
+    qkv = th.randn(N * L, 3 * E, device=DEV)
+    lens = th.tensor([L, L - 7, max(1, L // 2)], device=DEV)
+    kpm = (th.arange(L, device=DEV)[None, :] >= lens[:, None]).to(th.uint8).contiguous()
+    amask = th.zeros(L, L, device=DEV).masked_fill(th.rand(L, L, device=DEV) < 0.1, float("-inf"))
+    amask.fill_diagonal_(0.0)
+    pos1 = th.randn(2 * L - 1, E // H, device=DEV)
+    pos2 = th.randn(2 * L - 1, E, device=DEV)
+    u, v = th.randn(H, E // H, device=DEV), th.randn(H, E // H, device=DEV)
+    cases = [dict(mode=0, kpm=kpm, kpm_fill=float("-inf")), dict(mode=0, attn_mask=amask, kpm_fill=float("-inf")),
+             dict(mode=1, pos=pos1, kpm=kpm, kpm_fill=-3.4028234663852886e38),
+             dict(mode=2, pos=pos2, rel_u=u, rel_v=v, kpm=kpm, kpm_fill=-3.4028234663852886e38, qpos_is_value=True, attn_mask=amask)]
+    for kw in cases:
+        monkeypatch.delenv("APS_B200_MHSA", raising=False)
+        fast = ops.mhsa(qkv, N, L, H, **kw)
+        monkeypatch.setenv("APS_B200_MHSA", "simple")
+        slow = ops.mhsa(qkv, N, L, H, **kw)
+        assert rel_err(fast, slow) < 2e-5, kw["mode"]
+    monkeypatch.delenv("APS_B200_MHSA", raising=False)
+    q, k, vv = [t.view(N, L, H, E // H).permute(0, 2, 1, 3).double() for t in qkv.view(N, L, 3, E).unbind(2)]
+    sc = q @ k.transpose(-1, -2) / (E // H)**0.5
+    sc = sc.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
+    ref = (th.softmax(sc, -1) @ vv).permute(0, 2, 1, 3).reshape(N * L, E)
+    assert rel_err(ops.mhsa(qkv, N, L, H, mode=0, kpm=kpm, kpm_fill=float("-inf")), ref) < 2e-5
