@@ -228,6 +228,10 @@ extern "C" int aps_b200_lstm_group_fwd(const float* const* xg, int64_t ld_xg, in
     cfg.numAttrs = 1;
     for (int64_t t = 0; t < num_frames; ++t) {
         p.step = (int)t;
+        // The kernel prefetches its input projections BEFORE griddepcontrol.wait: safe against the previous STEP (which
+        // does not write them), not against the GEMM that produces them — that kernel now triggers its dependents early
+        // (pdl_trigger in tc_gemm.cu), so the first step is launched without the attribute and starts after the GEMM.
+        cfg.numAttrs = t == 0 ? 0 : 1;
         APSB_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel, p));
     }
     return 0;

@@ -58,26 +58,22 @@ class SplitCache:
         self._items.clear()
 
 
-# bench.py's kernel leg: when set to a list, every tensor-core GEMM launch appends (kind, flops, start event, end event)
+# bench.py's kernel leg: when set to a list, every tensor-core GEMM launch appends (kind, flops, replay) where `replay()`
+# re-issues exactly the same C-ABI call (same buffers): bench.py captures all of them into one CUDA graph and times the
+# replay, i.e. the device time of the GEMM launches of one step without the other kernels and without host gaps.
 PROFILE = None
 
 
-class _Timed:
-    """CUDA events on the launching stream around one GEMM launch (only while ops.PROFILE is a list)."""
-
-    def __init__(self, kind: str, flops: float, dev):
-        self.kind, self.flops, self.dev = kind, flops, dev
-
-    def __enter__(self):
-        if PROFILE is not None:
-            self.e0, self.e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-            self.e0.record(th.cuda.current_stream(self.dev))
-
-    def __exit__(self, *exc):
-        if PROFILE is not None:
-            self.e1.record(th.cuda.current_stream(self.dev))
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
-        return False
+def _tc_call(kind: str, flops: float, dev, fn, *args, keep=()):
+    """Issue the C-ABI call `fn(*args)` on `dev`; remember it for bench.py when ops.PROFILE is a list (`keep`: the
+    tensors behind the raw pointers in `args`, held by the replay closure so the addresses stay valid)."""
+    with th.cuda.device(dev):
+        _lib.check(fn(*args))
+    if PROFILE is not None:
+        def replay(fn=fn, args=args, dev=dev, keep=keep):
+            with th.cuda.device(dev):
+                _lib.check(fn(*args[:-1], _lib.stream_ptr(dev)))      # the last argument is always the stream
+        PROFILE.append((kind, flops, replay))
 
 
 class PackGuard:
@@ -145,10 +141,9 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
         parts = th.empty((ksplit, M, N), dtype=th.float32, device=dev)
         w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
         e = _epilogue()
-        with th.cuda.device(dev), _Timed("linear", 2.0 * M * K * N, dev):
-            _lib.check(_lib.load().aps_b200_linear_tc2_fwd(x.data_ptr(), x_lo.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
-                                                           w_lo.data_ptr(), w_hi.stride(0), N, e, parts.data_ptr(), 0,
-                                                           N, ksplit, M * N, _lib.stream_ptr(dev)))
+        _tc_call("linear", 2.0 * M * K * N, dev, _lib.load().aps_b200_linear_tc2_fwd, x.data_ptr(), x_lo.data_ptr(), M, K,
+                 x.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e, parts.data_ptr(), 0, N, ksplit, M * N,
+                 _lib.stream_ptr(dev), keep=(x, x_lo, w_hi, w_lo, parts))
         return parts
     if out is None:
         out = th.empty((M, ncol), dtype=th.float32, device=dev)
@@ -156,16 +151,14 @@ def linear(x: th.Tensor, weight: th.Tensor, bias: Optional[th.Tensor] = None, ac
     if tc:
         w_hi, w_lo = cache.get(weight) if cache is not None else tf32_split(weight)
         lo = th.empty_like(out) if want_lo else None
-        with th.cuda.device(dev), _Timed("linear", 2.0 * M * K * N, dev):
-            if x_lo is None and lo is None:
-                _lib.check(_lib.load().aps_b200_linear_tc_fwd(x.data_ptr(), M, K, x.stride(0), w_hi.data_ptr(),
-                                                              w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(),
-                                                              out.stride(0), _lib.stream_ptr(dev)))
-            else:
-                _lib.check(_lib.load().aps_b200_linear_tc2_fwd(x.data_ptr(), _lib.ptr(x_lo), M, K, x.stride(0),
-                                                               w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e,
-                                                               out.data_ptr(), _lib.ptr(lo), out.stride(0), 1, 0,
-                                                               _lib.stream_ptr(dev)))
+        if x_lo is None and lo is None:
+            _tc_call("linear", 2.0 * M * K * N, dev, _lib.load().aps_b200_linear_tc_fwd, x.data_ptr(), M, K, x.stride(0),
+                     w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(), out.stride(0),
+                     _lib.stream_ptr(dev), keep=(x, w_hi, w_lo, out, bias, residual, slope, post))
+        else:
+            _tc_call("linear", 2.0 * M * K * N, dev, _lib.load().aps_b200_linear_tc2_fwd, x.data_ptr(), _lib.ptr(x_lo), M, K,
+                     x.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N, e, out.data_ptr(), _lib.ptr(lo),
+                     out.stride(0), 1, 0, _lib.stream_ptr(dev), keep=(x, x_lo, w_hi, w_lo, out, lo, bias, residual, slope, post))
         return (out, lo) if want_lo else out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_linear_fwd(x.data_ptr(), M, K, x.stride(0), weight.data_ptr(), weight.stride(0),
@@ -193,11 +186,9 @@ def conv2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1, 1), paddi
         w2 = weight.view(Cout, K)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
         lo = th.empty_like(out) if (want_lo and act != "glu" and Cout % 4 == 0) else None
-        with th.cuda.device(dev), _Timed("conv2d", 2.0 * M * K * Cout, dev):
-            _lib.check(_lib.load().aps_b200_conv2d_nhwc_tc2_fwd(x.data_ptr(), B, H, W, Cin, w_hi.data_ptr(),
-                                                                w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
-                                                                padding[0], padding[1], dilation[0], dilation[1], e,
-                                                                out.data_ptr(), _lib.ptr(lo), _lib.stream_ptr(dev)))
+        _tc_call("conv2d", 2.0 * M * K * Cout, dev, _lib.load().aps_b200_conv2d_nhwc_tc2_fwd, x.data_ptr(), B, H, W, Cin,
+                 w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1], padding[0], padding[1], dilation[0],
+                 dilation[1], e, out.data_ptr(), _lib.ptr(lo), _lib.stream_ptr(dev), keep=(x, w_hi, w_lo, out, lo, bias, slope))
         return (out, lo) if want_lo else out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv2d_nhwc_fwd(x.data_ptr(), B, H, W, Cin, weight.data_ptr(), Cout, KH, KW,
@@ -247,11 +238,13 @@ def conv_transpose2d_nhwc(x: th.Tensor, weight: th.Tensor, bias=None, stride=(1,
     if _tc_conv_ok(x, Cin, Cout, B * OH * OW) and stride[1] == 1:     # the engine's transposed gather needs stride_w == 1
         w2 = weight.view(Cout, KH * KW * Cin)
         w_hi, w_lo = cache.get(w2) if cache is not None else tf32_split(w2)
-        with th.cuda.device(dev):
-            _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_tc_fwd(
-                x.data_ptr(), _lib.ptr(fused_skip), B, H, W, Cin, w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW,
-                stride[0], stride[1], padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(),
-                _lib.stream_ptr(dev)))
+        # FLOPs actually executed: with stride 2 along H the class-major row order skips the taps that are identically
+        # zero for a tile (half of the reference's conv_transpose2d arithmetic)
+        flops = 2.0 * B * OH * OW * KH * KW * Cin * Cout / (stride[0] if stride[0] in (2, 3, 4) else 1)
+        _tc_call("conv_transpose2d", flops, dev, _lib.load().aps_b200_conv_transpose2d_nhwc_tc_fwd, x.data_ptr(),
+                 _lib.ptr(fused_skip), B, H, W, Cin, w_hi.data_ptr(), w_lo.data_ptr(), Cout, KH, KW, stride[0], stride[1],
+                 padding[0], padding[1], output_padding[0], output_padding[1], e, out.data_ptr(), _lib.stream_ptr(dev),
+                 keep=(x, fused_skip, w_hi, w_lo, out, bias))
         return out
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_conv_transpose2d_nhwc_fwd(

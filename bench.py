@@ -416,30 +416,43 @@ def _set_graphs(wl, flag):
 
 
 def kernel_leg(wl, step, batches, dev, peak_tf, peak_hbm, peak_src, ms_per_step):
-    """Roofline of the dominant kernel, measured live: one eager step (no CUDA graph) with every tensor-core GEMM launch
-    bracketed by CUDA events on the launching stream (ops.PROFILE).  Also returns the C-ABI launch calls per step."""
+    """Roofline of the dominant kernel, measured live.  One eager step (no CUDA graph) records every tensor-core GEMM
+    launch as a replayable C-ABI call (ops.PROFILE); the recorded calls alone — same buffers, same order — are then
+    captured into a CUDA graph and the replay is timed with CUDA events: the device time of all tc_gemm_kernel launches
+    of one step, free of host gaps (event pairs around eager launches of 10-30 us kernels measure the Python call).
+    Also returns the C-ABI launch calls per step."""
     from aps_b200 import _lib, ops
     _set_graphs(wl, False)
     with th.no_grad():
         step(*batches[0])
         th.cuda.synchronize(dev)
         c0 = _lib.CALLS
+        ops.PROFILE = []
         step(*batches[1 % len(batches)])
+        th.cuda.synchronize(dev)
+        recs, ops.PROFILE = ops.PROFILE, None
         calls = _lib.CALLS - c0
-        reps, recs = 3, []
-        for r in range(reps):
-            ops.PROFILE = []
-            step(*batches[r % len(batches)])
-            th.cuda.synchronize(dev)
-            recs.append(ops.PROFILE)
-            ops.PROFILE = None
     _set_graphs(wl, True)
     if wl.tensor_bound:
-        flops = sum(r[1] for r in recs[0])
-        ms = min(sum(r[2].elapsed_time(r[3]) for r in rec) for rec in recs)
-        n = len(recs[0])
+        n = len(recs)
         if not n:
             return None, calls
+        flops = sum(r[1] for r in recs)
+        for r in recs:                                   # warm (tensor maps, attributes) outside the capture
+            r[2]()
+        th.cuda.synchronize(dev)
+        graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(graph):
+            for r in recs:
+                r[2]()
+        ms = 1e30
+        for _ in range(6):
+            e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            e0.record(th.cuda.current_stream(dev))
+            graph.replay()
+            e1.record(th.cuda.current_stream(dev))
+            th.cuda.synchronize(dev)
+            ms = min(ms, e0.elapsed_time(e1))
         mma_tf = 3.0 * flops / (ms * 1e-3) / 1e12
         peak = peak_tf / 2.0
         return {"bound": "tensor", "achieved": mma_tf, "peak": peak, "unit": "TFLOP/s", "frac": mma_tf / peak,
@@ -447,8 +460,8 @@ def kernel_leg(wl, step, batches, dev, peak_tf, peak_hbm, peak_src, ms_per_step)
                 "kernel": f"tc_gemm_kernel<BN,MODE> (tcgen05.mma kind::tf32, 3 passes hi*hi + hi*lo + lo*hi): all {n} launches of one step",
                 "launches_per_step": n, "kernel_ms_per_step": ms, "share_of_step": ms / ms_per_step,
                 "algorithmic_flops_per_step": flops, "fp32_equivalent_tflops": flops / (ms * 1e-3) / 1e12,
-                "how": "achieved = 3 x algorithmic FLOPs (the TF32 MMA passes that fp32 parity needs) / summed event-timed launch "
-                       "durations of one eager step (includes ~2 us of launch gap per launch); peak = dense TF32 = bf16_tflops / 2",
+                "how": "achieved = 3 x algorithmic FLOPs (the TF32 MMA passes that fp32 parity needs) / device time of the step's "
+                       "GEMM launches replayed alone from a CUDA graph (CUDA events, best of 6); peak = dense TF32 = bf16_tflops / 2",
                 "peak_source": peak_src + " bf16_tflops (burst) / 2"}, calls
     nbytes = wl.hbm_bytes()
     ach = nbytes / (ms_per_step * 1e-3) / 1e9
