@@ -264,8 +264,9 @@ def _build_layers(arch: str, pose: str, num_layers: int, kw: Dict) -> LayerStack
     att_dropout, ffn_dropout = kw.pop("att_dropout", 0.1), kw.pop("ffn_dropout", 0.1)
     tie = kw.pop("tie", False) if pose == "xl" else False
     kw.pop("rel_u", None), kw.pop("rel_v", None)
-    pre_norm = kw.get("pre_norm", arch == "cfmr")
-    final_norm = nn.LayerNorm(att_dim) if pre_norm else None
+    # Reference quirk (impl.py:768): the final LayerNorm exists only when "pre_norm" is GIVEN and true — a conformer built
+    # without the key has pre-norm layers (their own default, impl.py:445) but no final norm.  Found by tests/test_dropin.py.
+    final_norm = nn.LayerNorm(att_dim) if kw.get("pre_norm", False) else None
     shared = (_relative_uv((nhead, att_dim // nhead)), _relative_uv((nhead, att_dim // nhead))) if tie else None
     layers = []
     for _ in range(num_layers):

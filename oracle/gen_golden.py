@@ -281,7 +281,43 @@ def reference_fixture_cases():
          pcm=w2, packed=packed[..., ::STEP, :], feats=feats[:, ::STEP])
 
 
+def ctc_cases():
+    """`asr@ctc` (CtcASR: AsrTransform -> conformer encoder with the CTC projection) through the reference's own
+    factories: the golden of tests/test_dropin.py (the `_training_prep` chain of aps/asr/ctc.py:113-134)."""
+    import copy
+    from aps.libs import aps_asr_nnet, aps_transform
+    tkw = dict(feats="fbank-log-cmvn", frame_len=400, frame_hop=160, window="hamm", pre_emphasis=0.97, num_mels=80)
+    nkw = dict(input_size=80, vocab_size=40, ctc=True, ead=False, enc_type="cfmr",
+               enc_kwargs=dict(arch_kwargs=dict(att_dim=128, nhead=2, feedforward_dim=1024, att_dropout=0.1, ffn_dropout=0.1,
+                                                kernel_size=15), num_layers=1, proj="conv2d",
+                               proj_kwargs=dict(conv_channels=32, num_layers=2), pose="rel",
+                               pose_kwargs=dict(lradius=64, rradius=64)))
+    g = th.Generator().manual_seed(900)
+    th.manual_seed(900)
+    net = aps_asr_nnet("asr@ctc")(asr_transform=aps_transform("asr")(**tkw), **copy.deepcopy(nkw)).eval()
+    with th.no_grad():
+        for name, buf in net.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.2 * th.randn(buf.shape, generator=g))
+            if name.endswith("running_var"):
+                buf.copy_(0.5 + th.rand(buf.shape, generator=g))
+        for name, prm in net.named_parameters():
+            if name.endswith("bias") or "norm" in name:
+                prm.add_(0.1 * th.randn(prm.shape, generator=g))
+    x = 0.1 * th.randn(6, 16000, generator=g)
+    lens = th.tensor([16000, 16000, 14000, 12000, 9000, 6000])
+    with th.no_grad():
+        enc_out, enc_ctc, enc_len = net(x.clone(), lens.clone())
+    arrays = dict(x=x, lens=lens, enc_out=enc_out, enc_len=enc_len)
+    # the transform's buffers (DFT kernel, window, mel filters) are rebuilt by its constructor: only the encoder is stored
+    arrays.update({"p." + k: v for k, v in net.encoder.state_dict().items()})
+    save("ctc_0", dict(transform=tkw, net=nkw), **arrays)
+
+
 def main():
+    if "--only-ctc" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return ctc_cases()
     if "--only-fixtures" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         return reference_fixture_cases()
