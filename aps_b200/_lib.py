@@ -32,7 +32,7 @@ class FeatDesc(Structure):
                 ("mel_weight", c_void_p), ("mel_stride", c_int32), ("log_mode", c_int32),
                 ("log_eps", c_float), ("log_lower_bound", c_float), ("cmvn_mode", c_int32),
                 ("norm_mean", c_int32), ("norm_var", c_int32), ("cmvn_eps", c_float), ("gmean", c_void_p),
-                ("gstd", c_void_p), ("nan_count", c_void_p)]
+                ("gstd", c_void_p), ("nan_count", c_void_p), ("aug_mask", c_void_p)]
 
 
 class Epilogue(Structure):
@@ -109,7 +109,7 @@ _SIGNATURES = {
                                         c_int64, c_void_p]),
     "aps_b200_dwconv1d2_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                        c_void_p, c_int, c_int, c_int, POINTER(Epilogue), c_void_p, c_void_p, c_int64,
-                                       c_void_p]),
+                                       c_void_p, c_void_p]),
     "aps_b200_mhsa2_fwd": (c_int, [POINTER(AttnDesc), c_void_p, c_void_p, c_int64, c_void_p]),
     "aps_b200_conv2d_nhwc_tc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Epilogue),
@@ -125,6 +125,14 @@ _SIGNATURES = {
                                                    POINTER(Epilogue), c_void_p, c_void_p]),
     "aps_b200_cmask_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_float, c_int,
                                    c_void_p, c_void_p]),
+    "aps_b200_specaug_workspace_bytes": (c_int64, [c_int64]),
+    "aps_b200_specaug_apply": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_int64,
+                                       c_void_p, c_void_p]),
+    "aps_b200_splice_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "aps_b200_delta_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_void_p]),
+    "aps_b200_speed_perturb_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "aps_b200_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_float,
                                        c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "aps_b200_dwconv1d_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,

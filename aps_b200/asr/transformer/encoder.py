@@ -325,6 +325,7 @@ class TransformerEncoder(nn.Module):
         self._graphs = {}
         self._guard = ops.PackGuard(self)
         self._fast = False
+        self._ragged_lens = None
         self.use_graphs = os.environ.get("APS_B200_GRAPHS", "1") != "0"
         self.register_load_state_dict_post_hook(lambda m, k: m._drop_packs())
 
@@ -448,8 +449,10 @@ class TransformerEncoder(nn.Module):
                 lens = blk.compute_outp_dim(lens, 0)
         return lens
 
-    def _front(self, x: th.Tensor, pk):
-        """-> (rows pair, N, T): token rows [N*T, D] after the projection front."""
+    def _front(self, x: th.Tensor, pk, in_lens: Optional[th.Tensor] = None):
+        """-> (rows pair, N, T): token rows [N*T, D] after the projection front.  `in_lens` (device int64 [N], ragged-exact
+        mode): frames beyond an utterance's length are zeroed before every convolution, i.e. each utterance sees the
+        zero padding it would see alone (aps/asr/ctc.py:58-84 runs utterances one by one for exactly this reason)."""
         if self.proj is None:
             N, T, _ = x.shape
             return (ops.rows2d(x), None), N, T
@@ -466,11 +469,23 @@ class TransformerEncoder(nn.Module):
         nhwc = x4.permute(0, 2, 3, 1).contiguous()
         lo = None
         nconv = len(pk["convs"])
+        lens = in_lens
+
+        def zero_tail(t, ln):                                       # [N, T, F, C]: frames >= ln[n] <- 0
+            keep = th.arange(t.shape[1], device=t.device)[None, :] < ln[:, None]
+            return t * keep[:, :, None, None].to(t.dtype)
+
+        if lens is not None:
+            nhwc = zero_tail(nhwc, lens)
         for i, ((w, b, stride, padding), blk) in enumerate(zip(pk["convs"], self.proj.conv.enc_layers)):
             last = i + 1 == nconv and "front_w" in pk and self._fast
             nhwc = ops.conv2d_nhwc(nhwc, w, b, stride=stride, padding=padding, act="relu", cache=self._splits, want_lo=last)
             if last:
                 nhwc, lo = nhwc
+            if lens is not None:
+                lens = blk.compute_outp_dim(lens, 0)
+                if i + 1 < nconv:                                   # the projection after the last layer is per token
+                    nhwc = zero_tail(nhwc, lens)
         N, T, Fq, C = nhwc.shape
         flat = nhwc.view(N * T, Fq * C)
         if "front_w" in pk:
@@ -516,7 +531,7 @@ class TransformerEncoder(nn.Module):
         g = self._lin2(up, d["pw1_w"], d["pw1_b"], act="glu")
         K = lay.kernel_size
         c = ops.dwconv1d(g, N, T, d["dw_w"], d["dw_b"], dilation=1, left_pad=(K - 1) if lay.padding else (K - 1) // 2,
-                         act=lay.activation, want_lo=self._fast)
+                         act=lay.activation, want_lo=self._fast, lens=self._ragged_lens)
         return self._lin2(c if self._fast else (c, None), d["pw2_w"], d["pw2_b"], residual=res)
 
     def _cfmr_layer(self, lay, d, xp, N, T, inj, kpm, amask):
@@ -540,10 +555,12 @@ class TransformerEncoder(nn.Module):
         return self._second(hp, lay.feedforward2[3], xp[0], mac, lay.norm_ffn2)
 
     # ---- forward --------------------------------------------------------------------------------------------
-    def _run(self, x: th.Tensor, lens_dev: Optional[th.Tensor]) -> th.Tensor:
-        """Device-only part of the forward (safe to capture in a CUDA graph): x N x Ti x F -> N x To x D."""
+    def _run(self, x: th.Tensor, lens_dev: Optional[th.Tensor], in_lens: Optional[th.Tensor] = None) -> th.Tensor:
+        """Device-only part of the forward (safe to capture in a CUDA graph): x N x Ti x F -> N x To x D.
+        `in_lens` (input frames per utterance, device): ragged-exact mode, see `forward_ragged`."""
         pk, dev = self._packs, x.device
-        xp, N, T = self._front(x, pk)
+        self._ragged_lens = lens_dev if in_lens is not None else None
+        xp, N, T = self._front(x, pk, in_lens)
         D = xp[0].shape[-1]
         kpm = None
         if lens_dev is not None:
@@ -606,11 +623,7 @@ class TransformerEncoder(nn.Module):
         graph.replay()
         return out.clone()
 
-    def forward(self, inp_pad: th.Tensor, inp_len: Optional[th.Tensor]):
-        """inp_pad N x Ti x F (or N x C x Ti x F), inp_len N or None -> (N x To x D, lengths)."""
-        if self.training:
-            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
-        dev = _lib.require_cuda(inp_pad, "encoder input")
+    def _ensure_packs(self, dev):
         if self._packs is None or self._packs["dev"] != dev or self._guard.stale():
             if next(self.parameters()).device != dev:
                 raise RuntimeError(f"encoder parameters on {next(self.parameters()).device}, input on {dev}")
@@ -620,6 +633,45 @@ class TransformerEncoder(nn.Module):
         # pair mode: tensor-core engine and a model width the fused LayerNorm / reduce kernel takes
         self._fast = (ops.GEMM_ENGINE == "tc" and ops.layernorm2_ok(self.att_dim)
                       and os.environ.get("APS_B200_ENC_PAIRS", "1") != "0")
+
+    def ragged_exact_ok(self) -> bool:
+        """Can a padded batch reproduce the one-utterance-at-a-time results?  Needs length-independent position terms
+        ("xl" indexes its sinusoid table by T) and per-token normalisation in the front (LinearProj "LN" = GroupNorm over
+        the utterance)."""
+        if self.pose_type == "xl":
+            return False
+        if isinstance(self.proj, LinearProj) and not isinstance(self.proj.norm.norm, nn.BatchNorm1d):
+            return False
+        return True
+
+    def forward_ragged(self, inp_pad: th.Tensor, inp_len: th.Tensor):
+        """Padded batch N x Ti x F with lengths -> (N x To x D with rows beyond each length zeroed, lengths), where every
+        utterance gets EXACTLY what `forward(inp_pad[n:n+1, :len[n]], None)` gives (up to the rounding of a different
+        GEMM tile path): besides the key-padding mask, frames beyond an utterance's length are zeroed in front of every
+        convolution (conv2d front, depthwise conv of the conformer layers) so that it sees the zero padding it would see
+        alone.  The reference gets this by looping over the utterances (aps/asr/ctc.py:58-84); `forward` itself keeps the
+        reference's batched semantics."""
+        if self.training:
+            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
+        if not self.ragged_exact_ok():
+            raise RuntimeError("forward_ragged: this encoder configuration depends on the padded length (pose 'xl' or an "
+                               "utterance-level norm in the projection); run the utterances one by one")
+        dev = _lib.require_cuda(inp_pad, "encoder input")
+        self._ensure_packs(dev)
+        out_len = self._front_lens(inp_len)
+        in_dev = inp_len.detach().to(device=dev, dtype=th.int64)
+        lens_dev = out_len.detach().to(device=dev, dtype=th.int64)
+        out = self._run(inp_pad.detach().float(), lens_dev, in_dev)
+        self._ragged_lens = None
+        keep = th.arange(out.shape[1], device=dev)[None, :] < lens_dev[:, None]
+        return out * keep[:, :, None].to(out.dtype), out_len
+
+    def forward(self, inp_pad: th.Tensor, inp_len: Optional[th.Tensor]):
+        """inp_pad N x Ti x F (or N x C x Ti x F), inp_len N or None -> (N x To x D, lengths)."""
+        if self.training:
+            raise RuntimeError("aps_b200.TransformerEncoder implements the inference forward only: call .eval()")
+        dev = _lib.require_cuda(inp_pad, "encoder input")
+        self._ensure_packs(dev)
         x = inp_pad.detach().float()
         out_len = self._front_lens(inp_len)
         lens_dev = None

@@ -145,6 +145,8 @@ struct DwParams {
     int N, T, D, Kw, dil, lpad;   // out[t] = sum_k w[k] * x[t - lpad + k*dil]
     long long sn, st;    // row(n, t) = n*sn + t*st
     Epilogue e;          // e.out_lo: optional TF32 "lo" companion of the output (V == 4 path)
+    const long long* lens;   // optional [N]: frames t >= lens[n] read as ZERO (ragged batches: an utterance must see the
+                             // zero padding it would see alone, not its neighbours' padded activations)
 };
 
 // thread = (row, group of V channels); rows are walked with 32-bit arithmetic (64-bit divisions per element made the
@@ -166,9 +168,10 @@ __global__ void __launch_bounds__(256) dwconv1d_kernel(const __grid_constant__ D
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = p.bias ? __ldg(p.bias + d + j) : 0.f;
+        const int tlim = p.lens ? (int)min((long long)p.T, p.lens[n]) : p.T;
         for (int k = 0; k < p.Kw; ++k) {
             const int tt = (int)t - p.lpad + k * p.dil;
-            if (tt >= 0 && tt < p.T) {
+            if (tt >= 0 && tt < tlim) {
                 const float* xp = p.x + ((long long)n * p.sn + (long long)tt * p.st) * p.ldx + d;
                 const float* wp = p.w + (long long)k * p.D + d;
                 if (V == 4) {
@@ -597,7 +600,7 @@ extern "C" int aps_b200_layernorm2_fwd(const float* x, int64_t ld_x, int32_t num
 static int dwconv1d_impl(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
                          int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
                          int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
-                         float* out_lo, int64_t ld_out, void* stream) {
+                         float* out_lo, int64_t ld_out, const int64_t* lens, void* stream) {
     APSB_CHECK_ARG(x && weight_kd && epi && out, "null pointer argument");
     APSB_CHECK_ARG(batch > 0 && num_frames > 0 && channels > 0 && kernel > 0 && dilation > 0 && left_pad >= 0,
                    "bad shape");
@@ -610,6 +613,7 @@ static int dwconv1d_impl(const float* x, int64_t ld_x, int64_t batch, int64_t nu
     p.e.slope_stride = epi->prelu_per_channel ? 1 : 0; p.e.leak = epi->leaky_slope;
     p.e.res = epi->residual; p.e.ldres = epi->ld_residual; p.e.beta = epi->beta; p.e.out = out; p.e.ldo = ld_out;
     p.e.out_lo = out_lo;
+    p.lens = reinterpret_cast<const long long*>(lens);
     p.e.post_scale = epi->post_scale; p.e.post_shift = epi->post_shift;
     APSB_CHECK_ARG(!epi->post_scale == !epi->post_shift, "post_scale and post_shift come together");
     APSB_CHECK_ARG(epi->act != ACT_PRELU || epi->prelu_slope, "PReLU slope missing");
@@ -632,15 +636,15 @@ extern "C" int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch
                                      int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
                                      int64_t ld_out, void* stream) {
     return dwconv1d_impl(x, ld_x, batch, num_frames, channels, stride_n, stride_t, weight_kd, bias, kernel, dilation,
-                         left_pad, epi, out, nullptr, ld_out, stream);
+                         left_pad, epi, out, nullptr, ld_out, nullptr, stream);
 }
 
 extern "C" int aps_b200_dwconv1d2_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames, int64_t channels,
                                       int64_t stride_n, int64_t stride_t, const float* weight_kd, const float* bias,
                                       int kernel, int dilation, int left_pad, const aps_b200_epilogue* epi, float* out,
-                                      float* out_lo, int64_t ld_out, void* stream) {
+                                      float* out_lo, int64_t ld_out, const int64_t* lens, void* stream) {
     return dwconv1d_impl(x, ld_x, batch, num_frames, channels, stride_n, stride_t, weight_kd, bias, kernel, dilation,
-                         left_pad, epi, out, out_lo, ld_out, stream);
+                         left_pad, epi, out, out_lo, ld_out, lens, stream);
 }
 
 static int mhsa_impl(const aps_b200_attn_desc* d, float* out, float* out_lo, int64_t ld_out, void* stream) {

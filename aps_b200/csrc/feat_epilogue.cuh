@@ -18,6 +18,8 @@ struct FeatParams {
     const float* gmean;
     const float* gstd;
     int* nan_count;   // optional device counter of NaN feature values (asr.py:41 check_valid)
+    const float* aug_mask;   // optional SpecAugment 0/1 mask, same layout as the output [rows, T, D]
+    const float* out_base;   // start of the output (the mask row of a frame sits at the same offset as its output row)
 };
 
 template <int G>
@@ -112,6 +114,15 @@ __device__ __forceinline__ void feature_epilogue(const FeatParams& p, const floa
                 if (p.norm_mean) feat[i] -= __ldg(p.gmean + d);
                 if (p.norm_var) feat[i] = feat[i] / __ldg(p.gstd + d);
             }
+        }
+    }
+    if (o != nullptr && p.aug_mask != nullptr) {
+        // SpecAugment with mask_zero (asr.py:678-679): x * mask, fused here so the augmented features are written once
+        const float* mrow = p.aug_mask + (o - p.out_base);
+#pragma unroll
+        for (int i = 0; i < FI; ++i) {
+            const int d = l + G * i;
+            if (d < D) feat[i] *= __ldg(mrow + d);
         }
     }
     if (o != nullptr) {

@@ -590,6 +590,8 @@ int fill_feat_params(FeatParams& p, const aps_b200_feat_desc* feat, int num_bins
     p.cmvn_mode = feat->cmvn_mode; p.norm_mean = feat->norm_mean; p.norm_var = feat->norm_var;
     p.cmvn_eps = feat->cmvn_eps; p.gmean = feat->gmean; p.gstd = feat->gstd;
     p.nan_count = feat->nan_count;
+    p.aug_mask = feat->aug_mask;
+    p.out_base = nullptr;                 // set by the launcher that knows the output pointer
     APSB_CHECK_ARG(p.cmvn_mode != 2 || ((!p.norm_mean || p.gmean) && (!p.norm_var || p.gstd)),
                    "global cmvn statistics missing");
     return 0;
@@ -666,6 +668,7 @@ extern "C" int aps_b200_feats_fwd(const float* wav, int64_t rows, int64_t num_sa
     APSB_CHECK_ARG(p.ft.D <= 17 * (p.nfft / 32), "num_mels %d too large for nfft %d", p.ft.M, p.nfft);
     p.ld_out = p.ft.D;
     p.out = out;
+    p.ft.out_base = out;
     return dispatch_frontend<0>(p, (cudaStream_t)stream);
 }
 

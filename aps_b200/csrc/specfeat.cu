@@ -182,6 +182,8 @@ extern "C" int aps_b200_spec_feats_fwd(const float* spec, int64_t rows, int64_t 
     p.row_stride = channels * num_bins * num_frames * 2;
     p.ch_offset = ref_channel * num_bins * num_frames * 2;
     p.mag_eps = mag_eps; p.out = out; p.ld_out = (int)ld_out;
+    p.ft.out_base = out;
+    APSB_CHECK_ARG(!p.ft.aug_mask || ld_out == p.ft.D, "a fused SpecAugment mask needs ld_out == feature size");
     const int fi = (p.ft.D + kSG - 1) / kSG;
     cudaStream_t st = (cudaStream_t)stream;
     if (fi <= 8) return launch_specfeat<8>(p, st);

@@ -46,6 +46,7 @@ class SplitCache:
 
     def __init__(self):
         self._items = {}
+        self.extra = {}          # other derived copies owned by the same module (e.g. zero-padded LSTM weights)
 
     def get(self, w: th.Tensor):
         key = (w.data_ptr(), tuple(w.shape), w.stride(0))
@@ -56,6 +57,7 @@ class SplitCache:
 
     def clear(self):
         self._items.clear()
+        self.extra.clear()
 
 
 # bench.py's kernel leg: when set to a list, every tensor-core GEMM launch appends (kind, flops, replay) where `replay()`
@@ -347,8 +349,19 @@ def lstm_multi(xs, mods, caches=None):
             raise RuntimeError("ops.lstm_multi: the modules must have the same shape")
     N, T, _ = xs[0].shape
     H, dirs = m0.hidden_size, 2 if m0.bidirectional else 1
-    if H % 4:
-        raise RuntimeError(f"ops.lstm: hidden_size ({H}) must be a multiple of 4")
+    # The kernel moves 16-byte rows: a hidden size that is not a multiple of 4 runs ZERO PADDED to Hp (padded units have
+    # zero weights and biases: i = f = o = 1/2, g = 0, so their cell and output stay exactly 0 and feed nothing) and the
+    # result is sliced back — no library fallback.
+    Hp = (H + 3) // 4 * 4
+
+    def gate_rows(w):                                            # [4H, X] -> [4Hp, X]
+        return w if Hp == H else th.nn.functional.pad(w.reshape(4, H, -1), (0, 0, 0, Hp - H)).reshape(4 * Hp, -1)
+
+    def in_cols(w, layer):                                       # columns of w_ih for layers fed by a padded output
+        if Hp == H or layer == 0:
+            return w
+        return th.nn.functional.pad(w.reshape(w.shape[0], dirs, H), (0, Hp - H)).reshape(w.shape[0], dirs * Hp)
+
     if any(x.shape != xs[0].shape for x in xs):
         raise RuntimeError("ops.lstm_multi: the inputs must have the same shape")
     caches = caches or [None] * len(mods)
@@ -356,27 +369,45 @@ def lstm_multi(xs, mods, caches=None):
     max_groups = 4                                               # APS_B200_LSTM_MAX_GROUPS
     inps = [x.contiguous().float() for x in xs]
     for layer in range(m0.num_layers):
-        ys = [th.empty(N, T, H * dirs, dtype=th.float32, device=dev) for _ in mods]
+        ys = [th.empty(N, T, Hp * dirs, dtype=th.float32, device=dev) for _ in mods]
         jobs = []                                                # (xg, w_hh, cell, y pointer, reverse)
         for inp, mod, cache, y in zip(inps, mods, caches, ys):
             for d in range(dirs):
                 sfx = f"_l{layer}" + ("_reverse" if d else "")
                 w_ih = getattr(mod, "weight_ih" + sfx).detach()
-                w_hh = getattr(mod, "weight_hh" + sfx).detach().contiguous()
+                w_hh = getattr(mod, "weight_hh" + sfx).detach()
                 bias = (getattr(mod, "bias_ih" + sfx).detach() + getattr(mod, "bias_hh" + sfx).detach()) if mod.bias else None
-                xg = linear(inp.view(N * T, -1), w_ih, bias, cache=cache)
-                jobs.append((xg, w_hh, th.empty(N, H, dtype=th.float32, device=dev), y.data_ptr() + 4 * H * d, d))
+                if Hp != H:
+                    key = ("lstm_pad", layer, d)
+                    store = cache.extra if isinstance(cache, SplitCache) else None
+                    packed = store.get(key) if store is not None else None
+                    src_ver = (w_ih._version, w_hh._version, w_ih.data_ptr(), w_hh.data_ptr())
+                    if packed is None or packed[0] != src_ver:
+                        pw_ih = gate_rows(in_cols(w_ih, layer)).contiguous()
+                        pw_hh = gate_rows(th.nn.functional.pad(w_hh, (0, Hp - H))).contiguous()
+                        pb = gate_rows(bias[:, None]).reshape(-1).contiguous() if bias is not None else None
+                        packed = (src_ver, pw_ih, pw_hh, pb)
+                        if store is not None:
+                            store[key] = packed
+                    _, w_ih, w_hh, bias = packed
+                else:
+                    w_hh = w_hh.contiguous()
+                split_cache = cache if isinstance(cache, SplitCache) else None
+                xg = linear(inp.view(N * T, -1), w_ih, bias, cache=split_cache)
+                jobs.append((xg, w_hh, th.empty(N, Hp, dtype=th.float32, device=dev), y.data_ptr() + 4 * Hp * d, d))
         for i in range(0, len(jobs), max_groups):
             part = jobs[i:i + max_groups]
             n = len(part)
             arr = lambda vals: (ctypes.c_void_p * n)(*vals)
             mask = sum(1 << g for g, j in enumerate(part) if j[4])
             with th.cuda.device(dev):
-                _lib.check(lib.aps_b200_lstm_group_fwd(arr([j[0].data_ptr() for j in part]), part[0][0].stride(0), N, T, H,
+                _lib.check(lib.aps_b200_lstm_group_fwd(arr([j[0].data_ptr() for j in part]), part[0][0].stride(0), N, T, Hp,
                                                        arr([j[1].data_ptr() for j in part]), mask,
                                                        arr([j[2].data_ptr() for j in part]), arr([j[3] for j in part]),
-                                                       H * dirs, n, _lib.stream_ptr(dev)))
+                                                       Hp * dirs, n, _lib.stream_ptr(dev)))
         inps = ys
+    if Hp != H:
+        inps = [y.view(N, T, dirs, Hp)[..., :H].reshape(N, T, dirs * H) for y in inps]
     return inps
 
 
@@ -387,9 +418,9 @@ def lstm(x: th.Tensor, lstm_mod, cache: Optional[dict] = None) -> th.Tensor:
 
 def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation: int = 1, left_pad: int = 0,
              stride_n: Optional[int] = None, stride_t: int = 1, act: str = "none", slope=None,
-             residual=None, post=None, want_lo: bool = False):
+             residual=None, post=None, want_lo: bool = False, lens: Optional[th.Tensor] = None):
     """Depthwise conv over time on token rows [N*T, D] (row(n, t) = n*stride_n + t*stride_t);
-    `want_lo` -> (out, TF32 lo companion)."""
+    `want_lo` -> (out, TF32 lo companion); `lens` (device int64 [N]): frames t >= lens[n] read as zero."""
     dev = _lib.require_cuda(x, "dwconv input")
     D = x.shape[1]
     Kw = weight_kd.shape[0]
@@ -400,7 +431,8 @@ def dwconv1d(x: th.Tensor, N: int, T: int, weight_kd: th.Tensor, bias, dilation:
         _lib.check(_lib.load().aps_b200_dwconv1d2_fwd(x.data_ptr(), x.stride(0), N, T, D,
                                                       T if stride_n is None else stride_n, stride_t,
                                                       weight_kd.data_ptr(), _lib.ptr(bias), Kw, dilation, left_pad, e,
-                                                      out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.stream_ptr(dev)))
+                                                      out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.ptr(lens),
+                                                      _lib.stream_ptr(dev)))
     return (out, lo) if want_lo else out
 
 
@@ -432,3 +464,104 @@ def mhsa(qkv: th.Tensor, N: int, L: int, H: int, mode: int = 0, pos: Optional[th
     with th.cuda.device(dev):
         _lib.check(_lib.load().aps_b200_mhsa2_fwd(d, out.data_ptr(), _lib.ptr(lo), out.stride(0), _lib.stream_ptr(dev)))
     return (out, lo) if want_lo else out
+
+
+# ------------------------------------------------------------------------------------ feature-chain tokens (csrc/featops.cu)
+def project_rows(x: th.Tensor, weight: th.Tensor) -> th.Tensor:
+    """x [..., K] @ weight[N, K].T on this package's GEMM kernels (mel projection of unfused chains, DCT): no library GEMM."""
+    rows = rows2d(x.detach().float())
+    w = weight.detach().float().contiguous()
+    return linear(rows, w).view(*x.shape[:-1], w.shape[0])
+
+
+def specaug_apply(x: th.Tensor, mask: th.Tensor, mask_zero: bool = True) -> th.Tensor:
+    """x N x (C) x T x F, mask N x T x F (0 / 1): x * mask, or mean(x) where the mask is 0 (asr.py:678-683)."""
+    dev = _lib.require_cuda(x, "SpecAugment input")
+    x = x.detach().float().contiguous()
+    mask = mask.detach().float().contiguous()
+    N, C = x.shape[0], (x.shape[1] if x.dim() == 4 else 1)
+    T, F = x.shape[-2], x.shape[-1]
+    if mask.shape != (N, T, F) or mask.device != dev:
+        raise RuntimeError(f"SpecAugment mask {tuple(mask.shape)} on {mask.device} does not fit features {tuple(x.shape)} on {dev}")
+    lib = _lib.load()
+    out = th.empty_like(x)
+    nbytes = 0 if mask_zero else lib.aps_b200_specaug_workspace_bytes(x.numel())
+    ws = th.empty(max(nbytes // 8, 1), dtype=th.float64, device=dev)
+    with th.cuda.device(dev):
+        _lib.check(lib.aps_b200_specaug_apply(x.data_ptr(), N, C, T, F, mask.data_ptr(), int(bool(mask_zero)), ws.data_ptr(),
+                                              nbytes, out.data_ptr(), _lib.stream_ptr(dev)))
+    return out
+
+
+def splice(x: th.Tensor, lctx: int, rctx: int, subsampling: int = 1) -> th.Tensor:
+    """N x ... x T x F -> N x ... x (T // subsampling) x (lctx + rctx + 1) * F, edge frames clamped (asr.py:687-728)."""
+    dev = _lib.require_cuda(x, "splice input")
+    x = x.detach().float().contiguous()
+    T, F = x.shape[-2], x.shape[-1]
+    rows = x.numel() // (T * F)
+    To = T if subsampling == 1 else T // subsampling
+    out = th.empty(x.shape[:-2] + (To, (lctx + rctx + 1) * F), dtype=th.float32, device=dev)
+    if out.numel():
+        with th.cuda.device(dev):
+            _lib.check(_lib.load().aps_b200_splice_fwd(x.data_ptr(), rows, T, F, lctx, rctx, subsampling, out.data_ptr(),
+                                                       _lib.stream_ptr(dev)))
+    return out
+
+
+def delta(x: th.Tensor, scale: th.Tensor, order: int, as_channel: bool = False) -> th.Tensor:
+    """x N x (C) x T x F -> cat([x, d1, .., d_order], -1) or stack(.., 1) (asr.py:731-781); scale: the 2*ctx+1 taps."""
+    dev = _lib.require_cuda(x, "delta input")
+    x = x.detach().float().contiguous()
+    T, F = x.shape[-2], x.shape[-1]
+    rows = x.numel() // (T * F)
+    ctx = (scale.numel() - 1) // 2
+    sc = scale.detach().float().contiguous()
+    K = order + 1
+    lib = _lib.load()
+    if as_channel:
+        if x.dim() != 3:
+            raise RuntimeError(f"delta_as_channel expects N x T x F features, got {x.dim()}D")
+        out = th.empty((x.shape[0], K, T, F), dtype=th.float32, device=dev)
+        rs, ts, slot = K * T * F, F, T * F                    # element (row, k, t, f)
+    else:
+        out = th.empty(x.shape[:-1] + (K * F,), dtype=th.float32, device=dev)
+        rs, ts, slot = T * K * F, K * F, F                    # element (row, t, k*F + f)
+    view = out.view(-1)
+    # slot 0 is the input itself (scale = [1] over a zero context)
+    one = th.ones(1, dtype=th.float32, device=dev)
+    with th.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.aps_b200_delta_fwd(x.data_ptr(), T * F, F, rows, T, F, 0, one.data_ptr(), view.data_ptr(), rs, ts, st))
+        for k in range(1, K):
+            src = view.data_ptr() + 4 * (k - 1) * slot
+            dst = view.data_ptr() + 4 * k * slot
+            _lib.check(lib.aps_b200_delta_fwd(src, rs, ts, rows, T, F, ctx, sc.data_ptr(), dst, rs, ts, st))
+    return out
+
+
+def speed_perturb(wav: th.Tensor, choice: th.Tensor, weights) -> th.Tensor:
+    """wav N x S; utterance n is resampled with weights[choice[n]] ([dst, src, K] each) or kept when choice[n] ==
+    len(weights); the result is zero padded to the longest utterance (asr.py:168-195)."""
+    import ctypes
+    dev = _lib.require_cuda(wav, "speed perturb input")
+    wav = wav.detach().float()
+    if wav.stride(-1) != 1:
+        wav = wav.contiguous()
+    N, S = wav.shape
+    ws = [w.detach().float().contiguous() for w in weights]
+    nf = len(ws)
+    lens = [S if c == nf else (S // ws[c].shape[1]) * ws[c].shape[0] for c in choice.tolist()]
+    for c in set(choice.tolist()):
+        if c != nf and S // ws[c].shape[1] == 0:
+            raise RuntimeError(f"Input wav is too short to be perturbed, length = {S}")
+    ld_out = max(lens)
+    out = th.empty((N, ld_out), dtype=th.float32, device=dev)
+    ch = choice.to(device=dev, dtype=th.int32).contiguous()
+    arr = lambda vals: (ctypes.c_int32 * max(nf, 1))(*vals) if nf else None
+    ptrs = (ctypes.c_void_p * max(nf, 1))(*[w.data_ptr() for w in ws]) if nf else None
+    with th.cuda.device(dev):
+        _lib.check(_lib.load().aps_b200_speed_perturb_fwd(wav.data_ptr(), N, S, wav.stride(0), ch.data_ptr(), nf, ptrs,
+                                                          arr([w.shape[0] for w in ws]), arr([w.shape[1] for w in ws]),
+                                                          arr([w.shape[2] for w in ws]), out.data_ptr(), ld_out,
+                                                          _lib.stream_ptr(dev)))
+    return out

@@ -24,8 +24,6 @@ import torch.nn as nn
 from ... import _lib, ops
 
 EPSILON = float(np.finfo(np.float32).eps)
-LSTM_TF32 = os.environ.get("APS_B200_LSTM_TF32", "0") == "1"
-LSTM_ENGINE = os.environ.get("APS_B200_LSTM", "fused")        # "cudnn": torch.nn.LSTM (library), A/B only
 
 
 def parse_1dstr(s: str) -> List[int]:
@@ -122,14 +120,8 @@ class LSTMP(nn.Module):
 def lstmp_pair(mods, xs):
     """Several LSTMP modules of one shape on same-shaped inputs: input projections of all frames on the tensor-core
     engine, then one fused recurrence + cell-update launch per frame for all of them together (csrc/lstm.cu), exact
-    fp32.  APS_B200_LSTM=cudnn: torch.nn.LSTM (library), kept for A/B only — cuDNN would run the recurrent GEMMs as
-    single-pass TF32 by default (torch.backends.cudnn.allow_tf32): off unless APS_B200_LSTM_TF32=1."""
-    # hidden sizes that are not a multiple of 4 (no 16-byte rows for the kernel's copies) stay on the library as well
-    if LSTM_ENGINE == "cudnn" or any(m.lstm.hidden_size % 4 for m in mods):
-        with th.backends.cudnn.flags(enabled=True, allow_tf32=LSTM_TF32):
-            outs = [m.lstm(x)[0] for m, x in zip(mods, xs)]
-    else:
-        outs = ops.lstm_multi(xs, [m.lstm for m in mods], [m.splits() for m in mods])
+    fp32.  There is no library path: hidden sizes that are not a multiple of 4 run zero padded (ops.lstm_multi)."""
+    outs = ops.lstm_multi(xs, [m.lstm for m in mods], [m.splits() for m in mods])
     return [m.project(o) for m, o in zip(mods, outs)]
 
 

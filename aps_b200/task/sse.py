@@ -25,6 +25,15 @@ class Task(nn.Module):
         self.description = description
 
 
+def _mel_project(mel: th.Tensor, spec: th.Tensor) -> th.Tensor:
+    """mel M x F applied to spec N x F x T -> N x M x T (aps/task/sse.py:430-440): on the device through this package's
+    GEMM kernels (ops.project_rows), not a library matmul."""
+    if spec.is_cuda:
+        from .. import ops
+        return ops.project_rows(spec.transpose(-1, -2), mel).transpose(-1, -2)
+    return th.matmul(mel, spec)
+
+
 class TimeDomainTask(Task):
     """aps/task/sse.py:26-103 (SepTask + TimeDomainTask)"""
 
@@ -198,7 +207,7 @@ class MelFreqSaTask(FreqSaTask):
         """N x F x T -> N x M x T"""
         if self.power_mag:
             tensor = tensor**2
-        mel = th.matmul(self.mel[..., 0].to(tensor.device), tensor)
+        mel = _mel_project(self.mel[..., 0].to(tensor.device), tensor)
         return th.log(1 + mel) if self.log else mel
 
     def objf(self, out: th.Tensor, ref: th.Tensor) -> th.Tensor:

@@ -154,6 +154,11 @@ class SpeedPerturbTransform(_Layer):
             raise RuntimeError(f"Now only supports 2D tensor, got {wav.dim()}")
         choice = th.randint(0, len(self.weights) + 1, (wav.shape[0],))
         self.last_choice = choice
+        if wav.is_cuda:
+            # one launch for the whole batch: every utterance runs the polyphase filter of its own choice
+            # (csrc/featops.cu speed_perturb_kernel) and the result comes back zero padded to the longest one
+            from .. import ops
+            return ops.speed_perturb(wav, choice, list(self.weights))
         outs = []
         for i, c in enumerate(choice.tolist()):
             outs.append(wav[i] if c == len(self.weights) else self._resample(wav[i:i + 1], self.weights[c])[0])
@@ -293,6 +298,9 @@ class MelTransform(_Layer):
     def forward(self, linear: th.Tensor) -> th.Tensor:
         if linear.dim() not in (3, 4):
             raise RuntimeError(f"MelTransform expect 3/4D tensor, but got {linear.dim()} instead")
+        if linear.is_cuda:
+            from .. import ops
+            return ops.project_rows(linear, self.filters)       # unfused chains: this package's GEMM, not a library one
         return tf.linear(linear, self.filters, bias=None)
 
 
@@ -338,7 +346,11 @@ class DiscreteCosineTransform(_Layer):
         return "cepstral_lifter={0}, dct={1[0]}x{1[1]}".format(self.lifter, self.dct.shape)
 
     def forward(self, log_mel: th.Tensor) -> th.Tensor:
-        out = tf.linear(log_mel, self.dct, bias=None)
+        if log_mel.is_cuda:
+            from .. import ops
+            out = ops.project_rows(log_mel, self.dct)
+        else:
+            out = tf.linear(log_mel, self.dct, bias=None)
         return out if self.cepstral_lifter is None else out * self.cepstral_lifter
 
 
@@ -472,10 +484,21 @@ class SpecAugTransform(_Layer):
             N, T, F = (x.shape[0], x.shape[2], x.shape[3]) if x.dim() == 4 else x.shape
             mask = tf_mask(N, (T, F), pm=self.pm, ps=self.ps, max_bands=self.F, max_frame=self.T,
                            num_freq_masks=self.fnum, num_time_masks=self.tnum, device=x.device)
+            if x.is_cuda:
+                from .. import ops
+                return ops.specaug_apply(x, mask, self.mask_zero).view(x.shape)
             if x.dim() == 4:
                 mask = mask.unsqueeze(1)
             x = x * mask if self.mask_zero else th.masked_fill(x, mask == 0, x.mean())
         return x
+
+    def draw_mask(self, N: int, T: int, F: int, device) -> Optional[th.Tensor]:
+        """The mask `forward` would apply (same RNG calls in the same order), or None when this call does not augment:
+        lets the fused feature kernel multiply it in its epilogue (run_chain)."""
+        if self.training and th.rand(1).item() < self.p:
+            return tf_mask(N, (T, F), pm=self.pm, ps=self.ps, max_bands=self.F, max_frame=self.T,
+                           num_freq_masks=self.fnum, num_time_masks=self.tnum, device=device)
+        return None
 
 
 def splice_feature(feats: th.Tensor, lctx: int = 1, rctx: int = 1, op: str = "cat") -> th.Tensor:
@@ -505,6 +528,11 @@ class SpliceTransform(_Layer):
         return 1 + self.rctx + self.lctx
 
     def forward(self, feats: th.Tensor) -> th.Tensor:
+        if feats.is_cuda:
+            if self.lctx + self.rctx == 0 and self.subsampling_factor == 1:
+                return feats
+            from .. import ops
+            return ops.splice(feats, self.lctx, self.rctx, self.subsampling_factor)
         feats = splice_feature(feats, lctx=self.lctx, rctx=self.rctx)
         if self.subsampling_factor != 1:
             end = (feats.shape[-2] // self.subsampling_factor) * self.subsampling_factor
@@ -529,6 +557,9 @@ class DeltaTransform(_Layer):
         return self.order
 
     def forward(self, feats: th.Tensor) -> th.Tensor:
+        if feats.is_cuda and (not self.delta_as_channel or feats.dim() == 3):
+            from .. import ops
+            return ops.delta(feats, self.scale, self.order, as_channel=self.delta_as_channel)
         outs = [feats]
         for _ in range(self.order):
             ctx = splice_feature(outs[-1], lctx=self.ctx, rctx=self.ctx, op="stack")
@@ -600,9 +631,11 @@ def _apply_allband(out: th.Tensor, cmvn: CmvnTransform, dev: th.device) -> None:
 
 
 def fused_wave_features(spec: SpectrogramTransform, wav: th.Tensor, tail, rescale: bool,
-                        utt_preemph: float, nan_count: Optional[th.Tensor] = None) -> th.Tensor:
+                        utt_preemph: float, nan_count: Optional[th.Tensor] = None,
+                        aug: Optional["SpecAugTransform"] = None) -> th.Tensor:
     """F1: waveform N x (C) x S -> features N x (C) x T x D in one kernel.  `nan_count` (int32[1] on the
-    device, pre-zeroed) receives the number of NaN values written."""
+    device, pre-zeroed) receives the number of NaN values written.  `aug`: a zero-fill SpecAugment layer that follows
+    the chain — its mask (host RNG, drawn here exactly as its own forward would) is multiplied in the kernel's epilogue."""
     power, mel, log, cmvn, mag_eps, _ = tail
     if wav.dim() not in (2, 3):
         raise RuntimeError(f"STFT expect 2D/3D tensor, but got {wav.dim():d}D")
@@ -625,6 +658,12 @@ def fused_wave_features(spec: SpectrogramTransform, wav: th.Tensor, tail, rescal
     if T < 1:
         raise RuntimeError(f"STFT: {S} samples are too few for one frame of {sd.frame_width}")
     out = th.empty((rows, T, D), dtype=th.float32, device=dev)
+    if aug is not None:
+        mask = aug.draw_mask(rows, T, D, dev)
+        if mask is not None:
+            mask = mask.contiguous()
+            fd.aug_mask = mask.data_ptr()
+            fd._keep.append(mask)
     with th.cuda.device(dev):
         _lib.check(lib.aps_b200_feats_fwd(x.data_ptr(), rows, S, x.stride(0), sd, fd, out.data_ptr(),
                                           _lib.stream_ptr(dev)))
@@ -686,10 +725,18 @@ def run_chain(layers: List[nn.Module], x: th.Tensor, nan_count: Optional[th.Tens
         if j < n and isinstance(layers[j], SpectrogramTransform) and x.is_cuda:
             tail = _match_tail(layers, j + 1)
             if tail is not None:
-                y = fused_wave_features(layers[j], x, tail, rescale=r, utt_preemph=max(e, 0.0), nan_count=nan_count)
+                nxt = tail[5]
+                cm = tail[3]
+                allband = cm is not None and cm.gmean is None and not cm.per_band and (cm.norm_mean or cm.norm_var)
+                aug = None
+                if (nxt < n and isinstance(layers[nxt], SpecAugTransform) and layers[nxt].mask_zero and x.dim() == 2
+                        and not allband):
+                    aug, nxt = layers[nxt], nxt + 1      # SpecAugment (zero fill) rides in the kernel's epilogue
+                y = fused_wave_features(layers[j], x, tail, rescale=r, utt_preemph=max(e, 0.0), nan_count=nan_count,
+                                        aug=aug)
                 if emph_layer is not None and e > 0 and not r:
                     emph_layer(x)        # keep the reference's in-place side effect on the caller's wav (Q9)
-                x, i = y, tail[5]
+                x, i = y, nxt
                 continue
         x = lay(x)
         i += 1

@@ -86,6 +86,8 @@ typedef struct aps_b200_feat_desc {
     const float* gmean;    /* [dims] (cmvn_mode 2) */
     const float* gstd;     /* [dims] (cmvn_mode 2) */
     int32_t* nan_count;    /* optional: += number of NaN feature values written (asr.py:41-45)   */
+    const float* aug_mask; /* optional SpecAugment 0/1 mask [rows, T, dims] multiplied into the features AFTER cmvn
+                              (asr.py:656-684 with mask_zero=True; the mask is drawn by the host RNG, augment.py:13-53) */
 } aps_b200_feat_desc;
 
 /* F1: wav [rows, num_samples] (row stride ld_wav floats) -> feats [rows, T, dims],
@@ -283,6 +285,32 @@ int aps_b200_cmask_fwd(const float* mask, int64_t ld_mask, int64_t col_real, int
                        const float* stft, int64_t positions, int act, float eps, int apply, float* out,
                        void* stream);
 
+/* Remaining feature-chain tokens (rows a10, f2, f3) ----------------------------------------------------
+ * SpecAugment apply on x [batch, channels, frames, dims] with mask [batch, frames, dims] (0/1, host RNG):
+ * mask_zero != 0: out = x * mask; else out = mask == 0 ? mean(x) : x (global mean, asr.py:680-683).  workspace: >=
+ * aps_b200_specaug_workspace_bytes(numel) bytes (fp64 partial sums, deterministic order); may be NULL for mask_zero. */
+int64_t aps_b200_specaug_workspace_bytes(int64_t numel);
+int aps_b200_specaug_apply(const float* x, int64_t batch, int64_t channels, int64_t frames, int64_t dims,
+                           const float* mask, int32_t mask_zero, void* workspace, int64_t workspace_bytes,
+                           float* out, void* stream);
+/* Context splicing with edge clamping + frame subsampling: x [rows, frames, dims] -> out [rows, frames / subsampling,
+ * (lctx + rctx + 1) * dims] (asr.py:687-728, utils.py:193-224).                                              */
+int aps_b200_splice_fwd(const float* x, int64_t rows, int64_t frames, int64_t dims, int32_t lctx, int32_t rctx,
+                        int32_t subsampling, float* out, void* stream);
+/* One delta order: out[r, t, f] = sum_c scale[c] * in[r, clamp(t + c - ctx), f]; element (r, t, f) of in / out lives at
+ * r * row_stride + t * frame_stride + f, so the slots of the concatenated / stacked result are written in place
+ * (asr.py:731-781).                                                                                            */
+int aps_b200_delta_fwd(const float* in, int64_t in_row_stride, int64_t in_frame_stride, int64_t rows, int64_t frames,
+                       int64_t dims, int32_t ctx, const float* scale, float* out, int64_t out_row_stride,
+                       int64_t out_frame_stride, void* stream);
+/* Per-utterance speed perturbation (polyphase resampling): utterance n uses filter choice[n] (weights[i] is
+ * [dst_sr[i], src_sr[i], taps[i]], utils.py:159-190) or is copied when choice[n] == num_filters; out [batch, ld_out] is
+ * zero padded (asr.py:168-195, augment.py:85-109).                                                            */
+int aps_b200_speed_perturb_fwd(const float* wav, int64_t batch, int64_t num_samples, int64_t ld_wav,
+                               const int32_t* choice, int32_t num_filters, const float* const* weights,
+                               const int32_t* dst_sr, const int32_t* src_sr, const int32_t* taps, float* out,
+                               int64_t ld_out, void* stream);
+
 /* Encoder (non-GEMM) kernels ---------------------------------------------------------------------
  * Activations are token-major rows; row(n, t) = n*stride_n + t*stride_t.
  */
@@ -313,12 +341,14 @@ int aps_b200_dwconv1d_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t n
                           const float* weight_kd, const float* bias, int kernel, int dilation,
                           int left_pad, const aps_b200_epilogue* epi, float* out, int64_t ld_out,
                           void* stream);
-/* ... and the TF32 lo companion of the output (channels % 4 == 0, 16-byte aligned rows) */
+/* ... with the TF32 lo companion of the output (out_lo, optional: channels % 4 == 0, 16-byte aligned rows) and optional
+ * per-utterance lengths (device int64 [batch]): input frames t >= lens[n] read as zero, which is what an utterance sees
+ * alone (ragged batched decoding, aps/asr/ctc.py:58-84).                                                          */
 int aps_b200_dwconv1d2_fwd(const float* x, int64_t ld_x, int64_t batch, int64_t num_frames,
                            int64_t channels, int64_t stride_n, int64_t stride_t,
                            const float* weight_kd, const float* bias, int kernel, int dilation,
                            int left_pad, const aps_b200_epilogue* epi, float* out, float* out_lo,
-                           int64_t ld_out, void* stream);
+                           int64_t ld_out, const int64_t* lens, void* stream);
 
 /* Multi-head self-attention, softmax((q.k + pos_term) * scale [masked]) . v per (batch, head).
  * mode 0: no position term (aps/asr/transformer/impl.py:120-131 / torch MHA);

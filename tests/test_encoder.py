@@ -428,3 +428,47 @@ def test_register_tiled_attention_matches_the_simple_kernel(monkeypatch, L):
     sc = sc.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
     ref = (th.softmax(sc, -1) @ vv).permute(0, 2, 1, 3).reshape(N * L, E)
     assert rel_err(ops.mhsa(qkv, N, L, H, mode=0, kpm=kpm, kpm_fill=float("-inf")), ref) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch,pose", [("cfmr", "rel"), ("xfmr", "abs"), ("cfmr", "xl")])
+def test_batch_decoding_prep_equals_one_utterance_at_a_time(arch, pose):
+    """Row f4: the ragged decoding batch of aps/asr/ctc.py:58-84 in ONE pass.  Every utterance must come out as if it had
+    been run alone (the reference loops for exactly that reason); "xl" depends on the padded length and takes the loop."""
+    from aps_b200.asr.decoding import batch_decoding_prep
+    from aps_b200.asr.transformer import TransformerEncoder
+    from aps_b200.transform import AsrTransform
+    th.manual_seed(7)
+    tf = AsrTransform(feats="fbank-log-cmvn", frame_len=400, frame_hop=160, window="hamm", pre_emphasis=0.97,
+                      num_mels=80).to(DEV).eval()
+    ak = dict(att_dim=128, nhead=2, feedforward_dim=1024, att_dropout=0.1, ffn_dropout=0.1, pre_norm=False)
+    if arch == "cfmr":
+        ak["kernel_size"] = 15
+    cfg = dict(arch=arch, input_size=80, output_proj=-1, num_layers=2, proj="conv2d",
+               proj_kwargs=dict(conv_channels=32, num_layers=3), pose=pose,
+               pose_kwargs=dict(lradius=32, rradius=32) if pose == "rel" else {}, arch_kwargs=ak)
+    enc = TransformerEncoder(**copy.deepcopy(cfg)).eval()
+    with th.no_grad():
+        for name, buf in enc.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.2 * th.randn(buf.shape))
+            if name.endswith("running_var"):
+                buf.copy_(0.5 + th.rand(buf.shape))
+    dev_enc = copy.deepcopy(enc).to(DEV)
+    wavs = [0.1 * th.randn(n) for n in (32000, 24321, 18000, 40000, 14001, 32000)]
+    out, ln = batch_decoding_prep(tf, dev_enc, [w.to(DEV) for w in wavs])
+    assert out.shape[0] == len(wavs) and out.shape[1] == int(ln.max())
+    for i, w in enumerate(wavs):
+        f, _ = tf(w[None].to(DEV), None)
+        y, _ = dev_enc(f, None)
+        assert int(ln[i]) == y.shape[1]
+        assert rel_err(out[i, :y.shape[1]], y[0]) < FLOAT_TOL, (arch, pose, i)
+        assert float(out[i, y.shape[1]:].abs().max()) == 0.0 if y.shape[1] < out.shape[1] else True
+    # ... and against the CPU oracle of the reference, utterance 1 alone
+    from oracle import transform as OT
+    f1, _ = OT.AsrFeatures(OT.AsrFeatCfg())(wavs[1][None], None)
+    o1, _ = EncoderOracle(cfg, enc.state_dict())(f1, None)
+    assert rel_err(out[1, :o1.shape[1]], o1[0]) < FLOAT_TOL
+    # time-major variant
+    out_t, _ = batch_decoding_prep(tf, dev_enc, [w.to(DEV) for w in wavs], batch_first=False)
+    assert th.equal(out_t.transpose(0, 1), out)

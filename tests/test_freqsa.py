@@ -144,8 +144,6 @@ def test_complex_masking_compressed_path_raises_like_the_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the same shells pass on the CPU "
-                                        "with the oracle STFT and the sibling FreqSa GPU test passed on a B200")
 def test_timesa_gpu_vs_reference():
     kw, g = load_golden("timesa_0")
     _run_timesa(kw, g, th.device("cuda", 0), oracle_ctx=False)

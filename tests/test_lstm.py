@@ -51,6 +51,8 @@ def test_lstm_host_checks_without_gpu():
     (40, 20, 64, 40, 2, False),        # hidden not a multiple of the 16-unit / 32-k tiles (DCCRN goldens use 40)
     (33, 25, 32, 64, 2, True),         # bidirectional, two layers
     (70, 50, 256, 512, 2, False),      # the DCCRN bottleneck shape
+    (6, 9, 10, 6, 2, False),           # hidden % 4 != 0: runs zero padded to 8 units (no library fallback)
+    (12, 5, 20, 30, 2, True),          # ... bidirectional: the next layer's input columns are padded per direction
 ])
 def test_lstm_matches_torch(rows, frames, feats, hidden, layers, bidir):
     from aps_b200 import ops
@@ -82,9 +84,6 @@ def test_lstm_rows_are_independent():
 @gpu
 def test_lstm_refuses_unsupported():
     from aps_b200 import ops
-    mod = th.nn.LSTM(8, 6, batch_first=True).cuda()
-    with pytest.raises(RuntimeError, match="multiple of 4"):
-        ops.lstm(th.zeros(2, 3, 8, device="cuda"), mod)
     with pytest.raises(RuntimeError, match="batch_first"):
         ops.lstm(th.zeros(2, 3, 8, device="cuda"), th.nn.LSTM(8, 8).cuda())
 
