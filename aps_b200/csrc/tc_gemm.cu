@@ -50,6 +50,10 @@ constexpr int TC_BM = 128;
 #ifndef APSB_TC_PW_LINEAR
 #define APSB_TC_PW_LINEAR 4
 #endif
+// default cluster size for the weight-tile multicast (1 = off)
+#ifndef APSB_TC_CLUSTER
+#define APSB_TC_CLUSTER 2
+#endif
 // MODE 3 (linear layer whose activation comes with its TF32 "lo" companion, see below) has NO producer warps: the TMA
 // warp loads the A tiles as well.
 template <int BN, int MODE> struct TcRoles {
@@ -125,10 +129,37 @@ __device__ __forceinline__ void tc_tma_load_2d(const CUtensorMap* map, uint64_t*
         "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same box written into the shared memory of every CTA of the cluster named in `mask` (same CTA-relative offset), each
+// destination's mbarrier (same offset) gets the complete_tx
+__device__ __forceinline__ void tc_tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(s_u32(dst)),
+        "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar))
+                 : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in EVERY CTA of `mask`: a stage that was filled by a multicast
+// may only be refilled when all CTAs of the cluster have finished reading it
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     s_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 // shared-memory matrix descriptor: K-major operand whose rows are one swizzle span (SWZ = 128 or 64 bytes) wide,
@@ -277,6 +308,7 @@ struct TcParams {
     AGather a;
     Epilogue e;
     int epi_vec;                 // output / residual rows are 16-byte aligned and N % 4 == 0 (N % 8 for GLU)
+    unsigned stiles;             // super tiles = ceil(row blocks / CL) x column blocks x K slices (CL = cluster size)
     int ksplit;                  // MODE 3: the K range is cut into `ksplit` slices, slice s -> out + s * split_stride
     long long split_stride;      //         (raw partial sums; bias / activation / residual happen in the reducing kernel)
     int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
@@ -321,7 +353,12 @@ template <int BN> struct TcCfg {
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN, int MODE>
+// CL > 1: thread-block cluster of CL CTAs that work on CL consecutive ROW blocks of the same column block (and K slice)
+// in lock step.  Every CTA fetches 1 / CL of each weight tile and MULTICASTS it to the whole cluster, so a weight tile
+// crosses the L2 -> SM fabric once per CL row blocks.  (Round-2 finding: at these shapes the engine is bound by L2 -> SM
+// bandwidth — FFN-a moves 210 MB in 28 us, conv2 re-reads its 4.7 MB filter for each of its 1000 row tiles — not by the
+// tensor pipe.)  A stage is released to the TMA threads of all CL CTAs by multicast commits (empty barriers count CL).
+template <int BN, int MODE, int CL>
 __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
@@ -345,6 +382,23 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
+    static_assert(CL == 1 || MODE != 2, "row classes of a transposed convolution skip k-blocks per tile: no lock step");
+    const unsigned crank = CL > 1 ? tc_cluster_rank() : 0u;
+    const unsigned cid = blockIdx.x / CL, ncl = gridDim.x / CL;       // cluster index / number of clusters
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+    // super tile -> flat tile index of THIS CTA (row block = CL * super row + rank; may lie beyond M: a dummy tile that
+    // keeps the lock step, reads zeros and stores nothing)
+    auto tile_of = [&](unsigned st) -> unsigned {
+        if (CL == 1) return st;
+        unsigned t2 = st, ks = 0;
+        if (MODE == 3 && p.ksplit > 1) {
+            t2 = st / (unsigned)p.ksplit;
+            ks = st - t2 * (unsigned)p.ksplit;
+        }
+        const unsigned msup = t2 / (unsigned)p.tiles_n, nb = t2 - msup * (unsigned)p.tiles_n;
+        const unsigned flat = (msup * CL + crank) * (unsigned)p.tiles_n + nb;
+        return (MODE == 3 && p.ksplit > 1) ? flat * (unsigned)p.ksplit + ks : flat;
+    };
     // k-blocks are walked tap by tap (convolutions: a k-block never crosses a (kh, kw) tap since Cin % 32 == 0) so that
     // a transposed-convolution tile can skip the taps that are zero for its row class; a linear layer is one "tap"
     // Order inside a tile: kernel row kh (skippable), then channel block cb, then kw INNERMOST: the three kw taps of one
@@ -403,7 +457,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             for (int s = 0; s < S; ++s) {
                 tc_mbar_init(full_a + s, MODE == 3 ? 1 : TcRoles<BN, MODE>::PW);
                 tc_mbar_init(full_b + s, 1);
-                tc_mbar_init(empty + s, 1);
+                tc_mbar_init(empty + s, CL);
             }
             for (int b = 0; b < 2; ++b) {
                 tc_mbar_init(tmem_full + b, 1);
@@ -419,6 +473,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) tc_cluster_sync();          // every CTA's barriers are initialised before a peer may signal them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TR(9);
@@ -426,13 +481,26 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     // nothing below may start before that kernel has completed (activations, residuals, output buffers it still reads)
     pdl_wait();
 
+    // W_hi / W_lo tile of one stage: the whole box (CL = 1), or this CTA's 1 / CL of its rows multicast to the cluster
+    auto load_w = [&](uint64_t* bar, uint8_t* dst, int k0, int n0) {
+        if (CL == 1) {
+            tc_tma_load_2d(&tmB, bar, dst, k0, n0);
+            tc_tma_load_2d(&tmBlo, bar, dst + C::B_BYTES, k0, n0);
+        } else {
+            constexpr int SL = BN / CL;                               // rows of the slice (a multiple of 8: swizzle atoms)
+            const uint32_t off = crank * (uint32_t)(SL * SWZ);
+            tc_tma_load_2d_mc(&tmB, bar, dst + off, k0, n0 + (int)crank * SL, CMASK);
+            tc_tma_load_2d_mc(&tmBlo, bar, dst + C::B_BYTES + off, k0, n0 + (int)crank * SL, CMASK);
+        }
+    };
     if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
         if (MODE == 3) {
             // operands of both sides by TMA: [A (raw x = hi) | A lo | W hi | W lo] per stage, one mbarrier transaction
             if (lane == 0) {
                 uint32_t it = 0;
-                for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
+                    const unsigned tile = tile_of(st_);
                     const TileIdx t = decode3(tile);
                     for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
                         const int s = it % S;
@@ -442,15 +510,15 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         tc_mbar_expect_tx(full_b + s, 2 * A_BYTES + 2 * C::B_BYTES);
                         tc_tma_load_2d(&tmA, full_b + s, st, kb * BK, t.m_blk * TC_BM);
                         tc_tma_load_2d(&tmAlo, full_b + s, st + A_BYTES, kb * BK, t.m_blk * TC_BM);
-                        tc_tma_load_2d(&tmB, full_b + s, st + 2 * A_BYTES, kb * BK, t.n_blk * BN);
-                        tc_tma_load_2d(&tmBlo, full_b + s, st + 2 * A_BYTES + C::B_BYTES, kb * BK, t.n_blk * BN);
+                        load_w(full_b + s, st + 2 * A_BYTES, kb * BK, t.n_blk * BN);
                         TC_TR(1);
                     }
                 }
             }
         } else if (lane == 0) {
             uint32_t it = 0;
-            for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
+                const unsigned tile = tile_of(st_);
                 const int n_blk = (int)(tile % (unsigned)p.tiles_n);
                 const int cls = tile_class(tile);
                 for (int kh = 0; kh < num_kh; ++kh) {
@@ -470,8 +538,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         }
 #endif
                         tc_mbar_expect_tx(full_b + s, 2 * C::B_BYTES);
-                        tc_tma_load_2d(&tmB, full_b + s, st, kb * BK, n_blk * BN);
-                        tc_tma_load_2d(&tmBlo, full_b + s, st + C::B_BYTES, kb * BK, n_blk * BN);
+                        load_w(full_b + s, st, kb * BK, n_blk * BN);
                         TC_TR(1);
                     }
                 }
@@ -484,7 +551,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, tcount = 0;
-            for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
+            for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl, ++tcount) {
+                const unsigned tile = tile_of(st_);
                 const uint32_t buf = tcount & 1;
                 tc_mbar_wait_parked(tmem_empty + buf, ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
@@ -510,7 +578,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             tc_mma_tf32(d_tmem, dal, db, idesc, 1);
                         }
                         first = 0;
-                        tc_commit(empty + s);
+                        if (CL == 1) tc_commit(empty + s); else tc_commit_mc(empty + s, CMASK);
                     }
                 } else
                 for (int kh = 0; kh < num_kh; ++kh) {
@@ -534,7 +602,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         tc_mma_tf32(d_tmem, dal, db, idesc, 1);
                     }
                     first = 0;
-                    tc_commit(empty + s);          // frees the stage once the MMAs above have read it
+                    // frees the stage once the MMAs above have read it (in every CTA of the cluster: multicast fills)
+                    if (CL == 1) tc_commit(empty + s); else tc_commit_mc(empty + s, CMASK);
                   }
                 }
                 tc_commit(tmem_full + buf);        // accumulator complete
@@ -551,7 +620,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         const Epilogue& e = p.e;
         const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
-        for (unsigned tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
+        for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl, ++tcount) {
+            const unsigned tile = tile_of(st_);
             int n_blk = (int)(tile % (unsigned)p.tiles_n);
             unsigned m_blk = tile / (unsigned)p.tiles_n;
             float* eout = e.out;                   // split-K: slice ks of the partial-sum workspace
@@ -868,13 +938,14 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         // mode carries no per-row convolution geometry, so it affords one more block
         constexpr int D = BK == 16 ? 4 : (MODE == 0 ? 3 : (TcRoles<BN, MODE>::PW == 8 ? 4 : 2));
         // iterator over the (tile, tap, k-block) sequence of this CTA, skipping taps that are zero for the tile's class
-        unsigned ltile = blockIdx.x;
+        unsigned lst = cid;                                 // super tile; ltile = this CTA's flat tile of it
+        unsigned ltile = tile_of(lst);
         int lkh = 0, lcb = 0, lkw = 0, lh = 0;              // lcb counts 32-channel groups, lh the half inside (BK = 16)
         bool lfresh = true;                     // the tile's rows have not been decoded yet
         unsigned lmask = 0, lmask_tile = 0xffffffffu;
         int lkh_set = -1;                       // kernel row the prow[] pointers were computed for
         auto seek = [&]() {                     // move (ltile, lkh) to the next valid kernel row; false at the end
-            while (ltile < p.tiles) {
+            while (lst < p.stiles) {
                 if (lfresh && lmask_tile != ltile) {       // once per tile: class and the bit mask of its non-zero kernel rows
                     lcls = tile_class(ltile);
                     lmask = 0;
@@ -883,7 +954,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 }
                 while (lkh < num_kh && !(lkh < 32 ? (bool)((lmask >> lkh) & 1u) : tc_kh_valid(a, lcls, lkh))) ++lkh;
                 if (lkh < num_kh) return true;
-                ltile += gridDim.x;
+                lst += ncl;
+                ltile = tile_of(lst);
                 lkh = 0;
                 lcb = 0;
                 lkw = 0;
@@ -1015,6 +1087,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) tc_cluster_sync();          // no CTA leaves while a peer may still multicast into it or signal its barriers
 #ifdef APSB_TC_TRACE
     if (p.trace && blockIdx.x == 0)
         for (int i = threadIdx.x; i < TC_TRACE_WORDS; i += blockDim.x) p.trace[i] = tr_smem[i];
@@ -1109,25 +1182,79 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
     return 0;
 }
 
-template <int BN, int MODE>
-static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const CUtensorMap& tA, const CUtensorMap& tAl,
-                          const TcParams& p, long long grid, cudaStream_t st) {
+// launch with a cluster of CL CTAs (CL = 1: plain launch), optionally as a programmatic dependent launch.  The grid is
+// `nclusters` x CL with nclusters bounded by what the device can keep resident at once (cudaOccupancyMaxActiveClusters:
+// a cluster must sit inside one GPC, and 148 SMs are not a multiple of every GPC's width).
+template <int BN, int MODE, int CL>
+static int launch_tc_cl(const CUtensorMap& tB, const CUtensorMap& tBl, const CUtensorMap& tA, const CUtensorMap& tAl,
+                        TcParams p, cudaStream_t st) {
     using C = TcCfg<BN>;
     static bool attr_done[64] = {false};       // function attributes are per device (one context per GPU)
+    static int max_clusters[64] = {0};
     int dev = 0;
     APSB_CUDA(cudaGetDevice(&dev));
-    bool& attr = attr_done[dev & 63];
-    if (!attr) {
-        APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    auto kern = tc_gemm_kernel<BN, MODE, CL>;
+    if (!attr_done[dev & 63]) {
+        APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         // smallest shared-memory carve-out that holds the CTA: what is left of the 228 KB array stays L1 for the gathers
-        APSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (C::SMEM + 1024) * 100 / (228 * 1024) + 1));
-        attr = true;
+        int mc = num_sms() / CL;
+        if (CL > 1) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3((unsigned)(num_sms() / CL * CL));
+            q.blockDim = dim3(TcRoles<BN, MODE>::THREADS);
+            q.dynamicSmemBytes = C::SMEM;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int n = 0;
+            APSB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+            APSB_CHECK_ARG(n >= 1, "no cluster of %d CTAs of the tensor-core GEMM fits on this device", CL);
+            mc = n < mc ? n : mc;
+        }
+        max_clusters[dev & 63] = mc;
+        attr_done[dev & 63] = true;
     }
-    APSB_CUDA(launch_pdl(tc_gemm_kernel<BN, MODE>, dim3((unsigned)grid), dim3(TcRoles<BN, MODE>::THREADS), C::SMEM, st, tB, tBl,
-                         tA, tAl, p));
+    const long long tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    const long long stiles = (tiles_m + CL - 1) / CL * p.tiles_n * p.ksplit;
+    p.stiles = (unsigned)stiles;
+    const long long ncl = stiles < max_clusters[dev & 63] ? stiles : max_clusters[dev & 63];
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ncl * CL));
+    cfg.blockDim = dim3(TcRoles<BN, MODE>::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    APSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tB, tBl, tA, tAl, p));
     APSB_LAUNCH_CHECK();
     return 0;
+}
+
+// cluster size of a launch: weight-tile multicast pays when several row blocks share a column block (row classes of a
+// strided transposed convolution break the lock step: MODE 2 stays at 1).  APS_B200_TC_CL = 1 | 2 | 4 overrides.
+template <int BN, int MODE>
+static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const CUtensorMap& tA, const CUtensorMap& tAl,
+                          const TcParams& p, int cl, cudaStream_t st) {
+    if constexpr (MODE != 2) {
+        if (cl == 4) return launch_tc_cl<BN, MODE, 4>(tB, tBl, tA, tAl, p, st);
+        if (cl == 2) return launch_tc_cl<BN, MODE, 2>(tB, tBl, tA, tAl, p, st);
+    }
+    return launch_tc_cl<BN, MODE, 1>(tB, tBl, tA, tAl, p, st);
 }
 
 // `xlo` != nullptr selects MODE 3 (A tiles by TMA from x / xlo); `ksplit` > 1 cuts K into slices (MODE 3 only)
@@ -1136,9 +1263,16 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
                      const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
                      long long split_stride = 0) {
     using C = TcCfg<BN>;
+    // cluster size (weight-tile multicast)
+    const long long tiles_m_ = (M + TC_BM - 1) / TC_BM;
+    int cl = (a.mode != 2 && tiles_m_ >= 8) ? APSB_TC_CLUSTER : 1;
+    if (const char* ce = getenv("APS_B200_TC_CL")) {
+        const int v = atoi(ce);
+        if ((v == 1 || v == 2 || v == 4) && a.mode != 2) cl = v;
+    }
     CUtensorMap tB, tBl, tA, tAl;
-    if (int rc = make_map(&tB, W, N, K, ldw, BN, C::BK)) return rc;
-    if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN, C::BK)) return rc;
+    if (int rc = make_map(&tB, W, N, K, ldw, BN / cl, C::BK)) return rc;          // a CTA fetches BN / cl rows of the box
+    if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN / cl, C::BK)) return rc;
     tA = tB; tAl = tBl;
     if (xlo) {
         if (int rc = make_map(&tA, a.x, M, K, a.ld, TC_BM, C::BK)) return rc;
@@ -1168,11 +1302,10 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     p.dbg = getenv("APS_B200_TC_DBG") ? atoi(getenv("APS_B200_TC_DBG")) : 0;
     p.e.dbg_nobias = (p.dbg & 128) ? 1 : 0;
 #endif
-    const long long grid = tiles < num_sms() ? tiles : num_sms();
-    if (xlo) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, grid, st);
-    if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, grid, st);
-    if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, grid, st);
-    return launch_tc_mode<BN, 2>(tB, tBl, tA, tAl, p, grid, st);
+    if (xlo) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, cl, st);
+    if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, cl, st);
+    if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, cl, st);
+    return launch_tc_mode<BN, 2>(tB, tBl, tA, tAl, p, 1, st);
 }
 
 // Tile width from a small cost model fitted to B200 measurements (profiles/r01_tc_gemm_v2_microbench.txt, cycles):

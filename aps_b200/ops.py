@@ -515,7 +515,7 @@ def delta(x: th.Tensor, scale: th.Tensor, order: int, as_channel: bool = False) 
     T, F = x.shape[-2], x.shape[-1]
     rows = x.numel() // (T * F)
     ctx = (scale.numel() - 1) // 2
-    sc = scale.detach().float().contiguous()
+    sc = scale.detach().to(device=dev, dtype=th.float32).contiguous()       # the layer may still live on the host
     K = order + 1
     lib = _lib.load()
     if as_channel:

@@ -84,3 +84,34 @@ os.environ["APS_B200_NO_THIN_CONV"] = "1"
 t_old = timeit(lambda: ops.conv2d_nhwc(xin, w1, b1, stride=(2, 2), padding=(1, 1), act="relu"), 4)
 os.environ.pop("APS_B200_NO_THIN_CONV")
 print(f"front conv1 [64,398,80,1] -> 256 ch: thin3x3 {t_new:7.1f} us, conv2d_narrow {t_old:7.1f} us (521 MB written: {521.6 / t_new * 1e3:6.0f} GB/s)")
+
+# ---- weight-tile multicast across a cluster of CL CTAs (round 2): the key shapes at the tile width the cost model picks
+os.environ.pop("APS_B200_TC_BN", None)
+print("\ncluster size sweep (APS_B200_TC_CL), us per launch")
+print(f"{'shape':22s} {'CL=1':>8s} {'CL=2':>8s} {'CL=4':>8s}")
+xc2 = th.randn(64, 199, 40, 256, device=dev)
+wc2 = th.randn(256, 3, 3, 256, device=dev) / 48
+xc3 = th.randn(64, 100, 20, 256, device=dev)
+bc = th.randn(256, device=dev)
+rows = []
+for name, K, N, act, ks in SHAPES:
+    if "k4" in name or "k8" in name or (name in ("ffn_b", "front")):
+        continue
+    x = th.randn(M, K, device=dev)
+    xl = ops.lo_companion(x)
+    w = th.randn(N, K, device=dev) / K**0.5
+    b = th.randn(N, device=dev)
+    if ks == 1:
+        rows.append((name + " tma", lambda x=x, w=w, b=b, act=act, xl=xl: ops.linear(x, w, b, act=act, cache=cache, x_lo=xl)))
+        rows.append((name + " gather", lambda x=x, w=w, b=b, act=act: ops.linear(x, w, b, act=act, cache=cache)))
+    else:
+        rows.append((name, lambda x=x, w=w, xl=xl, ks=ks: ops.linear(x, w, None, cache=cache, x_lo=xl, ksplit=ks)))
+rows.append(("conv2 3x3 s2 [64,199,40,256]", lambda: ops.conv2d_nhwc(xc2, wc2, bc, stride=(2, 2), padding=(1, 1), act="relu", cache=cache)))
+rows.append(("conv3 3x3 s2 [64,100,20,256]", lambda: ops.conv2d_nhwc(xc3, wc2, bc, stride=(2, 2), padding=(1, 1), act="relu", cache=cache)))
+for name, fn in rows:
+    ts = []
+    for cl in ("1", "2", "4"):
+        os.environ["APS_B200_TC_CL"] = cl
+        ts.append(timeit(fn, 4 if "conv" in name else 20))
+    print(f"{name:22s} {ts[0]:8.1f} {ts[1]:8.1f} {ts[2]:8.1f}")
+os.environ.pop("APS_B200_TC_CL", None)
