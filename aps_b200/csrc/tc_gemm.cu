@@ -50,9 +50,13 @@ constexpr int TC_BM = 128;
 #ifndef APSB_TC_PW_LINEAR
 #define APSB_TC_PW_LINEAR 4
 #endif
-// default cluster size for the weight-tile multicast (1 = off)
+// default cluster size for the weight-tile multicast.  1 = off: MEASURED SLOWER on every shape of the encoder (B200,
+// profiles/r02h_tc_cluster_sweep.txt: conv2 850 / 1065 / 1198 us and FFN-a 31.1 / 32.0 / 39.2 us at CL = 1 / 2 / 4) — the
+// lock step couples the CTAs' pipelines (a stage is refilled only when the SLOWEST CTA has consumed it) and that costs
+// more than the halved L2 -> SM weight traffic saves, i.e. the engine is not bound by that traffic.  The path stays
+// (numerics verified for CL = 1, 2, 4) behind APS_B200_TC_CL for shapes where it might pay.
 #ifndef APSB_TC_CLUSTER
-#define APSB_TC_CLUSTER 2
+#define APSB_TC_CLUSTER 1
 #endif
 // MODE 3 (linear layer whose activation comes with its TF32 "lo" companion, see below) has NO producer warps: the TMA
 // warp loads the A tiles as well.

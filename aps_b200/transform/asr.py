@@ -132,7 +132,8 @@ class SpeedPerturbTransform(_Layer):
         if self.last_choice is None or inp_len is None:
             return inp_len
         c = self.last_choice
-        return th.div(inp_len, self.src_sr[c], rounding_mode="trunc") * self.dst_sr[c]
+        src, dst = self.src_sr.to(inp_len.device)[c.to(inp_len.device)], self.dst_sr.to(inp_len.device)[c.to(inp_len.device)]
+        return th.div(inp_len, src, rounding_mode="trunc") * dst
 
     @staticmethod
     def _resample(wav: th.Tensor, weight: th.Tensor) -> th.Tensor:

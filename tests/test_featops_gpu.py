@@ -76,7 +76,7 @@ def test_specaug_apply_kernel(mask_zero):
         m = mask if x.dim() == 3 else mask.unsqueeze(1)
         ref = x * m if mask_zero else th.masked_fill(x, m == 0, x.mean())
         assert rel_err(got, ref) < 1e-6
-        assert rel_err(got, O.specaug_apply(x, m, mask_zero)) < 1e-6
+        assert rel_err(got, O.specaug_apply(x, mask, mask_zero)) < 1e-6
         if mask_zero:
             assert th.equal(got.cpu(), ref)
 
