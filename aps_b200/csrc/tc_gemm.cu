@@ -217,6 +217,20 @@ __device__ __forceinline__ float tc_act(float v, float slope) {
     return v;
 }
 
+// 16-byte shared-memory accesses on a 32-bit shared-window address.  Through the generic pointer the compiler emitted
+// LD.E.128 / ST.E.128 with 64-bit addresses AND kept every read-back behind the previous row's global store (it cannot
+// prove that the output does not alias the tile): ncu source view of the FFN-a kernel, r02j — eight serialised
+// ~200-cycle round trips per 32 x 32 block made the epilogue (14-16 k cycles per 128 x 128 tile) slower than the tile's
+// main loop (10 k).
+__device__ __forceinline__ void tc_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 tc_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // Epilogue arithmetic on 4 consecutive columns of one output row (after the shared-memory transpose, see the epilogue
 // warps): bias / activation / post affine / alpha / residual; the per-column vectors are the lane's own 4 columns.
 template <int ACT>
@@ -702,6 +716,23 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     : "r"(taddr)
                     : "memory");
                 if (ch + 1 < nchunks) fetch_res(ch + 1, res_nxt);
+                // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
+                const int n = n0 + ec;
+                const bool nok = n < p.N;          // N % 4 == 0 (N % 8 for GLU) on the vector path
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
+                if (p.epi_vec && nok) {
+                    if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    if (e.post_scale) {
+                        ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                        pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                    }
+                    if (e.act == ACT_PRELU) {
+                        if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                        else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+                    }
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ch == nchunks - 1) {           // last read of this accumulator buffer: hand it back to the MMA warp
                     tc_fence_before();
@@ -712,20 +743,25 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 if (p.epi_vec) {
                     // ---- transpose: lane = row -> lane = (row group, 4 columns) ----
                     __syncwarp();                  // the previous chunk's reads of the tile are done
+                    const uint32_t ts_w = s_u32(tile_s) + (uint32_t)lane * 144u;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
-                        *reinterpret_cast<uint4*>(tile_s + lane * 36 + 4 * j4) =
-                            make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                        tc_sts128(ts_w + 16u * j4, r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
                     __syncwarp();
-                    const int n = n0 + ec;
-                    const bool nok = n < p.N;      // N % 4 == 0 (N % 8 for GLU) on this path
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e.bias && nok && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    // the rows of this lane come back four at a time BEFORE any arithmetic or global store of the group
+                    const uint32_t ts_r = s_u32(tile_s) + (uint32_t)er * 144u + (uint32_t)ec * 4u;
+                    float4 tv[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tv[i] = tc_lds128(ts_r + (uint32_t)i * (4u * 144u));
                     if (glu) {
                         // columns (2j, 2j+1) -> output column j: this lane's 4 columns give 2 outputs
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 v = *reinterpret_cast<const float4*>(tile_s + (er + 4 * i) * 36 + ec);
+                            if (i == 4) {
+#pragma unroll
+                                for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u));
+                            }
+                            const float4 v = tv[i];
                             float2 o;
                             o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
                             o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
@@ -734,21 +770,13 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             if (nok && mr[i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[i] * e.ldo + (n >> 1)) = o;
                         }
                     } else {
-                        float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
-                        if (e.post_scale && nok) {
-                            ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
-                            pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
-                        }
-                        if (e.act == ACT_PRELU && nok) {
-                            if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
-                            else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
-                        }
 #define TC_EPI_CASE(A)                                                                                                  \
     case A:                                                                                                             \
         _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                                                 \
-            const float4 v = *reinterpret_cast<const float4*>(tile_s + (er + 4 * i) * 36 + ec);                         \
-            const float4 o = tc_epilogue4<A>(v, b4, ps4, pt4, sl4, res_cur[i], e.alpha, e.beta);                        \
+            if (i == 4) {                                                                                               \
+                _Pragma("unroll") for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u)); \
+            }                                                                                                           \
+            const float4 o = tc_epilogue4<A>(tv[i], b4, ps4, pt4, sl4, res_cur[i], e.alpha, e.beta);                    \
             if (nok && mr[i] >= 0) {                                                                                    \
                 *reinterpret_cast<float4*>(eout + (long long)mr[i] * e.ldo + n) = o;                                               \
                 if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[i] * e.ldo + n) = tf32_lo4(o);                   \
