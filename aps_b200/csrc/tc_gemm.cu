@@ -63,7 +63,12 @@ constexpr int TC_BM = 128;
 template <int BN, int MODE> struct TcRoles {
     static constexpr int PW = MODE == 3 ? 0 : (BN > 128 ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
     static constexpr int PRODUCERS = PW * 32;
-    static constexpr int THREADS = (6 + PW) * 32;
+    // epilogue warps: 4 (one per TMEM lane quarter), or 8 in MODE 3 (two per quarter taking alternate 32-column chunks):
+    // a 32 x 32 block costs ~900 dependent-issue-bound instructions, and ONE warp per scheduler cannot hide their
+    // latencies (trace r02k: 11-13 k cycles of epilogue per 128 x 128 tile against a 10 k main loop).  MODE 3 has no
+    // producer warps, so the second set is free.
+    static constexpr int EW = MODE == 3 ? 8 : 4;
+    static constexpr int THREADS = (2 + EW + PW) * 32;
 };
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_PROD0 = 6;
 
@@ -360,7 +365,9 @@ template <int BN> struct TcCfg {
     static constexpr int A_BYTES = TC_BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;      // per epilogue warp: a 32 x 32 block, rows padded to 36 floats
+    // per epilogue warp a 32 x 32 block: rows padded to 36 floats (4 warps), or unpadded with an XOR swizzle of the
+    // 16-byte columns (8 warps, MODE 3) — 8 x 4096 B: the padded form would not fit beside three 64 KB stages
+    static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
 #ifdef APSB_TC_TRACE
     static constexpr int TRACE_BYTES = 8 * 1024;
 #else
@@ -402,7 +409,10 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     pdl_trigger();
     static_assert(CL == 1 || MODE != 2, "row classes of a transposed convolution skip k-blocks per tile: no lock step");
     const unsigned crank = CL > 1 ? tc_cluster_rank() : 0u;
-    const unsigned cid = blockIdx.x / CL, ncl = gridDim.x / CL;       // cluster index / number of clusters
+    // cluster index / number of clusters (macros, not variables: at CL = 1 they are the special registers themselves and
+    // must not occupy two of the 128 registers of the 448-thread variants for the whole kernel)
+#define cid (blockIdx.x / CL)
+#define ncl (gridDim.x / CL)
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     // super tile -> flat tile index of THIS CTA (row block = CL * super row + rank; may lie beyond M: a dummy tile that
     // keeps the lock step, reads zeros and stores nothing)
@@ -479,7 +489,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             }
             for (int b = 0; b < 2; ++b) {
                 tc_mbar_init(tmem_full + b, 1);
-                tc_mbar_init(tmem_empty + b, 4);
+                tc_mbar_init(tmem_empty + b, TcRoles<BN, MODE>::EW);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -628,13 +638,20 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 TC_TR(3);
             }
         }
-    } else if (warp < WARP_PROD0) {
+    } else if (warp < WARP_EPI0 + TcRoles<BN, MODE>::EW) {
         // ================= epilogue warps 2..5: TMEM lane quarter = warp % 4 =================
         // Fast path (p.epi_vec: 16-byte aligned output / residual rows, N % 4 == 0): lane = row straight out of TMEM,
         // vector loads / stores on the lane's own row.  Fallback (e.g. N = 257 mask rows): the 32x32 block is transposed
         // through a padded shared tile so that lane = column and the scalar accesses are still 128-byte rows.
         const int q = warp & 3;
-        float* tile_s = epi_tiles + (warp - WARP_EPI0) * (32 * 36);
+        constexpr bool EW8 = TcRoles<BN, MODE>::EW == 8;
+        const int ehalf = EW8 ? ((warp - WARP_EPI0) >> 2) : 0;     // which of the two warps of this lane quarter
+        constexpr int ESTEP = EW8 ? 2 : 1;                         // chunks are dealt out alternately
+        float* tile_s = epi_tiles + (warp - WARP_EPI0) * (EW8 ? 32 * 32 : 32 * 36);
+        // byte offset of the 16-byte column c4 of row r in the warp's tile
+        auto ts_off = [&](uint32_t r, uint32_t c4) -> uint32_t {
+            return EW8 ? r * 128u + ((c4 ^ (r & 7u)) << 4) : r * 144u + (c4 << 4);
+        };
         const Epilogue& e = p.e;
         const bool glu = e.act == ACT_GLU;
         uint32_t tcount = 0;
@@ -690,13 +707,18 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 }
             };
             // the first residual chunk is requested BEFORE the wait, i.e. while the tile's main loop is still running
-            fetch_res(0, res_nxt);
+            fetch_res(ehalf, res_nxt);
             if (lane == 0) tc_mbar_wait_parked(tmem_full + buf, (tcount >> 1) & 1);
             __syncwarp();
             tc_fence_after();
             if (threadIdx.x == 64) TC_TR(4);
+            if (EW8 && ehalf >= nchunks) {         // nothing for this warp in a one-chunk tile: just hand the buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
+            }
 #pragma unroll 1
-            for (int ch = 0; ch < nchunks; ++ch) {
+            for (int ch = ehalf; ch < nchunks; ch += ESTEP) {
                 const int c0 = ch * 32;
                 const int n0 = n_blk * BN + c0;
                 uint32_t r[32];
@@ -715,71 +737,78 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                       "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr)
                     : "memory");
-                if (ch + 1 < nchunks) fetch_res(ch + 1, res_nxt);
+                if (ch + ESTEP < nchunks) fetch_res(ch + ESTEP, res_nxt);
                 // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
                 const int n = n0 + ec;
                 const bool nok = n < p.N;          // N % 4 == 0 (N % 8 for GLU) on the vector path
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
-                if (p.epi_vec && nok) {
-                    if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-                    if (e.post_scale) {
-                        ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
-                        pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                constexpr bool LEAN = TcRoles<BN, MODE>::THREADS > 400;   // 128-register variants: load them late instead
+                auto load_cols = [&]() {
+                    if ((MODE == 3 || p.epi_vec) && nok) {
+                        if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                        if (e.post_scale) {
+                            ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                            pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                        }
+                        if (e.act == ACT_PRELU) {
+                            if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                            else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+                        }
                     }
-                    if (e.act == ACT_PRELU) {
-                        if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
-                        else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
-                    }
-                }
+                };
+                if (!LEAN) load_cols();
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (ch == nchunks - 1) {           // last read of this accumulator buffer: hand it back to the MMA warp
+                if (ch + ESTEP >= nchunks) {       // this warp's last read of the accumulator buffer: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
                     if (threadIdx.x == 64) TC_TR(5);
                 }
-                if (p.epi_vec) {
+                if (MODE == 3 || p.epi_vec) {      // MODE 3 is only launched with the vector epilogue (host check)
                     // ---- transpose: lane = row -> lane = (row group, 4 columns) ----
                     __syncwarp();                  // the previous chunk's reads of the tile are done
-                    const uint32_t ts_w = s_u32(tile_s) + (uint32_t)lane * 144u;
+                    const uint32_t ts_b = s_u32(tile_s);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
-                        tc_sts128(ts_w + 16u * j4, r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                        tc_sts128(ts_b + ts_off((uint32_t)lane, (uint32_t)j4), r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
                     __syncwarp();
-                    // the rows of this lane come back four at a time BEFORE any arithmetic or global store of the group
-                    const uint32_t ts_r = s_u32(tile_s) + (uint32_t)er * 144u + (uint32_t)ec * 4u;
-                    float4 tv[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) tv[i] = tc_lds128(ts_r + (uint32_t)i * (4u * 144u));
+                    // the rows of this lane come back GRP at a time BEFORE the arithmetic and global stores of the group
+                    // (1 in the 448-thread variants, whose 128-register budget is taken by the producers' gather ring)
+                    constexpr int GRP = LEAN ? 1 : 4;
+                    if (LEAN) load_cols();
                     if (glu) {
                         // columns (2j, 2j+1) -> output column j: this lane's 4 columns give 2 outputs
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i == 4) {
+                        for (int g = 0; g < 8; g += GRP) {
+                            float4 tv[GRP];
 #pragma unroll
-                                for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u));
+                            for (int i = 0; i < GRP; ++i) tv[i] = tc_lds128(ts_b + ts_off((uint32_t)(er + 4 * (g + i)), (uint32_t)(ec >> 2)));
+#pragma unroll
+                            for (int i = 0; i < GRP; ++i) {
+                                const float4 v = tv[i];
+                                float2 o;
+                                o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
+                                o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
+                                o.x = fmaf(e.beta, res_cur[g + i].x, o.x);
+                                o.y = fmaf(e.beta, res_cur[g + i].y, o.y);
+                                if (nok && mr[g + i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[g + i] * e.ldo + (n >> 1)) = o;
                             }
-                            const float4 v = tv[i];
-                            float2 o;
-                            o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
-                            o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
-                            o.x = fmaf(e.beta, res_cur[i].x, o.x);
-                            o.y = fmaf(e.beta, res_cur[i].y, o.y);
-                            if (nok && mr[i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[i] * e.ldo + (n >> 1)) = o;
                         }
                     } else {
 #define TC_EPI_CASE(A)                                                                                                  \
     case A:                                                                                                             \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                                                 \
-            if (i == 4) {                                                                                               \
-                _Pragma("unroll") for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u)); \
-            }                                                                                                           \
-            const float4 o = tc_epilogue4<A>(tv[i], b4, ps4, pt4, sl4, res_cur[i], e.alpha, e.beta);                    \
-            if (nok && mr[i] >= 0) {                                                                                    \
-                *reinterpret_cast<float4*>(eout + (long long)mr[i] * e.ldo + n) = o;                                               \
-                if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[i] * e.ldo + n) = tf32_lo4(o);                   \
+        _Pragma("unroll") for (int g = 0; g < 8; g += GRP) {                                                            \
+            float4 tv[GRP];                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < GRP; ++i)                                                             \
+                tv[i] = tc_lds128(ts_b + ts_off((uint32_t)(er + 4 * (g + i)), (uint32_t)(ec >> 2)));                    \
+            _Pragma("unroll") for (int i = 0; i < GRP; ++i) {                                                           \
+                const float4 o = tc_epilogue4<A>(tv[i], b4, ps4, pt4, sl4, res_cur[g + i], e.alpha, e.beta);            \
+                if (nok && mr[g + i] >= 0) {                                                                            \
+                    *reinterpret_cast<float4*>(eout + (long long)mr[g + i] * e.ldo + n) = o;                            \
+                    if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[g + i] * e.ldo + n) = tf32_lo4(o); \
+                }                                                                                                       \
             }                                                                                                           \
         }                                                                                                               \
         break;
@@ -796,7 +825,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         }
 #undef TC_EPI_CASE
                     }
-                } else {
+                } else if constexpr (MODE != 3) {
                     // ---- transposed scalar fallback (unaligned rows) ----
                     __syncwarp();
 #pragma unroll
@@ -1130,6 +1159,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                      : "memory");
     }
 }
+#undef cid
+#undef ncl
 
 __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ x, long long ldx,
                                                          float* __restrict__ hi, float* __restrict__ lo,
@@ -1334,7 +1365,9 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     p.dbg = getenv("APS_B200_TC_DBG") ? atoi(getenv("APS_B200_TC_DBG")) : 0;
     p.e.dbg_nobias = (p.dbg & 128) ? 1 : 0;
 #endif
-    if (xlo) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, cl, st);
+    APSB_CHECK_ARG(!(xlo && p.ksplit > 1 && !p.epi_vec), "split-K needs 16-byte aligned partial rows (N %% 4 == 0)");
+    // the TMA-fed kernel has the vector epilogue only: unaligned outputs take the gather-fed kernel and its scalar path
+    if (xlo && p.epi_vec) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, cl, st);
     return launch_tc_mode<BN, 2>(tB, tBl, tA, tAl, p, 1, st);
