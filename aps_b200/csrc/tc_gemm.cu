@@ -357,7 +357,7 @@ static int g_tc_trace_cap = 0;
 
 // BN = 256 uses 16-float k-blocks (64-byte swizzle) so that FOUR 48 KB stages fit: with 32-float blocks only two
 // 96 KB stages fit and neither the TMA weight loads nor the A gathers can run far enough ahead of the MMAs.
-template <int BN> struct TcCfg {
+template <int BN, int MODE = 0> struct TcCfg {
     static constexpr int BK = BN == 256 ? 16 : 32;
     static constexpr int SWZ = BK * 4;                                          // bytes per operand row = swizzle span
     // BN = 64 keeps one stage less than would fit: the 48 KB it leaves become L1, which serves the kw reuse of the gathers
@@ -366,8 +366,10 @@ template <int BN> struct TcCfg {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     // per epilogue warp a 32 x 32 block: rows padded to 36 floats (4 warps), or unpadded with an XOR swizzle of the
-    // 16-byte columns (8 warps, MODE 3) — 8 x 4096 B: the padded form would not fit beside three 64 KB stages
-    static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
+    // 16-byte columns (8 warps, MODE 3) — 8 x 4096 B: the padded form would not fit beside three 64 KB stages.  The
+    // gather modes keep the small allocation: every KB of shared memory they do not claim stays L1 for the im2col
+    // gathers (conv2 went 848 -> 1071 us when this was 32 KB for every mode).
+    static constexpr int EPI_BYTES = MODE == 3 ? 8 * 32 * 32 * 4 : 4 * 32 * 36 * 4;
 #ifdef APSB_TC_TRACE
     static constexpr int TRACE_BYTES = 8 * 1024;
 #else
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                    const __grid_constant__ TcParams p) {
-    using C = TcCfg<BN>;
+    using C = TcCfg<BN, MODE>;
     constexpr int S = C::STAGES, BK = C::BK, SWZ = C::SWZ, A_BYTES = C::A_BYTES;
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
@@ -1251,7 +1253,7 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
 template <int BN, int MODE, int CL>
 static int launch_tc_cl(const CUtensorMap& tB, const CUtensorMap& tBl, const CUtensorMap& tA, const CUtensorMap& tAl,
                         TcParams p, cudaStream_t st) {
-    using C = TcCfg<BN>;
+    using C = TcCfg<BN, MODE>;
     static bool attr_done[64] = {false};       // function attributes are per device (one context per GPU)
     static int max_clusters[64] = {0};
     int dev = 0;
@@ -1389,16 +1391,25 @@ static int run_tc(const AGather& a, const float* W, const float* Wlo, long long 
         const int cand[3] = {256, 128, 64};
         // cycles per unit of k in the main loop: gather-fed tiles are bound by the producer warps (~the same time per
         // k-block whatever the width), TMA-fed tiles (MODE 3) by the MMAs and the shared-memory operand traffic
-        const double per_k_gather[3] = {87.0, 64.0, 53.0}, per_k_tma[3] = {60.0, 36.0, 26.0};
-        const double* per_k = xlo ? per_k_tma : per_k_gather;
+        // TMA-fed tiles (MODE 3): fitted to the round-2 trace / microbenchmark (profiles/r02l_tc_mode3_microbench.txt):
+        // the main loop is bound by shared-memory operand traffic (~1170 / 1250 / 1700 cycles per 32 k at 64 / 128 / 256
+        // columns), the pipeline runs on across tiles (one fill per launch), eight epilogue warps take ~1400 cycles per
+        // 32 columns and overlap the next tile
+        const double per_k_gather[3] = {87.0, 64.0, 53.0}, per_k_tma[3] = {53.0, 39.0, 37.0};
         if (ksplit > 1) K = (K + ksplit - 1) / ksplit;
         double best = 0.0;
         for (int i = 0; i < 3; ++i) {
             if (cand[i] > 64 && N <= cand[i] / 2) continue;       // more than half of the tile would be padding
             const long long tiles = tm * ((N + cand[i] - 1) / cand[i]) * (ksplit > 1 ? ksplit : 1);
             const double waves = (double)((tiles + sms - 1) / sms);
-            const double main_c = (double)K * per_k[i] + 5000.0, epi_c = 4000.0 * (cand[i] / 32);
-            const double t = main_c + (waves - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
+            double t;
+            if (xlo) {
+                const double kc = (double)K * per_k_tma[i], epi_c = 1400.0 * (cand[i] / 32);
+                t = 4000.0 + (waves - 1.0) * (kc > epi_c ? kc : epi_c) + kc + epi_c;
+            } else {
+                const double main_c = (double)K * per_k_gather[i] + 5000.0, epi_c = 4000.0 * (cand[i] / 32);
+                t = main_c + (waves - 1.0) * (main_c > epi_c ? main_c : epi_c) + epi_c;
+            }
             if (bn == 0 || t < best) { best = t; bn = cand[i]; }
         }
     }
