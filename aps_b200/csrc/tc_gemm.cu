@@ -411,10 +411,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     pdl_trigger();
     static_assert(CL == 1 || MODE != 2, "row classes of a transposed convolution skip k-blocks per tile: no lock step");
     const unsigned crank = CL > 1 ? tc_cluster_rank() : 0u;
-    // cluster index / number of clusters (macros, not variables: at CL = 1 they are the special registers themselves and
-    // must not occupy two of the 128 registers of the 448-thread variants for the whole kernel)
-#define cid (blockIdx.x / CL)
-#define ncl (gridDim.x / CL)
+    const unsigned cid = blockIdx.x / CL, ncl = gridDim.x / CL;       // cluster index / number of clusters
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     // super tile -> flat tile index of THIS CTA (row block = CL * super row + rank; may lie beyond M: a dummy tile that
     // keeps the lock step, reads zeros and stores nothing)
@@ -740,6 +737,10 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     : "r"(taddr)
                     : "memory");
                 if (ch + ESTEP < nchunks) fetch_res(ch + ESTEP, res_nxt);
+                // Two textually separate bodies on purpose: the gather-fed instantiations (MODE 0-2) keep the exact
+                // code they were tuned with — their producer warps are instruction-fetch sensitive and the layout of this
+                // function moved conv2 by 26 % (844 -> 1068 us) when the 8-warp variant shared the code below.
+                if constexpr (MODE == 3) {
                 // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
                 const int n = n0 + ec;
                 const bool nok = n < p.N;          // N % 4 == 0 (N % 8 for GLU) on the vector path
@@ -827,7 +828,110 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         }
 #undef TC_EPI_CASE
                     }
-                } else if constexpr (MODE != 3) {
+                }
+                } else {
+                // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
+                const int n = n0 + ec;
+                const bool nok = n < p.N;          // N % 4 == 0 (N % 8 for GLU) on the vector path
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 ps4 = make_float4(1.f, 1.f, 1.f, 1.f), pt4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
+                // the 448-thread variants (8 producer warps, 128 registers) request these AFTER the transposition and read
+                // the tile back one row at a time: the early / batched form spills there (DCCRN 43.6 -> 45.9 ms)
+                constexpr bool LEAN = TcRoles<BN, MODE>::THREADS > 400;
+                if (!LEAN && p.epi_vec && nok) {
+                    if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    if (e.post_scale) {
+                        ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                        pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                    }
+                    if (e.act == ACT_PRELU) {
+                        if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                        else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ch == nchunks - 1) {           // last read of this accumulator buffer: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
+                    if (threadIdx.x == 64) TC_TR(5);
+                }
+                if (p.epi_vec) {
+                    // ---- transpose: lane = row -> lane = (row group, 4 columns) ----
+                    __syncwarp();                  // the previous chunk's reads of the tile are done
+                    const uint32_t ts_w = s_u32(tile_s) + (uint32_t)lane * 144u;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        tc_sts128(ts_w + 16u * j4, r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                    __syncwarp();
+                    // the rows of this lane come back four at a time BEFORE any arithmetic or global store of the group
+                    const uint32_t ts_r = s_u32(tile_s) + (uint32_t)er * 144u + (uint32_t)ec * 4u;
+                    float4 tv[8];
+                    if constexpr (LEAN) {
+                        if (nok) {
+                            if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                            if (e.post_scale) {
+                                ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
+                                pt4 = __ldg(reinterpret_cast<const float4*>(e.post_shift + n));
+                            }
+                            if (e.act == ACT_PRELU) {
+                                if (e.slope_stride) sl4 = __ldg(reinterpret_cast<const float4*>(e.slope + n));
+                                else { const float s0 = __ldg(e.slope); sl4 = make_float4(s0, s0, s0, s0); }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tv[i] = tc_lds128(ts_r + (uint32_t)i * (4u * 144u));
+                    }
+                    if (glu) {
+                        // columns (2j, 2j+1) -> output column j: this lane's 4 columns give 2 outputs
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if constexpr (LEAN) {
+                                tv[i] = tc_lds128(ts_r + (uint32_t)i * (4u * 144u));
+                            } else if (i == 4) {
+#pragma unroll
+                                for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u));
+                            }
+                            const float4 v = tv[i];
+                            float2 o;
+                            o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
+                            o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
+                            o.x = fmaf(e.beta, res_cur[i].x, o.x);
+                            o.y = fmaf(e.beta, res_cur[i].y, o.y);
+                            if (nok && mr[i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[i] * e.ldo + (n >> 1)) = o;
+                        }
+                    } else {
+#define TC_EPI_CASE(A)                                                                                                  \
+    case A:                                                                                                             \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                                                 \
+            if constexpr (LEAN) {                                                                                       \
+                tv[i] = tc_lds128(ts_r + (uint32_t)i * (4u * 144u));                                                    \
+            } else if (i == 4) {                                                                                        \
+                _Pragma("unroll") for (int i2 = 4; i2 < 8; ++i2) tv[i2] = tc_lds128(ts_r + (uint32_t)i2 * (4u * 144u)); \
+            }                                                                                                           \
+            const float4 o = tc_epilogue4<A>(tv[i], b4, ps4, pt4, sl4, res_cur[i], e.alpha, e.beta);                    \
+            if (nok && mr[i] >= 0) {                                                                                    \
+                *reinterpret_cast<float4*>(eout + (long long)mr[i] * e.ldo + n) = o;                                               \
+                if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[i] * e.ldo + n) = tf32_lo4(o);                   \
+            }                                                                                                           \
+        }                                                                                                               \
+        break;
+                        switch (e.act) {
+                            TC_EPI_CASE(ACT_RELU)
+                            TC_EPI_CASE(ACT_SWISH)
+                            TC_EPI_CASE(ACT_TANH)
+                            TC_EPI_CASE(ACT_SIGMOID)
+                            TC_EPI_CASE(ACT_PRELU)
+                            TC_EPI_CASE(ACT_LEAKY)
+                            TC_EPI_CASE(ACT_GELU)
+                            default:
+                            TC_EPI_CASE(ACT_NONE)
+                        }
+#undef TC_EPI_CASE
+                    }
+                } else {
                     // ---- transposed scalar fallback (unaligned rows) ----
                     __syncwarp();
 #pragma unroll
@@ -876,6 +980,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     }
                     __syncwarp();                  // tile_s is reused by the next chunk
                 }
+                }   // MODE != 3
             }
             if (threadIdx.x == 64) TC_TR(6);
         }
@@ -1161,8 +1266,6 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                      : "memory");
     }
 }
-#undef cid
-#undef ncl
 
 __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ x, long long ldx,
                                                          float* __restrict__ hi, float* __restrict__ lo,
