@@ -411,7 +411,15 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     pdl_trigger();
     static_assert(CL == 1 || MODE != 2, "row classes of a transposed convolution skip k-blocks per tile: no lock step");
     const unsigned crank = CL > 1 ? tc_cluster_rank() : 0u;
-    const unsigned cid = blockIdx.x / CL, ncl = gridDim.x / CL;       // cluster index / number of clusters
+    // cluster index / number of clusters.  Code generation of this 35 k-instruction function is touchy (measured, B200,
+    // same-box A/B of library builds): with these two values in registers and the first epilogue body below the
+    // 256-wide im2col kernel of the conformer front runs conv2 in 844 us, with the special registers re-read and the
+    // second body in 1068 us (+26 %) — while every other gather-fed instantiation (DCCRN's convolutions and transposed
+    // convolutions: 23.9 vs 26.6 ms for the 18 launches of a step) prefers exactly the opposite.  Each gets its form.
+    constexpr bool KFORM = MODE == 1 && BN == 256;    // the conformer-front convolutions: see the epilogue
+    const unsigned cid_v = blockIdx.x / CL, ncl_v = gridDim.x / CL;
+#define cid (KFORM ? cid_v : blockIdx.x / CL)
+#define ncl (KFORM ? ncl_v : gridDim.x / CL)
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     // super tile -> flat tile index of THIS CTA (row block = CL * super row + rank; may lie beyond M: a dummy tile that
     // keeps the lock step, reads zeros and stores nothing)
@@ -737,10 +745,9 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     : "r"(taddr)
                     : "memory");
                 if (ch + ESTEP < nchunks) fetch_res(ch + ESTEP, res_nxt);
-                // Two textually separate bodies on purpose: the gather-fed instantiations (MODE 0-2) keep the exact
-                // code they were tuned with — their producer warps are instruction-fetch sensitive and the layout of this
-                // function moved conv2 by 26 % (844 -> 1068 us) when the 8-warp variant shared the code below.
-                if constexpr (MODE == 3) {
+                // Two textually separate bodies on purpose (see KFORM above): the producer warps of the gather-fed
+                // instantiations are instruction-fetch sensitive and the layout of this function decides their speed.
+                if constexpr (!KFORM) {
                 // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
                 const int n = n0 + ec;
                 const bool nok = n < p.N;          // N % 4 == 0 (N % 8 for GLU) on the vector path
@@ -1266,6 +1273,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                      : "memory");
     }
 }
+#undef cid
+#undef ncl
 
 __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ x, long long ldx,
                                                          float* __restrict__ hi, float* __restrict__ lo,
