@@ -82,9 +82,20 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* __restrict
     for (int j = 0; j < VPL; ++j) {
         const int d = 4 * lane + 128 * j;
         float4 a = __ldg(reinterpret_cast<const float4*>(x + m * ldx + d));
-        for (int p = 1; p < nparts; ++p) {                 // fixed order: deterministic
-            const float4 b = __ldg(reinterpret_cast<const float4*>(x + p * part_stride + m * ldx + d));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (nparts > 1) {
+            // split-K slices: all loads first (up to 7 in flight instead of one L2 round trip per slice), then the adds in
+            // slice order — deterministic, and x + 0 leaves the sum of a shorter split untouched
+            float4 b[7];
+#pragma unroll
+            for (int p = 1; p < 8; ++p)
+                b[p - 1] = p < nparts ? __ldg(reinterpret_cast<const float4*>(x + p * part_stride + m * ldx + d))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < 7; ++p) { a.x += b[p].x; a.y += b[p].y; a.z += b[p].z; a.w += b[p].w; }
+            for (int p = 8; p < nparts; ++p) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(x + p * part_stride + m * ldx + d));
+                a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+            }
         }
         if (bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(bias + d));
@@ -360,10 +371,11 @@ __global__ void __launch_bounds__(kAttnWarps * 32) mhsa_kernel(const __grid_cons
 // position term q . R[j - i + L - 1] (the reference's pad / transpose skew, utils.py:14-39) needs rows
 // (tx - ty) + 16 (b - a) + 63 of the staged window of R: 7 distinct rows per thread.  P . V is tiled the same way
 // (queries ty + 16a, 4 head dims per thread).  Same arithmetic order per row whatever the batch.
-constexpr int kTQ = 64, kTK = 64;
-
-template <int DH>
+// NT = tile edge / 16: 4 in general, 3 (48 x 48) when the whole sequence fits one such tile — the BASELINE encoder has
+// L = 48, where a 64 x 64 tile spends 44 % of its FMAs on padding.  One tile either way, so the order of every sum is the same.
+template <int DH, int NT>
 __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int kTQ = 16 * NT, kTK = 16 * NT;
     constexpr int LD = DH + 4;              // floats per staged row: 16-byte aligned, conflict free for 8 consecutive rows
     constexpr int C4 = DH / 4;
     extern __shared__ float4 attn_smem4[];
@@ -398,9 +410,9 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
     }
     if (tid < kTQ) { sMax[tid] = -INFINITY; sSum[tid] = 0.f; }
     const float* sQq = p.mode == 2 ? sQp : sQ;
-    float acc[4][4];
+    float acc[NT][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
 
@@ -432,51 +444,51 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
         }
         __syncthreads();
         // ---- scores: s[a][b] = q[ty + 16a] . k[tx + 16b] (+ position term) ----
-        float s[4][4];
+        float s[NT][NT];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < NT; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) s[a][b] = 0.f;
-        const int wbase = tx - ty + (kTQ - 1) - 48;      // window row of (a, b): wbase + 16 (b - a + 3)
+            for (int b = 0; b < NT; ++b) s[a][b] = 0.f;
+        const int wbase = tx - ty + (kTQ - 1) - 16 * (NT - 1);      // window row of (a, b): wbase + 16 (b - a + NT - 1)
 #pragma unroll 2
         for (int d = 0; d < DH; d += 4) {
-            float4 q4[4], k4[4];
+            float4 q4[NT], k4[NT];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) q4[a] = *reinterpret_cast<const float4*>(sQ + (ty + 16 * a) * LD + d);
+            for (int a = 0; a < NT; ++a) q4[a] = *reinterpret_cast<const float4*>(sQ + (ty + 16 * a) * LD + d);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) k4[b] = *reinterpret_cast<const float4*>(sK + (tx + 16 * b) * LD + d);
+            for (int b = 0; b < NT; ++b) k4[b] = *reinterpret_cast<const float4*>(sK + (tx + 16 * b) * LD + d);
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NT; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
+                for (int b = 0; b < NT; ++b)
                     s[a][b] = fmaf(q4[a].x, k4[b].x, fmaf(q4[a].y, k4[b].y, fmaf(q4[a].z, k4[b].z, fmaf(q4[a].w, k4[b].w, s[a][b]))));
             if (p.mode) {
-                float4 r4[7];
+                float4 r4[2 * NT - 1];
 #pragma unroll
-                for (int c = 0; c < 7; ++c) {
+                for (int c = 0; c < 2 * NT - 1; ++c) {
                     const int w = wbase + 16 * c;
                     r4[c] = (w >= 0 && w < kTQ + kTK - 1) ? *reinterpret_cast<const float4*>(sR + w * LD + d)
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (p.mode == 2) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) q4[a] = *reinterpret_cast<const float4*>(sQq + (ty + 16 * a) * LD + d);
+                    for (int a = 0; a < NT; ++a) q4[a] = *reinterpret_cast<const float4*>(sQq + (ty + 16 * a) * LD + d);
                 }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < NT; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float4 r = r4[b - a + 3];
+                    for (int b = 0; b < NT; ++b) {
+                        const float4 r = r4[b - a + NT - 1];
                         s[a][b] = fmaf(q4[a].x, r.x, fmaf(q4[a].y, r.y, fmaf(q4[a].z, r.z, fmaf(q4[a].w, r.w, s[a][b]))));
                     }
             }
         }
         __syncthreads();                    // every thread is done with the key tile: it becomes the score tile
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < NT; ++a) {
             const int i = i0 + ty + 16 * a;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < NT; ++b) {
                 const int j = j0 + tx + 16 * b;
                 float v = -INFINITY;
                 if (i < L && j < L) {
@@ -490,9 +502,9 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
         __syncthreads();
         // ---- streaming softmax: warp w owns rows 8w .. 8w+7, lane = keys lane, lane + 32 ----
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = warp * 8 + rr;
-            const float v0 = sS[r * LD + lane], v1 = sS[r * LD + lane + 32];
+        for (int rr = 0; rr < kTQ / 8; ++rr) {
+            const int r = warp * (kTQ / 8) + rr;
+            const float v0 = sS[r * LD + lane], v1 = (lane + 32 < kTK) ? sS[r * LD + lane + 32] : -INFINITY;
             float tmax = fmaxf(v0, v1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
             sS[r * LD + lane] = p0;
-            sS[r * LD + lane + 32] = p1;
+            if (lane + 32 < kTK) sS[r * LD + lane + 32] = p1;
             if (lane == 0) {
                 const float corr = (mold == -INFINITY) ? 0.f : __expf(mold - mnew);
                 sCorr[r] = (mnew == -INFINITY) ? 1.f : corr;
@@ -514,20 +526,20 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
         __syncthreads();
         // ---- acc[a][c] += P[ty + 16a][:] . V[:][4tx + c] ----
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < NT; ++a) {
             const float corr = sCorr[ty + 16 * a];
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][c] *= corr;
         }
 #pragma unroll 2
         for (int j = 0; j < kTK; j += 4) {
-            float4 p4[4], v4[4];
+            float4 p4[NT], v4[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) p4[a] = *reinterpret_cast<const float4*>(sS + (ty + 16 * a) * LD + j);
+            for (int a = 0; a < NT; ++a) p4[a] = *reinterpret_cast<const float4*>(sS + (ty + 16 * a) * LD + j);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) v4[jj] = *reinterpret_cast<const float4*>(sV + (j + jj) * LD + 4 * tx);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < NT; ++a) {
                 acc[a][0] = fmaf(p4[a].x, v4[0].x, fmaf(p4[a].y, v4[1].x, fmaf(p4[a].z, v4[2].x, fmaf(p4[a].w, v4[3].x, acc[a][0]))));
                 acc[a][1] = fmaf(p4[a].x, v4[0].y, fmaf(p4[a].y, v4[1].y, fmaf(p4[a].z, v4[2].y, fmaf(p4[a].w, v4[3].y, acc[a][1]))));
                 acc[a][2] = fmaf(p4[a].x, v4[0].z, fmaf(p4[a].y, v4[1].z, fmaf(p4[a].z, v4[2].z, fmaf(p4[a].w, v4[3].z, acc[a][2]))));
@@ -538,7 +550,7 @@ __global__ void __launch_bounds__(256, 2) mhsa_tiled_kernel(const __grid_constan
     // ---- normalise and store (4 consecutive head dims per thread: 16-byte stores) ----
     if (4 * tx < DH) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < NT; ++a) {
             const int i = i0 + ty + 16 * a;
             if (i >= L) continue;
             const float l = sSum[ty + 16 * a];
@@ -670,15 +682,18 @@ static int mhsa_impl(const aps_b200_attn_desc* d, float* out, float* out_lo, int
     const char* force = getenv("APS_B200_MHSA");
     if (p.dh == 64 && (al & 15) == 0 && (lds & 3) == 0 && !(force && force[0] == 's')) {
         constexpr int LD = 64 + 4;
-        const int smem = (kTQ + 2 * kTK + (p.mode ? kTQ + kTK : 0) + (p.mode == 2 ? kTQ : 0)) * LD * 4;
-        static LaunchCache slots[64];
-        LaunchCache& lc = launch_cache(slots);
+        const bool tile64 = getenv("APS_B200_MHSA_TILE64") != nullptr;   // A/B switch
+        const int tile = (p.L <= 48 && !tile64) ? 48 : 64;
+        const int smem = (3 * tile + (p.mode ? 2 * tile : 0) + (p.mode == 2 ? tile : 0)) * LD * 4;
+        static LaunchCache slots[2][64];
+        LaunchCache& lc = launch_cache(slots[tile == 48]);
+        auto kern = tile == 48 ? mhsa_tiled_kernel<64, 3> : mhsa_tiled_kernel<64, 4>;
         if (smem > lc.smem_set) {
-            APSB_CUDA(cudaFuncSetAttribute(mhsa_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            APSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             lc.smem_set = smem;
         }
-        dim3 tg((unsigned)((p.L + kTQ - 1) / kTQ), (unsigned)p.H, (unsigned)p.N);
-        APSB_CUDA(launch_pdl(mhsa_tiled_kernel<64>, tg, dim3(256), (size_t)smem, st, p));
+        dim3 tg((unsigned)((p.L + tile - 1) / tile), (unsigned)p.H, (unsigned)p.N);
+        APSB_CUDA(launch_pdl(kern, tg, dim3(256), (size_t)smem, st, p));
         APSB_LAUNCH_CHECK();
         return 0;
     }

@@ -39,6 +39,7 @@ struct NarrowConvParams {
     int H, W, KH, KW, sh, sw, ph, pw, dh, dw, OH, OW, Cout, Cin;
     long long M;
     Epilogue e;
+    int rw;             // conv2d_thin3x3_kernel: floats per staged input row
 };
 
 // thread = (position, group of 4 output channels), positions walked with 32-bit arithmetic (the first version spent
@@ -109,73 +110,93 @@ __global__ void __launch_bounds__(256) conv2d_narrow_kernel(const __grid_constan
 }
 
 // 3x3 convolution of a 1- or 2-channel image (conv2d front of the encoder: [N, T, 80] -> 256 channels; first DCCRN
-// encoder layer: stacked re/im).  The layer is a pure WRITE-bandwidth problem (521 MB of output for 16 MB of input at
-// B = 64), so everything is arranged around issuing as few instructions per stored float4 as possible: a thread owns 4
-// output channels for its whole life and keeps their 9 * CIN * 4 weights and the bias in REGISTERS; a block walks
-// output rows (nb, oh) — one division per row, none per position — and the lanes of a warp share the position, so the
-// 9 * CIN input loads are warp-uniform L1 hits.  ~70 instructions per 4 outputs instead of the ~130 (+ a run-time
-// activation switch) of conv2d_narrow_kernel, which measured 547 us against an 85 us write bound.
+// encoder layer: stacked re/im).  The layer is a pure WRITE-bandwidth problem (506 MB of output for 8 MB of input at
+// B = 64; a plain fill of that tensor takes 68 us), so everything is arranged around issuing as few instructions per
+// stored float4 as possible: a thread owns 4 output channels for its whole life and keeps their 9 * CIN * 4 weights and
+// the bias in REGISTERS (as f32x2 pairs: FFMA2 halves the FMA issue slots); a block walks output rows (nb, oh).
+// Second version (round 2, visit O: ncu of the first showed 99 instructions per stored float4, 9.7 long-scoreboard
+// stall cycles per issue): the three input rows of an output row are staged in shared memory WITH their zero padding
+// by cp.async one row ahead (double buffer), so the position loop has no bounds test, no predicated global load and
+// no wait on L2 — 6 to 9 shared-memory loads, 18 * CIN FFMA2, the activation and one 16-byte store per position.
+__device__ __forceinline__ unsigned long long thin_pack(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
 template <int CIN, int ACT>
 __global__ void __launch_bounds__(256) conv2d_thin3x3_kernel(const __grid_constant__ NarrowConvParams p) {
     constexpr int K = 9 * CIN;
+    extern __shared__ __align__(16) float thin_rows[];            // [2][3][rw]
     const unsigned groups = (unsigned)p.Cout >> 2;                // power of two <= 256 (host check)
     const unsigned ppb = 256u / groups;                           // position lanes of the block
     const unsigned g = threadIdx.x & (groups - 1), pl = threadIdx.x / groups;
-    float4 w[K];
+    unsigned long long w01[K], w23[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float* wp = p.w + (long long)(4 * g) * K + k;
-        w[k] = make_float4(__ldg(wp), __ldg(wp + K), __ldg(wp + 2 * K), __ldg(wp + 3 * K));
+        w01[k] = thin_pack(__ldg(wp), __ldg(wp + K));
+        w23[k] = thin_pack(__ldg(wp + 2 * K), __ldg(wp + 3 * K));
     }
     const float4 b = p.e.bias ? __ldg(reinterpret_cast<const float4*>(p.e.bias) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned long long b01 = thin_pack(b.x, b.y), b23 = thin_pack(b.z, b.w);
     const unsigned rows = (unsigned)(p.M / p.OW);                 // Nb * OH
     const float alpha = p.e.alpha, leak = p.e.leak;
-    for (unsigned row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int rw = p.rw, wc = p.W * CIN, lead = p.pw * CIN;       // staged row: lead zeros, W * CIN samples, zeros up to rw
+    // stage the 3 input rows of output row `row` into buffer `buf` (asynchronously; padding written as zeros)
+    auto stage = [&](unsigned row, int buf) {
         const unsigned nb = row / (unsigned)p.OH, oh = row - nb * (unsigned)p.OH;
         const int ih0 = (int)oh * p.sh - p.ph;
-        const float* img = p.x + (long long)nb * p.H * p.W * CIN;
-        const float* r[3];
-        bool rv[3];
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int ih = ih0 + kh;
-            rv[kh] = ih >= 0 && ih < p.H;
-            r[kh] = img + (long long)(rv[kh] ? ih : 0) * p.W * CIN;
+        const float* img = p.x + (long long)nb * p.H * wc;
+        float* dst = thin_rows + buf * 3 * rw;
+        for (int i = threadIdx.x; i < 3 * rw; i += 256) {
+            const int kh = i / rw, col = i - kh * rw, ih = ih0 + kh, ic = col - lead;
+            if (ih >= 0 && ih < p.H && ic >= 0 && ic < wc) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(img + (long long)ih * wc + ic) : "memory");
+            } else {
+                dst[i] = 0.f;
+            }
         }
-        // pointers walk with the position lane: the loads below use immediate offsets (no 64-bit address arithmetic per load)
-        const long long xstep = (long long)ppb * p.sw * CIN;
-        const float* px0 = r[0] + ((long long)pl * p.sw - p.pw) * CIN;
-        const float* px1 = r[1] + ((long long)pl * p.sw - p.pw) * CIN;
-        const float* px2 = r[2] + ((long long)pl * p.sw - p.pw) * CIN;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int buf = 0;
+    if (blockIdx.x < rows) stage(blockIdx.x, 0);
+    const int step = (int)ppb * p.sw * CIN;                       // floats between this lane's consecutive positions
+    for (unsigned row = blockIdx.x; row < rows; row += gridDim.x, buf ^= 1) {
+        const unsigned next = row + gridDim.x;
+        if (next < rows) {
+            stage(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                          // this row's samples (and zeros) are visible
+        const float* r0 = thin_rows + buf * 3 * rw + (int)pl * p.sw * CIN;
         float* op = p.e.out + ((long long)row * p.OW + pl) * p.e.ldo + 4 * g;
         const long long ostep = (long long)ppb * p.e.ldo;
-        int iw0 = (int)pl * p.sw - p.pw;
-        for (unsigned ow = pl; ow < (unsigned)p.OW; ow += ppb, px0 += xstep, px1 += xstep, px2 += xstep, op += ostep, iw0 += (int)ppb * p.sw) {
-            float4 a = b;
+        for (unsigned ow = pl; ow < (unsigned)p.OW; ow += ppb, r0 += step, op += ostep) {
+            unsigned long long a01 = b01, a23 = b23;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-                const float* px = kh == 0 ? px0 : (kh == 1 ? px1 : px2);
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const bool ok = rv[kh] && (unsigned)(iw0 + kw) < (unsigned)p.W;
-#pragma unroll
-                    for (int c = 0; c < CIN; ++c) {
-                        const float xv = ok ? __ldg(px + kw * CIN + c) : 0.f;
-                        const float4 wv = w[(kh * 3 + kw) * CIN + c];
-                        a.x = fmaf(xv, wv.x, a.x); a.y = fmaf(xv, wv.y, a.y);
-                        a.z = fmaf(xv, wv.z, a.z); a.w = fmaf(xv, wv.w, a.w);
-                    }
+                for (int t = 0; t < 3 * CIN; ++t) {
+                    const float xv = r0[kh * rw + t];
+                    const unsigned long long x2 = thin_pack(xv, xv);
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a01) : "l"(x2), "l"(w01[kh * 3 * CIN + t]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a23) : "l"(x2), "l"(w23[kh * 3 * CIN + t]));
                 }
             }
+            float4 a = make_float4(__uint_as_float((unsigned)a01), __uint_as_float((unsigned)(a01 >> 32)),
+                                   __uint_as_float((unsigned)a23), __uint_as_float((unsigned)(a23 >> 32)));
             if (ACT == ACT_RELU) {
                 a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
             } else if (ACT == ACT_LEAKY) {
                 a.x = a.x >= 0.f ? a.x : a.x * leak; a.y = a.y >= 0.f ? a.y : a.y * leak;
                 a.z = a.z >= 0.f ? a.z : a.z * leak; a.w = a.w >= 0.f ? a.w : a.w * leak;
             }
-            a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+            if (alpha != 1.f) { a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha; }
             *reinterpret_cast<float4*>(op) = a;
         }
+        __syncthreads();                                          // the buffer is free for the row after next
     }
 }
 
@@ -493,7 +514,9 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
         if (thin) {
             const long long rows = batch * OH;
             const unsigned tg = (unsigned)(rows < (long long)num_sms() * 3 ? rows : (long long)num_sms() * 3);
-#define APSB_THIN(CI, A) conv2d_thin3x3_kernel<CI, A><<<tg, 256, 0, st>>>(c)
+            c.rw = (int)(((width + 2 * pad_w) * in_channels + 3) & ~3LL);
+            const size_t tsm = (size_t)2 * 3 * c.rw * sizeof(float);
+#define APSB_THIN(CI, A) conv2d_thin3x3_kernel<CI, A><<<tg, 256, tsm, st>>>(c)
             if (in_channels == 1) {
                 if (e.act == ACT_RELU) APSB_THIN(1, ACT_RELU); else if (e.act == ACT_LEAKY) APSB_THIN(1, ACT_LEAKY); else APSB_THIN(1, ACT_NONE);
             } else {

@@ -211,6 +211,12 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& v) {
 
 // Activation resolved at compile time (a run-time switch inside the unrolled element loops would replicate tanhf / erff
 // dozens of times: the epilogue is instruction-issue bound, one warp per scheduler).
+// (A 4-instruction sigmoid — ex2.approx.ftz + rcp.approx.ftz through inline PTX instead of __expf / __fdividef, which carry
+// a range test and two scaling multiplies each — removed 500 of the 8 664 instructions of the 128-wide TMA-fed kernel and
+// made the step SLOWER: 3.995 -> 4.13 ms, conv2 848 -> 973 us although its ReLU epilogue does not even use it.  Same
+// layout sensitivity as KFORM below; measured in round 2, visit O, and left out.)
+__device__ __forceinline__ float tc_glu_gate(float g) { return 1.f / (1.f + __expf(-g)); }
+
 template <int ACT>
 __device__ __forceinline__ float tc_act(float v, float slope) {
     if (ACT == ACT_RELU) return fmaxf(v, 0.f);
@@ -799,8 +805,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             for (int i = 0; i < GRP; ++i) {
                                 const float4 v = tv[i];
                                 float2 o;
-                                o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
-                                o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
+                                o.x = e.alpha * ((v.x + b4.x) * tc_glu_gate(v.y + b4.y));
+                                o.y = e.alpha * ((v.z + b4.z) * tc_glu_gate(v.w + b4.w));
                                 o.x = fmaf(e.beta, res_cur[g + i].x, o.x);
                                 o.y = fmaf(e.beta, res_cur[g + i].y, o.y);
                                 if (nok && mr[g + i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[g + i] * e.ldo + (n >> 1)) = o;
@@ -835,6 +841,54 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         }
 #undef TC_EPI_CASE
                     }
+                } else if constexpr (MODE != 3) {
+                    // ---- transposed scalar fallback (unaligned rows): same code as in the other body below ----
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int n = n0 + lane;                          // this lane's column from here on (shadows the 4-column index)
+                    const bool nok = n < p.N;
+                    const float bias = (e.bias && nok) ? __ldg(e.bias + n) : 0.f;
+                    if (glu) {
+                        const int no = n >> 1;
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const float v = tile_s[rr * 33 + lane] + bias;
+                            const float g = __shfl_down_sync(0xffffffffu, v, 1);
+                            if (!(lane & 1) && n + 1 < p.N) {
+                                const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
+                                float o = e.alpha * (v * tc_glu_gate(g));
+                                if (e.res) o = fmaf(e.beta, __ldg(e.res + m * e.ldres + no), o);
+                                eout[m * e.ldo + no] = o;
+                            }
+                        }
+                    } else {
+                        const float ps = (e.post_scale && nok) ? __ldg(e.post_scale + n) : 1.f;
+                        const float pt = (e.post_scale && nok) ? __ldg(e.post_shift + n) : 0.f;
+                        const float slope =
+                            (e.act == ACT_PRELU && nok) ? __ldg(e.slope + (long long)n * e.slope_stride) : e.leak;
+#pragma unroll 4
+                        for (int rr = 0; rr < rows; ++rr) {
+                            float v = tile_s[rr * 33 + lane] + bias;
+                            switch (e.act) {
+                                case ACT_RELU: v = fmaxf(v, 0.f); break;
+                                case ACT_SWISH: v = __fdividef(v, 1.f + __expf(-v)); break;
+                                case ACT_TANH: v = tanhf(v); break;
+                                case ACT_SIGMOID: v = __fdividef(1.f, 1.f + __expf(-v)); break;
+                                case ACT_PRELU:
+                                case ACT_LEAKY: v = v >= 0.f ? v : v * slope; break;
+                                case ACT_GELU: v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); break;
+                                default: break;
+                            }
+                            v = fmaf(v, ps, pt) * e.alpha;
+                            if (nok) {
+                                const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
+                                if (e.res) v = fmaf(e.beta, __ldg(e.res + m * e.ldres + n), v);
+                                eout[m * e.ldo + n] = v;
+                            }
+                        }
+                    }
+                    __syncwarp();                  // tile_s is reused by the next chunk
                 }
                 } else {
                 // per-column vectors of this lane's 4 columns: requested while the TMEM load is in flight
@@ -903,8 +957,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             }
                             const float4 v = tv[i];
                             float2 o;
-                            o.x = e.alpha * ((v.x + b4.x) * (1.f / (1.f + __expf(-(v.y + b4.y)))));
-                            o.y = e.alpha * ((v.z + b4.z) * (1.f / (1.f + __expf(-(v.w + b4.w)))));
+                            o.x = e.alpha * ((v.x + b4.x) * tc_glu_gate(v.y + b4.y));
+                            o.y = e.alpha * ((v.z + b4.z) * tc_glu_gate(v.w + b4.w));
                             o.x = fmaf(e.beta, res_cur[i].x, o.x);
                             o.y = fmaf(e.beta, res_cur[i].y, o.y);
                             if (nok && mr[i] >= 0) *reinterpret_cast<float2*>(eout + (long long)mr[i] * e.ldo + (n >> 1)) = o;
@@ -954,7 +1008,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                             const float g = __shfl_down_sync(0xffffffffu, v, 1);
                             if (!(lane & 1) && n + 1 < p.N) {
                                 const long long m = tc_out_row(p.a, (unsigned)(m0 + rr));
-                                float o = e.alpha * (v * (1.f / (1.f + __expf(-g))));
+                                float o = e.alpha * (v * tc_glu_gate(g));
                                 if (e.res) o = fmaf(e.beta, __ldg(e.res + m * e.ldres + no), o);
                                 eout[m * e.ldo + no] = o;
                             }

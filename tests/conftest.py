@@ -30,6 +30,24 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip_gpu)
 
 
+@pytest.fixture(autouse=True)
+def _poison_uninitialised_outputs(request, monkeypatch):
+    """GPU tests: every floating-point `torch.empty` / `empty_like` on a CUDA device comes back filled with NaN, so a kernel
+    that skips part of its output fails the comparison instead of passing on whatever an earlier test left in the caching
+    allocator's block (round 2: a missing scalar epilogue branch went unnoticed for exactly that reason)."""
+    if "gpu" not in request.keywords or not th.cuda.is_available():
+        yield
+        return
+    real_empty, real_like = th.empty, th.empty_like
+
+    def poisoned(t):
+        return t.fill_(float("nan")) if t.is_cuda and t.is_floating_point() else t
+
+    monkeypatch.setattr(th, "empty", lambda *a, **k: poisoned(real_empty(*a, **k)))
+    monkeypatch.setattr(th, "empty_like", lambda *a, **k: poisoned(real_like(*a, **k)))
+    yield
+
+
 def load_golden(name):
     """-> (kwargs dict, {array name: torch tensor})"""
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
