@@ -38,6 +38,7 @@
 
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace apsb {
 
@@ -59,9 +60,10 @@ constexpr int TC_BM = 128;
 #define APSB_TC_CLUSTER 1
 #endif
 // MODE 3 (linear layer whose activation comes with its TF32 "lo" companion, see below) has NO producer warps: the TMA
-// warp loads the A tiles as well.
+// warp loads the A tiles as well.  MODE 4 (stride-2 convolution fed by 5-D TMA boxes) has four CONVERTER warps in their
+// place: they derive the lo tile from the raw tile the TMA delivered, inside shared memory.
 template <int BN, int MODE> struct TcRoles {
-    static constexpr int PW = MODE == 3 ? 0 : (BN > 128 ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
+    static constexpr int PW = MODE == 3 ? 0 : ((BN > 128 || MODE == 4) ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
     static constexpr int PRODUCERS = PW * 32;
     // epilogue warps: 4 (one per TMEM lane quarter), or 8 in MODE 3 (two per quarter taking alternate 32-column chunks):
     // a 32 x 32 block costs ~900 dependent-issue-bound instructions, and ONE warp per scheduler cannot hide their
@@ -136,6 +138,14 @@ __device__ __forceinline__ void tc_tma_load_2d(const CUtensorMap* map, uint64_t*
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             s_u32(dst)),
         "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            s_u32(dst)),
+        "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 // the same box written into the shared memory of every CTA of the cluster named in `mask` (same CTA-relative offset), each
@@ -340,6 +350,10 @@ struct TcParams {
     unsigned stiles;             // super tiles = ceil(row blocks / CL) x column blocks x K slices (CL = cluster size)
     int ksplit;                  // MODE 3: the K range is cut into `ksplit` slices, slice s -> out + s * split_stride
     long long split_stride;      //         (raw partial sums; bias / activation / residual happen in the reducing kernel)
+    // MODE 4 (see tc_gemm_kernel): a row block is c4_rh whole output rows (oh) of ONE image — c4_rh * OW <= 128 GEMM rows —,
+    // c4_tpi row blocks per image, c4_tiles_m in all; or, for rows longer than a tile (c4_cw < OW, c4_rh = 1), c4_cw
+    // consecutive columns of one output row, c4_tpr such blocks per row
+    int c4_rh, c4_tpi, c4_tiles_m, c4_cw, c4_tpr;
     int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
     unsigned long long* trace;   // debug builds (-DAPSB_TC_TRACE): [0] = event counter, then (event << 48 | clock) words
 };
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
     static_assert(CL == 1 || MODE != 2, "row classes of a transposed convolution skip k-blocks per tile: no lock step");
+    static_assert(CL == 1 || MODE != 4, "the TMA-fed convolution is not clustered");
     const unsigned crank = CL > 1 ? tc_cluster_rank() : 0u;
     // cluster index / number of clusters.  Code generation of this 35 k-instruction function is touchy (measured, B200,
     // same-box A/B of library builds): with these two values in registers and the first epilogue body below the
@@ -492,6 +507,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
         }
+        if (MODE == 4) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     }
     if (warp == WARP_MMA) {
         if (lane == 0) {
@@ -552,6 +568,42 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         tc_tma_load_2d(&tmA, full_b + s, st, kb * BK, t.m_blk * TC_BM);
                         tc_tma_load_2d(&tmAlo, full_b + s, st + A_BYTES, kb * BK, t.m_blk * TC_BM);
                         load_w(full_b + s, st + 2 * A_BYTES, kb * BK, t.n_blk * BN);
+                        TC_TR(1);
+                    }
+                }
+            }
+        } else if constexpr (MODE == 4) {
+            // MODE 4: the NHWC input is the 4-D tensor [image][h][w][c] of a tiled tensor map whose TRAVERSAL strides are the
+            // convolution strides, so the A tile of tap (kh, kw) for c4_rh whole output rows (oh0.., all OW columns) is ONE box
+            // {32 (16) channels, OW pixels from w = kw dw - pw in steps of sw, c4_rh rows from h = oh0 sh + kh dh - ph in steps
+            // of sh, one image}.  Rows land in GEMM-row order (ow fastest) as 128-byte rows under the hardware swizzle; the
+            // zero padding is the TMA's out-of-bounds fill (coordinates may be negative).  No gather instructions at all.
+            if (lane == 0) {
+                uint32_t it = 0;
+                const uint32_t a_box = (uint32_t)(p.c4_rh * p.c4_cw) * (uint32_t)SWZ;
+                for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
+                    const unsigned m_blk = st_ / (unsigned)p.tiles_n;
+                    const int n_blk = (int)(st_ - m_blk * (unsigned)p.tiles_n);
+                    const unsigned img = m_blk / (unsigned)p.c4_tpi;
+                    unsigned oh0 = (m_blk - img * (unsigned)p.c4_tpi) * (unsigned)p.c4_rh, ow0 = 0;
+                    if (p.c4_tpr > 1) {            // (output row, column chunk)
+                        const unsigned j = oh0;
+                        oh0 = j / (unsigned)p.c4_tpr;
+                        ow0 = (j - oh0 * (unsigned)p.c4_tpr) * (unsigned)p.c4_cw;
+                    }
+                    const int h0 = (int)oh0 * p.a.sh - p.a.ph, w0 = (int)ow0 * p.a.sw - p.a.pw;
+                    for (int kh = 0; kh < num_kh; ++kh)
+                    for (int cb32 = 0; cb32 < cb32_per_tap; ++cb32)
+                    for (int kw = 0; kw < num_kw; ++kw)
+                    for (int h = 0; h < SUB; ++h, ++it) {
+                        const int kb = (kh * num_kw + kw) * kb_per_tap + cb32 * SUB + h;
+                        const int s = it % S;
+                        const uint32_t ph = (it / S) & 1;
+                        tc_mbar_wait_parked(empty + s, ph ^ 1);
+                        uint8_t* st = base + s * C::STAGE_BYTES;
+                        tc_mbar_expect_tx(full_b + s, a_box + 2 * C::B_BYTES);
+                        tc_tma_load_4d(&tmA, full_b + s, st, cb32 * 32 + h * BK, w0 + kw * p.a.dw, h0 + kh * p.a.dh, (int)img);
+                        load_w(full_b + s, st + 2 * A_BYTES, kb * BK, n_blk * BN);
                         TC_TR(1);
                     }
                 }
@@ -679,10 +731,30 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 eout += (long long)t.ks * p.split_stride;
             }
             const uint32_t buf = tcount & 1;
-            const long long m0 = (long long)m_blk * TC_BM + q * 32;
+            // first GEMM row of this warp's lane quarter and the number of valid rows from there on (MODE 4: a row block is
+            // c4_rh whole output rows of one image, packed from row 0 of the tile)
+            long long m0_ = (long long)m_blk * TC_BM + q * 32, rows_ = 0;
+            if constexpr (MODE == 4) {
+                const unsigned img = m_blk / (unsigned)p.c4_tpi;
+                int oh0 = (int)(m_blk - img * (unsigned)p.c4_tpi) * p.c4_rh, ow0 = 0;
+                int valid;
+                if (p.c4_tpr > 1) {
+                    const int j = oh0;
+                    oh0 = j / p.c4_tpr;
+                    ow0 = (j - oh0 * p.c4_tpr) * p.c4_cw;
+                    valid = min(p.c4_cw, p.a.OW - ow0);
+                } else {
+                    valid = min(p.c4_rh, p.a.OH - oh0) * p.a.OW;
+                }
+                m0_ = ((long long)img * p.a.OH + oh0) * p.a.OW + ow0 + q * 32;
+                rows_ = (long long)valid - q * 32;
+            } else {
+                rows_ = (long long)p.M - m0_;
+            }
+            const long long m0 = m0_;
             const int ncols = min(BN, p.N - n_blk * BN);
             const int nchunks = (ncols + 31) >> 5;
-            const long long rows_ll = (long long)p.M - m0;
+            const long long rows_ll = rows_;
             const int rows = rows_ll >= 32 ? 32 : (rows_ll > 0 ? (int)rows_ll : 0);
 #ifdef APSB_TC_TRACE
             const bool row_ok = lane < rows && !(p.dbg & 64);      // ablation: no residual loads / output stores
@@ -1044,6 +1116,32 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 }   // MODE != 3
             }
             if (threadIdx.x == 64) TC_TR(6);
+        }
+    } else if constexpr (MODE == 4) {
+        // ================= lo converters (warps 6..9) =================
+        // The TMA delivered the raw fp32 tile (the tensor core reads it as hi = trunc_tf32(x)); lo = rn_tf32(x - hi) goes to
+        // the stage's second A buffer at the SAME byte offsets (the swizzle is a property of the address, and this is an
+        // element-wise map), 16-byte chunks dealt out linearly: conflict free, 4 (BK 16) or 8 chunks per thread and k-block.
+        const int pt = threadIdx.x - WARP_PROD0 * 32;
+        const uint32_t nkb = (uint32_t)(num_kh * num_kw * kb_per_tap);
+        uint32_t it = 0;
+        for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
+            for (uint32_t j = 0; j < nkb; ++j, ++it) {
+                const int s = (int)(it % S);
+                const uint32_t ph = (it / S) & 1;
+                if (lane == 0) tc_mbar_wait_parked(full_b + s, ph);   // one poller per warp
+                __syncwarp();
+                const uint32_t sa = s_u32(base + s * C::STAGE_BYTES) + (uint32_t)pt * 16u;
+#pragma unroll
+                for (int i = 0; i < A_BYTES / (16 * 128); ++i) {
+                    const float4 l = tf32_lo4(tc_lds128(sa + (uint32_t)i * 2048u));
+                    tc_sts128(sa + (uint32_t)A_BYTES + (uint32_t)i * 2048u, __float_as_uint(l.x), __float_as_uint(l.y),
+                              __float_as_uint(l.z), __float_as_uint(l.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(full_a + s);      // one arrival per converter warp
+            }
         }
     } else if constexpr (MODE != 3) {
         // ================= A producers (warps 6..9) =================
@@ -1413,6 +1511,43 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
     return 0;
 }
 
+// MODE 4: geometry of a convolution whose A tiles are strided TMA boxes (see the kernel's TMA role)
+struct Conv4 {
+    int rh, tpi, tiles_m, cw, tpr;
+};
+
+// 4-D view [B][H][W][C] of the NHWC input; box = {box_c channels, OW pixels every sw, rh rows every sh, one image}
+// (cuTensorMapEncodeTiled: "to load N elements along the i-th dimension, boxDim[i] must be N * elementStrides[i]")
+static int make_map_conv(CUtensorMap* map, const float* ptr, long long B, long long H, long long W, long long Cc, int box_c,
+                         int OW, int rh, int sh, int sw) {   // OW: output columns per box
+    static std::mutex mu;
+    struct Key4 { const void* ptr; long long B, H, W, C; int box_c, OW, rh, sh, sw; CUtensorMap map; };
+    static std::vector<Key4> cache;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (const Key4& k : cache)
+            if (k.ptr == ptr && k.B == B && k.H == H && k.W == W && k.C == Cc && k.box_c == box_c && k.OW == OW &&
+                k.rh == rh && k.sh == sh && k.sw == sw) {
+                *map = k.map;
+                return 0;
+            }
+    }
+    EncodeTiledFn fn = encode_fn();
+    APSB_CHECK_ARG(fn, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cc * 4, (cuuint64_t)(W * Cc) * 4, (cuuint64_t)(H * W * Cc) * 4};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(OW * sw), (cuuint32_t)(rh * sh), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    APSB_CHECK_ARG(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled (strided 4-D) failed with code %d", (int)rc);
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 256) cache.clear();
+    cache.push_back(Key4{ptr, B, H, W, Cc, box_c, OW, rh, sh, sw, *map});
+    return 0;
+}
+
 // launch with a cluster of CL CTAs (CL = 1: plain launch), optionally as a programmatic dependent launch.  The grid is
 // `nclusters` x CL with nclusters bounded by what the device can keep resident at once (cudaOccupancyMaxActiveClusters:
 // a cluster must sit inside one GPC, and 148 SMs are not a multiple of every GPC's width).
@@ -1448,7 +1583,7 @@ static int launch_tc_cl(const CUtensorMap& tB, const CUtensorMap& tBl, const CUt
         max_clusters[dev & 63] = mc;
         attr_done[dev & 63] = true;
     }
-    const long long tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    const long long tiles_m = MODE == 4 ? (long long)p.c4_tiles_m : (p.M + TC_BM - 1) / TC_BM;
     const long long stiles = (tiles_m + CL - 1) / CL * p.tiles_n * p.ksplit;
     p.stiles = (unsigned)stiles;
     const long long ncl = stiles < max_clusters[dev & 63] ? stiles : max_clusters[dev & 63];
@@ -1492,7 +1627,7 @@ static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const C
 template <int BN>
 static int launch_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, int M, int N, int K,
                      const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
-                     long long split_stride = 0) {
+                     long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0) {
     using C = TcCfg<BN>;
     // cluster size (weight-tile multicast)
     const long long tiles_m_ = (M + TC_BM - 1) / TC_BM;
@@ -1501,6 +1636,7 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
         const int v = atoi(ce);
         if ((v == 1 || v == 2 || v == 4) && a.mode != 2) cl = v;
     }
+    if (c4) cl = 1;
     CUtensorMap tB, tBl, tA, tAl;
     if (int rc = make_map(&tB, W, N, K, ldw, BN / cl, C::BK)) return rc;          // a CTA fetches BN / cl rows of the box
     if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN / cl, C::BK)) return rc;
@@ -1534,7 +1670,13 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     p.e.dbg_nobias = (p.dbg & 128) ? 1 : 0;
 #endif
     APSB_CHECK_ARG(!(xlo && p.ksplit > 1 && !p.epi_vec), "split-K needs 16-byte aligned partial rows (N %% 4 == 0)");
-    // the TMA-fed kernel has the vector epilogue only: unaligned outputs take the gather-fed kernel and its scalar path
+    // the TMA-fed kernels have the vector epilogue only: unaligned outputs take the gather-fed kernel and its scalar path
+    if (c4 && p.epi_vec) {
+        if (int rc = make_map_conv(&tA, a.x, batch, a.H, a.W, a.Cin, C::BK, c4->cw, c4->rh, a.sh, a.sw)) return rc;
+        p.c4_rh = c4->rh; p.c4_tpi = c4->tpi; p.c4_tiles_m = c4->tiles_m; p.c4_cw = c4->cw; p.c4_tpr = c4->tpr;
+        p.tiles = (unsigned)((long long)c4->tiles_m * p.tiles_n);
+        return launch_tc_cl<BN, 4, 1>(tB, tBl, tA, tAl, p, st);
+    }
     if (xlo && p.epi_vec) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, cl, st);
@@ -1547,7 +1689,12 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
 // waves of one per SM.
 static int run_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, long long M, long long N,
                   long long K, const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
-                  long long split_stride = 0) {
+                  long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0) {
+    if (c4) {       // TMA-fed convolution: MMA bound at every width, so the widest tile that is not mostly padding
+        if (N > 128) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st, nullptr, 1, 0, c4, batch);
+        if (N > 64) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st, nullptr, 1, 0, c4, batch);
+        return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st, nullptr, 1, 0, c4, batch);
+    }
     const long long tm = (M + TC_BM - 1) / TC_BM;
     const long long K0 = K;
     const int sms = num_sms();
@@ -1725,6 +1872,31 @@ static int conv2d_tc_impl(const float* x, int64_t batch, int64_t height, int64_t
     if (out_lo)
         APSB_CHECK_ARG(((uintptr_t)out_lo & 15) == 0 && ((uintptr_t)out & 15) == 0 && (out_channels & 3) == 0 &&
                            epi->act != ACT_GLU, "a lo companion needs 16-byte aligned output rows and no GLU");
+    // A tiles by TMA (MODE 4) when the strides are within the TMA's traversal-stride range: a 128-row tile is either some
+    // whole output rows (short rows: the conformer front) or a chunk of one output row (long rows: DCCRN's time axis)
+    Conv4 c4{};
+    const bool tma_conv = stride_h <= 8 && stride_w <= 8 && (in_channels & 31) == 0 && ((uintptr_t)x & 15) == 0 &&
+                          !getenv("APS_B200_NO_CONV_TMA");
+    if (tma_conv) {
+        const int64_t cw_max = 256 / stride_w < TC_BM ? 256 / stride_w : TC_BM;     // box extent <= 256 elements
+        if (OW <= cw_max) {
+            c4.cw = (int)OW; c4.tpr = 1;
+            c4.rh = (int)(TC_BM / OW);
+            if ((long long)c4.rh > OH) c4.rh = (int)OH;
+            if (c4.rh * stride_h > 256) c4.rh = 256 / stride_h;
+            c4.tpi = (int)((OH + c4.rh - 1) / c4.rh);
+        } else {
+            c4.tpr = (int)((OW + cw_max - 1) / cw_max);
+            c4.cw = (int)((OW + c4.tpr - 1) / c4.tpr);        // even chunks
+            c4.rh = 1;
+            c4.tpi = (int)(OH * c4.tpr);
+        }
+        c4.tiles_m = (int)(batch * c4.tpi);
+        // rows actually used over rows paid for (tile padding + the short last tile of every image / row)
+        const double eff = (double)(OH * OW) / ((double)c4.tpi * TC_BM);
+        if (eff >= 0.7 && batch * c4.tpi < (1LL << 30))
+            return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream, nullptr, 1, 0, &c4, batch);
+    }
     return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream);
 }
 

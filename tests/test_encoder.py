@@ -168,6 +168,40 @@ def test_tensor_core_conv_path_vs_torch(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_tma_fed_conv_vs_fp64_and_gather(monkeypatch):
+    """Convolutions whose A tiles come in as strided TMA boxes (MODE 4 of the engine: whole output rows per 128-row tile,
+    zero padding = the TMA's out-of-bounds fill, lo tile derived in shared memory) against fp64, and against the
+    gather-fed kernel on the same input: the conformer front's geometries (padding 1, odd height), no padding, stride 1 and
+    (2, 1), dilation, 5 x 2 taps, a last tile shorter than the others, one output row per image, 64- / 128- / 256-wide
+    tiles, rows longer than a tile (column chunks), the lo companion output, and a geometry that must fall back."""
+    import torch.nn.functional as F
+    from aps_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_ENGINE", "tc")
+    th.manual_seed(11)
+    for (B, H, W, Ci, Co, k, s_, p_, d_) in (
+            (3, 39, 40, 256, 256, (3, 3), (2, 2), (1, 1), (1, 1)),      # front conv2 (OW 20: 6 rows per tile), odd height
+            (5, 100, 20, 256, 256, (3, 3), (2, 2), (1, 1), (1, 1)),     # front conv3 (OW 10, 12 rows per tile, short last tile)
+            (3, 38, 39, 32, 64, (3, 3), (2, 2), (0, 0), (1, 1)),        # no padding, odd width
+            (4, 4, 250, 64, 128, (3, 3), (2, 2), (0, 0), (1, 1)),       # one output row per image (OH = 1, OW = 124)
+            (2, 30, 25, 32, 320, (5, 2), (2, 1), (2, 1), (1, 1)),       # 5 x 2 taps, stride (2, 1), two column blocks
+            (2, 24, 31, 64, 48, (3, 3), (1, 1), (1, 1), (1, 2)),        # stride 1, dilation along w
+            (6, 9, 40, 32, 64, (3, 3), (3, 4), (2, 0), (2, 1)),         # stride (3, 4), dilation along h
+            (2, 10, 480, 32, 48, (3, 3), (2, 2), (0, 0), (1, 1)),       # OW = 239: two chunks of 120 columns per output row
+            (2, 33, 251, 64, 128, (5, 2), (2, 1), (2, 1), (1, 1)),      # DCCRN encoder geometry (OW = 252: chunks of 126)
+            (2, 6, 140, 32, 36, (3, 3), (1, 1), (1, 0), (1, 1))):       # OW = 138 in chunks of 69: 54 % fill -> gather fallback
+        x, w, b = th.randn(B, Ci, H, W), th.randn(Co, Ci, *k) * 0.1, th.randn(Co)
+        ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=s_, padding=p_, dilation=d_)).permute(0, 2, 3, 1)
+        xg, wg, bg = x.permute(0, 2, 3, 1).contiguous().to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV)
+        got, lo = ops.conv2d_nhwc(xg, wg, bg, stride=s_, padding=p_, dilation=d_, act="relu", want_lo=True)
+        assert got.shape == ref.shape and rel_err(got, ref) < 3e-5, (B, H, W, Ci, Co, k)
+        assert th.equal(lo, ops.lo_companion(got))
+        monkeypatch.setenv("APS_B200_NO_CONV_TMA", "1")
+        old = ops.conv2d_nhwc(xg, wg, bg, stride=s_, padding=p_, dilation=d_, act="relu")
+        monkeypatch.delenv("APS_B200_NO_CONV_TMA")
+        assert rel_err(got, old) < 1e-5, (B, H, W, Ci, Co, k)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("classes", [True, False])
 def test_tensor_core_conv_transpose_vs_torch(monkeypatch, classes):
     """conv_transpose2d as an implicit gather GEMM; with stride_h > 1 the rows are walked class-major (oh % stride_h)
