@@ -866,7 +866,20 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     // (1 in the 448-thread variants, whose 128-register budget is taken by the producers' gather ring)
                     constexpr int GRP = LEAN ? 1 : 4;
                     if (LEAN) load_cols();
-                    if (glu) {
+                    if (MODE == 3 && p.ksplit > 1) {
+                        // split-K slice: RAW partial sums (bias, activation, residual and the companion belong to the
+                        // reducing kernel) — straight from the tile to memory.  Through the general path below this cost
+                        // ~900 instructions per 32 x 32 block: 17 k cycles of a 39 k-cycle FFN-b work item (trace r02k).
+#pragma unroll
+                        for (int g = 0; g < 8; g += 4) {
+                            float4 tv[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) tv[i] = tc_lds128(ts_b + ts_off((uint32_t)(er + 4 * (g + i)), (uint32_t)(ec >> 2)));
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (nok && mr[g + i] >= 0) *reinterpret_cast<float4*>(eout + (long long)mr[g + i] * e.ldo + n) = tv[i];
+                        }
+                    } else if (glu) {
                         // columns (2j, 2j+1) -> output column j: this lane's 4 columns give 2 outputs
 #pragma unroll
                         for (int g = 0; g < 8; g += GRP) {
@@ -900,6 +913,29 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             }                                                                                                           \
         }                                                                                                               \
         break;
+                        // bias + activation only (no post affine, alpha = 1, no residual: FFN-a, QKV): three dependent
+                        // operations per element less than the general form
+#define TC_EPI_PLAIN(A)                                                                                                 \
+        _Pragma("unroll") for (int g = 0; g < 8; g += GRP) {                                                            \
+            float4 tv[GRP];                                                                                             \
+            _Pragma("unroll") for (int i = 0; i < GRP; ++i)                                                             \
+                tv[i] = tc_lds128(ts_b + ts_off((uint32_t)(er + 4 * (g + i)), (uint32_t)(ec >> 2)));                    \
+            _Pragma("unroll") for (int i = 0; i < GRP; ++i) {                                                           \
+                const float4 o = make_float4(tc_act<A>(tv[i].x + b4.x, 0.f), tc_act<A>(tv[i].y + b4.y, 0.f),            \
+                                             tc_act<A>(tv[i].z + b4.z, 0.f), tc_act<A>(tv[i].w + b4.w, 0.f));           \
+                if (nok && mr[g + i] >= 0) {                                                                            \
+                    *reinterpret_cast<float4*>(eout + (long long)mr[g + i] * e.ldo + n) = o;                            \
+                    if (e.out_lo) *reinterpret_cast<float4*>(e.out_lo + (long long)mr[g + i] * e.ldo + n) = tf32_lo4(o); \
+                }                                                                                                       \
+            }                                                                                                           \
+        }
+                        const bool plain = MODE == 3 && !e.res && !e.post_scale && e.alpha == 1.f;
+                        if (plain && e.act == ACT_SWISH) {
+                            TC_EPI_PLAIN(ACT_SWISH)
+                        } else if (plain && e.act == ACT_NONE) {
+                            TC_EPI_PLAIN(ACT_NONE)
+                        } else
+#undef TC_EPI_PLAIN
                         switch (e.act) {
                             TC_EPI_CASE(ACT_RELU)
                             TC_EPI_CASE(ACT_SWISH)
