@@ -510,7 +510,8 @@ extern "C" int aps_b200_conv2d_nhwc_fwd(const float* x, int64_t batch, int64_t h
         const bool thin = kernel_h == 3 && kernel_w == 3 && dil_h == 1 && dil_w == 1 && (in_channels == 1 || in_channels == 2) &&
                           (ncols & 3) == 0 && cg <= 256 && (cg & (cg - 1)) == 0 && !epi->post_scale &&
                           (e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LEAKY) && (e.ldo & 3) == 0 &&
-                          ((uintptr_t)out & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) && !getenv("APS_B200_NO_THIN_CONV");
+                          ((uintptr_t)out & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) && !getenv("APS_B200_NO_THIN_CONV") &&
+                          (size_t)2 * 3 * (((width + 2 * pad_w) * in_channels + 3) & ~3LL) * sizeof(float) <= 48 * 1024;   // staged rows
         if (thin) {
             const long long rows = batch * OH;
             const unsigned tg = (unsigned)(rows < (long long)num_sms() * 3 ? rows : (long long)num_sms() * 3);

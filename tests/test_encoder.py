@@ -304,6 +304,9 @@ def test_dense_kernels_vs_torch(monkeypatch):
     assert rel_err(ops.linear(big.to(DEV)[:, 20:148], wg[:, :128].contiguous()), F.linear(big[:, 20:148], w[:, :128])) < 1e-5
     # implicit-GEMM convolutions (NHWC) incl. Cin = 1 and dilation / asymmetric stride
     for (B, H, W, Ci, Co, k, s, p, d) in ((2, 33, 20, 1, 16, (3, 3), (2, 2), (1, 1), (1, 1)),
+                                          (2, 21, 40, 1, 256, (3, 3), (2, 2), (1, 1), (1, 1)),    # thin kernel, padded rows
+                                          (2, 9, 37, 2, 32, (3, 3), (2, 1), (0, 1), (1, 1)),      # thin kernel, 2 channels
+                                          (1, 5, 2500, 1, 16, (3, 3), (1, 2), (1, 0), (1, 1)),    # rows too wide to stage
                                           (3, 17, 11, 8, 24, (3, 3), (2, 2), (1, 1), (1, 1)),
                                           (2, 20, 9, 4, 6, (5, 2), (2, 1), (2, 0), (1, 1)),
                                           (1, 40, 1, 12, 10, (3, 1), (1, 1), (2, 0), (2, 1))):
