@@ -35,7 +35,7 @@ def main():
         print(f"{o:14s} {kernels:7d} {n:8d}  " + " ".join(f"{c.get(k, 0):8d}" for k in KEYS))
     # the tensor-core kernels one by one
     out = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "build", "tc_gemm.o")], capture_output=True, text=True).stdout
-    print("\n# tc_gemm.o per kernel: template <BN, MODE (0 linear gather, 1 conv2d, 2 conv_transpose2d, 3 TMA-fed linear), CL>")
+    print("\n# tc_gemm.o per kernel: template <BN, MODE (0 linear gather, 1 conv2d gather, 2 conv_transpose2d, 3 TMA-fed linear, 4 TMA-fed conv2d), CL>")
     name, c = None, collections.Counter()
     rows = []
     for line in out.splitlines():
