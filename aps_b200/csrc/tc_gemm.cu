@@ -354,6 +354,10 @@ struct TcParams {
     // c4_tpi row blocks per image, c4_tiles_m in all; or, for rows longer than a tile (c4_cw < OW, c4_rh = 1), c4_cw
     // consecutive columns of one output row, c4_tpr such blocks per row
     int c4_rh, c4_tpi, c4_tiles_m, c4_cw, c4_tpr;
+    // transposed convolution on the same kernel (c4_t = 1; stride_w = 1): a row block holds c4_rh output rows of ONE row
+    // class (oh = cls + sh i: their input rows (oh + ph - kh) / sh are consecutive) or a column chunk of one row;
+    // c4_ct[cls] row blocks per image and class, a.class_rows[cls] output rows per image and class
+    int c4_t, c4_ct[4];
     int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
     unsigned long long* trace;   // debug builds (-DAPSB_TC_TRACE): [0] = event counter, then (event << 48 | clock) words
 };
@@ -496,6 +500,31 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         return tc_tile_class(p.a, m_first, m_last);
     };
 
+    // MODE 4 row block -> image, row class (-1: plain convolution), first (class) row, first column, GEMM rows in use
+    struct Tile4 { unsigned img; int cls, i0, ow0, valid; };
+    auto decode4 = [&](unsigned m_blk) {
+        Tile4 t;
+        t.img = m_blk / (unsigned)p.c4_tpi;
+        unsigned j = m_blk - t.img * (unsigned)p.c4_tpi;
+        t.cls = -1;
+        int rows_all = p.a.OH;
+        if (p.c4_t) {
+            int c = 0;
+            while (c < 3 && j >= (unsigned)p.c4_ct[c]) { j -= (unsigned)p.c4_ct[c]; ++c; }
+            t.cls = c;
+            rows_all = p.a.class_rows[c];
+        }
+        if (p.c4_tpr > 1) {                // (row, column chunk)
+            t.i0 = (int)(j / (unsigned)p.c4_tpr);
+            t.ow0 = (int)(j - (unsigned)t.i0 * (unsigned)p.c4_tpr) * p.c4_cw;
+            t.valid = min(p.c4_cw, p.a.OW - t.ow0);
+        } else {
+            t.i0 = (int)j * p.c4_rh;
+            t.ow0 = 0;
+            t.valid = min(p.c4_rh, rows_all - t.i0) * p.a.OW;
+        }
+        return t;
+    };
     // Role -> warp assignment: the SM's schedulers prefer the HIGHEST warp id among eligible warps of a sub-partition
     // (warp % 4).  The A producers are the throughput-critical role, so they get the top ids (6-9); the single-thread
     // TMA / MMA roles (warps 0 / 1) mostly wait and must never out-prioritise them; warps 2-5 are the epilogue (TMEM
@@ -507,7 +536,10 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
         }
-        if (MODE == 4) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        if (MODE == 4) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
+        }
     }
     if (warp == WARP_MMA) {
         if (lane == 0) {
@@ -584,27 +616,34 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
                     const unsigned m_blk = st_ / (unsigned)p.tiles_n;
                     const int n_blk = (int)(st_ - m_blk * (unsigned)p.tiles_n);
-                    const unsigned img = m_blk / (unsigned)p.c4_tpi;
-                    unsigned oh0 = (m_blk - img * (unsigned)p.c4_tpi) * (unsigned)p.c4_rh, ow0 = 0;
-                    if (p.c4_tpr > 1) {            // (output row, column chunk)
-                        const unsigned j = oh0;
-                        oh0 = j / (unsigned)p.c4_tpr;
-                        ow0 = (j - oh0 * (unsigned)p.c4_tpr) * (unsigned)p.c4_cw;
-                    }
-                    const int h0 = (int)oh0 * p.a.sh - p.a.ph, w0 = (int)ow0 * p.a.sw - p.a.pw;
-                    for (int kh = 0; kh < num_kh; ++kh)
-                    for (int cb32 = 0; cb32 < cb32_per_tap; ++cb32)
-                    for (int kw = 0; kw < num_kw; ++kw)
-                    for (int h = 0; h < SUB; ++h, ++it) {
-                        const int kb = (kh * num_kw + kw) * kb_per_tap + cb32 * SUB + h;
-                        const int s = it % S;
-                        const uint32_t ph = (it / S) & 1;
-                        tc_mbar_wait_parked(empty + s, ph ^ 1);
-                        uint8_t* st = base + s * C::STAGE_BYTES;
-                        tc_mbar_expect_tx(full_b + s, a_box + 2 * C::B_BYTES);
-                        tc_tma_load_4d(&tmA, full_b + s, st, cb32 * 32 + h * BK, w0 + kw * p.a.dw, h0 + kh * p.a.dh, (int)img);
-                        load_w(full_b + s, st + 2 * A_BYTES, kb * BK, n_blk * BN);
-                        TC_TR(1);
+                    const Tile4 t = decode4(m_blk);
+                    // convolution: rows oh0.. every sh, columns every sw (the map's traversal strides); transposed (sw = 1,
+                    // plain box): class rows i0.. read input rows (cls + ph - kh) / sh + i0.., columns ow0 + pw - kw..
+                    const int hc = t.cls < 0 ? t.i0 * p.a.sh - p.a.ph : t.i0;
+                    const int wc = t.cls < 0 ? t.ow0 * p.a.sw - p.a.pw : t.ow0 + p.a.pw;
+                    for (int kh = 0; kh < num_kh; ++kh) {
+                        if (!tc_kh_valid(p.a, t.cls, kh)) continue;      // taps that are zero for this row class
+                        const int h0 = t.cls < 0 ? hc + kh * p.a.dh : hc + (t.cls + p.a.ph - kh) / p.a.sh;
+                        for (int cb32 = 0; cb32 < cb32_per_tap; ++cb32)
+                        for (int kw = 0; kw < num_kw; ++kw)
+                        for (int h = 0; h < SUB; ++h, ++it) {
+                            const int kb = (kh * num_kw + kw) * kb_per_tap + cb32 * SUB + h;
+                            const int s = it % S;
+                            const uint32_t ph = (it / S) & 1;
+                            tc_mbar_wait_parked(empty + s, ph ^ 1);
+                            uint8_t* st = base + s * C::STAGE_BYTES;
+                            tc_mbar_expect_tx(full_b + s, a_box + 2 * C::B_BYTES);
+                            int c0 = cb32 * 32 + h * BK;
+                            const CUtensorMap* am = &tmA;
+                            if (p.a.cat_c) {               // [re_a | re_b | im_a | im_b]: which source, which of its channels
+                                const int seg = (c0 >= p.a.cat_c) + (c0 >= 2 * p.a.cat_c) + (c0 >= 3 * p.a.cat_c);
+                                c0 = (seg >> 1) * p.a.cat_c + (c0 - seg * p.a.cat_c);
+                                if (seg & 1) am = &tmAlo;
+                            }
+                            tc_tma_load_4d(am, full_b + s, st, c0, t.cls < 0 ? wc + kw * p.a.dw : wc - kw, h0, (int)t.img);
+                            load_w(full_b + s, st + 2 * A_BYTES, kb * BK, n_blk * BN);
+                            TC_TR(1);
+                        }
                     }
                 }
             }
@@ -650,7 +689,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 tc_mbar_wait_parked(tmem_empty + buf, ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                const int cls = tile_class(tile);
+                const int cls = MODE == 4 ? decode4(tile / (unsigned)p.tiles_n).cls : tile_class(tile);
                 uint32_t first = 1;
                 if (MODE == 3) {
                     const TileIdx t = decode3(tile);
@@ -734,20 +773,19 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             // first GEMM row of this warp's lane quarter and the number of valid rows from there on (MODE 4: a row block is
             // c4_rh whole output rows of one image, packed from row 0 of the tile)
             long long m0_ = (long long)m_blk * TC_BM + q * 32, rows_ = 0;
+            bool row_ok4 = false;
+            long long mrow4 = 0;
             if constexpr (MODE == 4) {
-                const unsigned img = m_blk / (unsigned)p.c4_tpi;
-                int oh0 = (int)(m_blk - img * (unsigned)p.c4_tpi) * p.c4_rh, ow0 = 0;
-                int valid;
-                if (p.c4_tpr > 1) {
-                    const int j = oh0;
-                    oh0 = j / p.c4_tpr;
-                    ow0 = (j - oh0 * p.c4_tpr) * p.c4_cw;
-                    valid = min(p.c4_cw, p.a.OW - ow0);
-                } else {
-                    valid = min(p.c4_rh, p.a.OH - oh0) * p.a.OW;
-                }
-                m0_ = ((long long)img * p.a.OH + oh0) * p.a.OW + ow0 + q * 32;
-                rows_ = (long long)valid - q * 32;
+                const Tile4 t = decode4(m_blk);
+                // GEMM row r = i * OW + ow (whole rows) or ow (column chunk); output row of (i, ow): rows of a transposed
+                // convolution's class lie sh apart
+                const int r = q * 32 + lane;
+                const int i = p.c4_tpr > 1 ? 0 : r / p.a.OW;
+                const int orow = t.cls < 0 ? t.i0 + i : t.cls + p.a.sh * (t.i0 + i);
+                row_ok4 = r < t.valid;
+                mrow4 = ((long long)t.img * p.a.OH + orow) * p.a.OW + t.ow0 + (r - i * p.a.OW);
+                m0_ = 0;
+                rows_ = (long long)t.valid - q * 32;
             } else {
                 rows_ = (long long)p.M - m0_;
             }
@@ -757,11 +795,12 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             const long long rows_ll = rows_;
             const int rows = rows_ll >= 32 ? 32 : (rows_ll > 0 ? (int)rows_ll : 0);
 #ifdef APSB_TC_TRACE
-            const bool row_ok = lane < rows && !(p.dbg & 64);      // ablation: no residual loads / output stores
+            const bool row_ok = (MODE == 4 ? row_ok4 : lane < rows) && !(p.dbg & 64);      // ablation: no residual loads / output stores
 #else
-            const bool row_ok = lane < rows;
+            const bool row_ok = MODE == 4 ? row_ok4 : lane < rows;
 #endif
-            const long long mrow = row_ok ? tc_out_row(p.a, (unsigned)(m0 + lane)) : 0;   // row of the output / residual matrices
+            // row of the output / residual matrices
+            const long long mrow = MODE == 4 ? mrow4 : (row_ok ? tc_out_row(p.a, (unsigned)(m0 + lane)) : 0);
             // Vector path: TMEM delivers lane = row.  Storing that way makes every STG.128 of a warp touch 32 different
             // lines (32 LSU cycles per instruction — the epilogue, not the MMAs, bounded the K = 256 layers: r02b
             // microbenchmark, +8 us for a second output).  The 32 x 32 block is therefore transposed through this warp's
@@ -1159,9 +1198,15 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
         // the stage's second A buffer at the SAME byte offsets (the swizzle is a property of the address, and this is an
         // element-wise map), 16-byte chunks dealt out linearly: conflict free, 4 (BK 16) or 8 chunks per thread and k-block.
         const int pt = threadIdx.x - WARP_PROD0 * 32;
-        const uint32_t nkb = (uint32_t)(num_kh * num_kw * kb_per_tap);
         uint32_t it = 0;
         for (unsigned st_ = cid; st_ < p.stiles; st_ += ncl) {
+            uint32_t nkb = (uint32_t)(num_kh * num_kw * kb_per_tap);
+            if (p.c4_t) {                   // only the taps that exist for this row class
+                const int cls = decode4(st_ / (unsigned)p.tiles_n).cls;
+                int nv = 0;
+                for (int kh = 0; kh < num_kh; ++kh) nv += tc_kh_valid(p.a, cls, kh) ? 1 : 0;
+                nkb = (uint32_t)(nv * num_kw * kb_per_tap);
+            }
             for (uint32_t j = 0; j < nkb; ++j, ++it) {
                 const int s = (int)(it % S);
                 const uint32_t ph = (it / S) & 1;
@@ -1550,6 +1595,7 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, long lon
 // MODE 4: geometry of a convolution whose A tiles are strided TMA boxes (see the kernel's TMA role)
 struct Conv4 {
     int rh, tpi, tiles_m, cw, tpr;
+    int t, ct[4];       // transposed convolution: row blocks per image and row class
 };
 
 // 4-D view [B][H][W][C] of the NHWC input; box = {box_c channels, OW pixels every sw, rh rows every sh, one image}
@@ -1708,8 +1754,18 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
     APSB_CHECK_ARG(!(xlo && p.ksplit > 1 && !p.epi_vec), "split-K needs 16-byte aligned partial rows (N %% 4 == 0)");
     // the TMA-fed kernels have the vector epilogue only: unaligned outputs take the gather-fed kernel and its scalar path
     if (c4 && p.epi_vec) {
-        if (int rc = make_map_conv(&tA, a.x, batch, a.H, a.W, a.Cin, C::BK, c4->cw, c4->rh, a.sh, a.sw)) return rc;
+        if (c4->t) {        // transposed (stride_w = 1): plain boxes of rh consecutive input rows; the cat-skip tensor has its own map
+            const long long csrc = a.cat_c ? 2LL * a.cat_c : a.Cin;
+            if (int rc = make_map_conv(&tA, a.x, batch, a.H, a.W, csrc, C::BK, c4->cw, c4->rh, 1, 1)) return rc;
+            tAl = tA;
+            if (a.x2)
+                if (int rc = make_map_conv(&tAl, a.x2, batch, a.H, a.W, csrc, C::BK, c4->cw, c4->rh, 1, 1)) return rc;
+        } else {
+            if (int rc = make_map_conv(&tA, a.x, batch, a.H, a.W, a.Cin, C::BK, c4->cw, c4->rh, a.sh, a.sw)) return rc;
+        }
         p.c4_rh = c4->rh; p.c4_tpi = c4->tpi; p.c4_tiles_m = c4->tiles_m; p.c4_cw = c4->cw; p.c4_tpr = c4->tpr;
+        p.c4_t = c4->t;
+        for (int i = 0; i < 4; ++i) p.c4_ct[i] = c4->ct[i];
         p.tiles = (unsigned)((long long)c4->tiles_m * p.tiles_n);
         return launch_tc_cl<BN, 4, 1>(tB, tBl, tA, tAl, p, st);
     }
@@ -2005,5 +2061,34 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float
     APSB_CHECK_ARG(epi && epi->act != ACT_GLU, "GLU is not available here");
     Epilogue e{};
     if (int rc = fill_tc_epilogue(e, epi, out_channels, out, out_channels)) return rc;
+    // A tiles by TMA (MODE 4, transposed form): a 128-row tile is some output rows of ONE row class (their input rows
+    // are consecutive) or a column chunk of one output row (DCCRN's time axis); every class needs a tap (a.classes)
+    if ((stride_h == 1 || a.classes == stride_h) && (in_channels & 31) == 0 && ((uintptr_t)x & 15) == 0 &&
+        !getenv("APS_B200_NO_CONV_TMA")) {
+        Conv4 c4{};
+        c4.t = 1;
+        const int ncls = stride_h;
+        if (stride_h == 1) { a.class_rows[0] = (int)OH; a.class_rows[1] = a.class_rows[2] = a.class_rows[3] = 0; }
+        int max_rows = 0;
+        for (int c = 0; c < ncls; ++c) max_rows = a.class_rows[c] > max_rows ? a.class_rows[c] : max_rows;
+        if (OW <= TC_BM) {
+            c4.cw = (int)OW; c4.tpr = 1;
+            c4.rh = (int)(TC_BM / OW);
+            if (c4.rh > max_rows) c4.rh = max_rows;
+        } else {
+            c4.tpr = (int)((OW + TC_BM - 1) / TC_BM);
+            c4.cw = (int)((OW + c4.tpr - 1) / c4.tpr);
+            c4.rh = 1;
+        }
+        c4.tpi = 0;
+        for (int c = 0; c < 4; ++c) {
+            c4.ct[c] = c < ncls ? ((a.class_rows[c] + c4.rh - 1) / c4.rh) * c4.tpr : 0;
+            c4.tpi += c4.ct[c];
+        }
+        c4.tiles_m = (int)(batch * c4.tpi);
+        const double eff = (double)(OH * OW) / ((double)c4.tpi * TC_BM);
+        if (c4.rh >= 1 && eff >= 0.7 && batch * c4.tpi < (1LL << 30))
+            return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream, nullptr, 1, 0, &c4, batch);
+    }
     return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream);
 }
