@@ -15,7 +15,7 @@ import torch as th
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # APS_B200_LIB selects a tuning build of the same ABI (see aps_b200/build.py); default: the in-tree library
 LIB_PATH = os.environ.get("APS_B200_LIB") or os.path.join(_HERE, "libaps_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class StftDesc(Structure):
@@ -149,6 +149,8 @@ _SIGNATURES = {
                                         c_int64, c_int, c_void_p]),
     "aps_b200_lstm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                   c_int64, c_void_p]),
+    "aps_b200_lstm_group_tc_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                           c_int64, c_int, c_void_p, c_void_p]),
     "aps_b200_pair_objf_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "aps_b200_pair_objf_fwd": (c_int, [POINTER(SignalList), POINTER(SignalList), c_int64, c_int64, POINTER(ObjfDesc),
                                        c_void_p, c_int64, c_void_p, c_void_p]),

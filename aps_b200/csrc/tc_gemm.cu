@@ -59,17 +59,20 @@ constexpr int TC_BM = 128;
 #ifndef APSB_TC_CLUSTER
 #define APSB_TC_CLUSTER 1
 #endif
+// MODE 5 is MODE 3 for several independent problems of one shape side by side ("groups": the recurrent projections of the
+// LSTMs that advance together): row block m of the stacked activations takes the weight rows of ITS group
+#define TC_LIN3(M) ((M) == 3 || (M) == 5)
 // MODE 3 (linear layer whose activation comes with its TF32 "lo" companion, see below) has NO producer warps: the TMA
 // warp loads the A tiles as well.  MODE 4 (stride-2 convolution fed by 5-D TMA boxes) has four CONVERTER warps in their
 // place: they derive the lo tile from the raw tile the TMA delivered, inside shared memory.
 template <int BN, int MODE> struct TcRoles {
-    static constexpr int PW = MODE == 3 ? 0 : ((BN > 128 || MODE == 4) ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
+    static constexpr int PW = TC_LIN3(MODE) ? 0 : ((BN > 128 || MODE == 4) ? 4 : (MODE != 0 ? APSB_TC_PW_CONV : APSB_TC_PW_LINEAR));
     static constexpr int PRODUCERS = PW * 32;
     // epilogue warps: 4 (one per TMEM lane quarter), or 8 in MODE 3 (two per quarter taking alternate 32-column chunks):
     // a 32 x 32 block costs ~900 dependent-issue-bound instructions, and ONE warp per scheduler cannot hide their
     // latencies (trace r02k: 11-13 k cycles of epilogue per 128 x 128 tile against a 10 k main loop).  MODE 3 has no
     // producer warps, so the second set is free.
-    static constexpr int EW = MODE == 3 ? 8 : 4;
+    static constexpr int EW = TC_LIN3(MODE) ? 8 : 4;
     static constexpr int THREADS = (2 + EW + PW) * 32;
 };
 constexpr int WARP_TMA = 0, WARP_MMA = 1, WARP_EPI0 = 2, WARP_PROD0 = 6;
@@ -360,6 +363,7 @@ struct TcParams {
     int c4_t, c4_ct[4];
     int dbg;                     // debug builds: bit 0 skip the A stores, bit 1 skip the TMA loads, bit 2 skip the epilogue body
     unsigned long long* trace;   // debug builds (-DAPSB_TC_TRACE): [0] = event counter, then (event << 48 | clock) words
+    int grp_rows, grp_n;         // MODE 5: activation rows per group (a multiple of 128) and weight rows per group (= N)
 };
 
 // Pipeline timeline of CTA 0 for tuning (compiled out unless APSB_TC_TRACE is defined).
@@ -393,7 +397,7 @@ template <int BN, int MODE = 0> struct TcCfg {
     // 16-byte columns (8 warps, MODE 3) — 8 x 4096 B: the padded form would not fit beside three 64 KB stages.  The
     // gather modes keep the small allocation: every KB of shared memory they do not claim stays L1 for the im2col
     // gathers (conv2 went 848 -> 1071 us when this was 32 KB for every mode).
-    static constexpr int EPI_BYTES = MODE == 3 ? 8 * 32 * 32 * 4 : 4 * 32 * 36 * 4;
+    static constexpr int EPI_BYTES = TC_LIN3(MODE) ? 8 * 32 * 32 * 4 : 4 * 32 * 36 * 4;
 #ifdef APSB_TC_TRACE
     static constexpr int TRACE_BYTES = 8 * 1024;
 #else
@@ -451,13 +455,13 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     auto tile_of = [&](unsigned st) -> unsigned {
         if (CL == 1) return st;
         unsigned t2 = st, ks = 0;
-        if (MODE == 3 && p.ksplit > 1) {
+        if (TC_LIN3(MODE) && p.ksplit > 1) {
             t2 = st / (unsigned)p.ksplit;
             ks = st - t2 * (unsigned)p.ksplit;
         }
         const unsigned msup = t2 / (unsigned)p.tiles_n, nb = t2 - msup * (unsigned)p.tiles_n;
         const unsigned flat = (msup * CL + crank) * (unsigned)p.tiles_n + nb;
-        return (MODE == 3 && p.ksplit > 1) ? flat * (unsigned)p.ksplit + ks : flat;
+        return (TC_LIN3(MODE) && p.ksplit > 1) ? flat * (unsigned)p.ksplit + ks : flat;
     };
     // k-blocks are walked tap by tap (convolutions: a k-block never crosses a (kh, kw) tap since Cin % 32 == 0) so that
     // a transposed-convolution tile can skip the taps that are zero for its row class; a linear layer is one "tap"
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     // into L1 (the tex->L2 sector traffic of a 3x3 convolution drops towards a third).
     // MODE (0 linear, 1 conv2d, 2 conv_transpose2d) is a template parameter: each instantiation carries only its own
     // gather code — the producers are instruction-fetch bound when their per-k-block code does not fit the L0 i-cache.
-    constexpr bool LIN = MODE == 0 || MODE == 3;
+    constexpr bool LIN = MODE == 0 || TC_LIN3(MODE);
     const int num_kh = LIN ? 1 : p.a.KH;
     const int num_kw = LIN ? 1 : p.a.KW;
     const int kb_per_tap = LIN ? (p.K + BK - 1) / BK : p.a.Cin / BK;
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     if (warp == WARP_TMA && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        if (MODE == 3) {
+        if (TC_LIN3(MODE)) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
         }
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                tc_mbar_init(full_a + s, MODE == 3 ? 1 : TcRoles<BN, MODE>::PW);
+                tc_mbar_init(full_a + s, TC_LIN3(MODE) ? 1 : TcRoles<BN, MODE>::PW);
                 tc_mbar_init(full_b + s, 1);
                 tc_mbar_init(empty + s, CL);
             }
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
     };
     if (warp == WARP_TMA) {
         // ================= TMA producer: weight tiles =================
-        if (MODE == 3) {
+        if (TC_LIN3(MODE)) {
             // operands of both sides by TMA: [A (raw x = hi) | A lo | W hi | W lo] per stage, one mbarrier transaction
             if (lane == 0) {
                 uint32_t it = 0;
@@ -599,7 +603,8 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         tc_mbar_expect_tx(full_b + s, 2 * A_BYTES + 2 * C::B_BYTES);
                         tc_tma_load_2d(&tmA, full_b + s, st, kb * BK, t.m_blk * TC_BM);
                         tc_tma_load_2d(&tmAlo, full_b + s, st + A_BYTES, kb * BK, t.m_blk * TC_BM);
-                        load_w(full_b + s, st + 2 * A_BYTES, kb * BK, t.n_blk * BN);
+                        load_w(full_b + s, st + 2 * A_BYTES, kb * BK,
+                               t.n_blk * BN + (MODE == 5 ? (t.m_blk * TC_BM / p.grp_rows) * p.grp_n : 0));
                         TC_TR(1);
                     }
                 }
@@ -691,7 +696,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 const int cls = MODE == 4 ? decode4(tile / (unsigned)p.tiles_n).cls : tile_class(tile);
                 uint32_t first = 1;
-                if (MODE == 3) {
+                if (TC_LIN3(MODE)) {
                     const TileIdx t = decode3(tile);
                     for (int kb = t.kb0; kb < t.kb1; ++kb, ++it) {
                         const int s = it % S;
@@ -764,7 +769,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
             int n_blk = (int)(tile % (unsigned)p.tiles_n);
             unsigned m_blk = tile / (unsigned)p.tiles_n;
             float* eout = e.out;                   // split-K: slice ks of the partial-sum workspace
-            if (MODE == 3) {
+            if (TC_LIN3(MODE)) {
                 const TileIdx t = decode3(tile);
                 n_blk = t.n_blk; m_blk = (unsigned)t.m_blk;
                 eout += (long long)t.ks * p.split_stride;
@@ -873,7 +878,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 float4 sl4 = make_float4(e.leak, e.leak, e.leak, e.leak);
                 constexpr bool LEAN = TcRoles<BN, MODE>::THREADS > 400;   // 128-register variants: load them late instead
                 auto load_cols = [&]() {
-                    if ((MODE == 3 || p.epi_vec) && nok) {
+                    if ((TC_LIN3(MODE) || p.epi_vec) && nok) {
                         if (e.bias && !e.dbg_nobias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
                         if (e.post_scale) {
                             ps4 = __ldg(reinterpret_cast<const float4*>(e.post_scale + n));
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     if (lane == 0) tc_mbar_arrive(tmem_empty + buf);
                     if (threadIdx.x == 64) TC_TR(5);
                 }
-                if (MODE == 3 || p.epi_vec) {      // MODE 3 is only launched with the vector epilogue (host check)
+                if (TC_LIN3(MODE) || p.epi_vec) {      // MODE 3 is only launched with the vector epilogue (host check)
                     // ---- transpose: lane = row -> lane = (row group, 4 columns) ----
                     __syncwarp();                  // the previous chunk's reads of the tile are done
                     const uint32_t ts_b = s_u32(tile_s);
@@ -905,7 +910,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     // (1 in the 448-thread variants, whose 128-register budget is taken by the producers' gather ring)
                     constexpr int GRP = LEAN ? 1 : 4;
                     if (LEAN) load_cols();
-                    if (MODE == 3 && p.ksplit > 1) {
+                    if (TC_LIN3(MODE) && p.ksplit > 1) {
                         // split-K slice: RAW partial sums (bias, activation, residual and the companion belong to the
                         // reducing kernel) — straight from the tile to memory.  Through the general path below this cost
                         // ~900 instructions per 32 x 32 block: 17 k cycles of a 39 k-cycle FFN-b work item (trace r02k).
@@ -968,7 +973,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 }                                                                                                       \
             }                                                                                                           \
         }
-                        const bool plain = MODE == 3 && !e.res && !e.post_scale && e.alpha == 1.f;
+                        const bool plain = TC_LIN3(MODE) && !e.res && !e.post_scale && e.alpha == 1.f;
                         if (plain && e.act == ACT_SWISH) {
                             TC_EPI_PLAIN(ACT_SWISH)
                         } else if (plain && e.act == ACT_NONE) {
@@ -988,7 +993,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                         }
 #undef TC_EPI_CASE
                     }
-                } else if constexpr (MODE != 3) {
+                } else if constexpr (!TC_LIN3(MODE)) {
                     // ---- transposed scalar fallback (unaligned rows): same code as in the other body below ----
                     __syncwarp();
 #pragma unroll
@@ -1188,7 +1193,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                     }
                     __syncwarp();                  // tile_s is reused by the next chunk
                 }
-                }   // MODE != 3
+                }   // !TC_LIN3(MODE)
             }
             if (threadIdx.x == 64) TC_TR(6);
         }
@@ -1224,7 +1229,7 @@ __global__ void __launch_bounds__((TcRoles<BN, MODE>::THREADS), 1)
                 if (lane == 0) tc_mbar_arrive(full_a + s);      // one arrival per converter warp
             }
         }
-    } else if constexpr (MODE != 3) {
+    } else if constexpr (!TC_LIN3(MODE)) {
         // ================= A producers (warps 6..9) =================
         // thread -> 16-byte chunk c of rows rg, rg + RSTEP, ...: a warp instruction reads whole SWZ-byte row segments.
         // The gather for k-block i+1 is issued BEFORE block i is split and stored, so the L2 round trip is hidden.
@@ -1709,7 +1714,8 @@ static int launch_tc_mode(const CUtensorMap& tB, const CUtensorMap& tBl, const C
 template <int BN>
 static int launch_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, int M, int N, int K,
                      const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
-                     long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0) {
+                     long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0, int grp_rows = 0,
+                     int groups = 1) {
     using C = TcCfg<BN>;
     // cluster size (weight-tile multicast)
     const long long tiles_m_ = (M + TC_BM - 1) / TC_BM;
@@ -1718,10 +1724,11 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
         const int v = atoi(ce);
         if ((v == 1 || v == 2 || v == 4) && a.mode != 2) cl = v;
     }
-    if (c4) cl = 1;
+    if (c4 || grp_rows) cl = 1;
     CUtensorMap tB, tBl, tA, tAl;
-    if (int rc = make_map(&tB, W, N, K, ldw, BN / cl, C::BK)) return rc;          // a CTA fetches BN / cl rows of the box
-    if (int rc = make_map(&tBl, Wlo, N, K, ldw, BN / cl, C::BK)) return rc;
+    const long long wrows = grp_rows ? (long long)N * groups : N;                 // MODE 5: the groups' weights stacked
+    if (int rc = make_map(&tB, W, wrows, K, ldw, BN / cl, C::BK)) return rc;      // a CTA fetches BN / cl rows of the box
+    if (int rc = make_map(&tBl, Wlo, wrows, K, ldw, BN / cl, C::BK)) return rc;
     tA = tB; tAl = tBl;
     if (xlo) {
         if (int rc = make_map(&tA, a.x, M, K, a.ld, TC_BM, C::BK)) return rc;
@@ -1769,6 +1776,11 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
         p.tiles = (unsigned)((long long)c4->tiles_m * p.tiles_n);
         return launch_tc_cl<BN, 4, 1>(tB, tBl, tA, tAl, p, st);
     }
+    if (grp_rows) {
+        APSB_CHECK_ARG(xlo && p.epi_vec && p.ksplit == 1 && grp_rows % TC_BM == 0, "grouped GEMM: needs the lo companion, aligned rows and 128-row groups");
+        p.grp_rows = grp_rows; p.grp_n = N;
+        return launch_tc_cl<BN, 5, 1>(tB, tBl, tA, tAl, p, st);
+    }
     if (xlo && p.epi_vec) return launch_tc_mode<BN, 3>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 0) return launch_tc_mode<BN, 0>(tB, tBl, tA, tAl, p, cl, st);
     if (a.mode == 1) return launch_tc_mode<BN, 1>(tB, tBl, tA, tAl, p, cl, st);
@@ -1781,7 +1793,8 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
 // waves of one per SM.
 static int run_tc(const AGather& a, const float* W, const float* Wlo, long long ldw, long long M, long long N,
                   long long K, const Epilogue& e, cudaStream_t st, const float* xlo = nullptr, int ksplit = 1,
-                  long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0) {
+                  long long split_stride = 0, const Conv4* c4 = nullptr, long long batch = 0, int grp_rows = 0,
+                  int groups = 1) {
     if (c4) {       // TMA-fed convolution: MMA bound at every width, so the widest tile that is not mostly padding
         if (N > 128) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st, nullptr, 1, 0, c4, batch);
         if (N > 64) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K, e, st, nullptr, 1, 0, c4, batch);
@@ -1818,9 +1831,9 @@ static int run_tc(const AGather& a, const float* W, const float* Wlo, long long 
             if (bn == 0 || t < best) { best = t; bn = cand[i]; }
         }
     }
-    if (bn == 256) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
-    if (bn == 128) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
-    return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride);
+    if (bn == 256) return launch_tc<256>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride, nullptr, 0, grp_rows, groups);
+    if (bn == 128) return launch_tc<128>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride, nullptr, 0, grp_rows, groups);
+    return launch_tc<64>(a, W, Wlo, ldw, (int)M, (int)N, (int)K0, e, st, xlo, ksplit, split_stride, nullptr, 0, grp_rows, groups);
 }
 
 static int fill_tc_epilogue(Epilogue& e, const aps_b200_epilogue* epi, long long N, float* out, long long ld_out) {
@@ -2091,4 +2104,88 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float
             return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream, nullptr, 1, 0, &c4, batch);
     }
     return run_tc(a, weight_hi, weight_lo, K, M, out_channels, K, e, (cudaStream_t)stream);
+}
+
+// ---- LSTM recurrence on the tensor-core engine ---------------------------------------------------------------------
+namespace apsb {
+// gates -> cell / hidden state of one frame for all groups (rows of the stacked [groups * rows_pad, .] buffers)
+struct LstmCellParams {
+    const float* pre;     // [R, 4H] gate pre-activations (i | f | g | o blocks of H), R = groups * rows_pad
+    float* c;             // [R, H] cell state, in place
+    float* h;             // [R, H] next hidden state (the next frame's GEMM operand) ...
+    float* h_lo;          // ... and its TF32 lo companion
+    float* y[APS_B200_LSTM_MAX_GROUPS];   // per group: output rows of this frame (row stride ld_y)
+    long long ld_y;
+    int rows, rows_pad, H;
+    long long total;      // R * H / 4
+};
+
+__global__ void __launch_bounds__(256) lstm_cell_kernel(const __grid_constant__ LstmCellParams p) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= p.total) return;
+    const int h4 = p.H >> 2;
+    const int r = (int)(idx / h4), u = (int)(idx - (long long)r * h4) * 4;
+    const int g = r / p.rows_pad, row = r - g * p.rows_pad;
+    if (row >= p.rows) return;                        // padding rows of a group
+    const float* pr = p.pre + (long long)r * 4 * p.H + u;
+    const float4 gi = __ldg(reinterpret_cast<const float4*>(pr)), gf = __ldg(reinterpret_cast<const float4*>(pr + p.H));
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(pr + 2 * p.H)), go = __ldg(reinterpret_cast<const float4*>(pr + 3 * p.H));
+    float4 c = *reinterpret_cast<const float4*>(p.c + (long long)r * p.H + u);
+    auto sg = [](float x) { return 1.f / (1.f + expf(-x)); };     // precise: the recurrence amplifies rounding
+    c.x = sg(gf.x) * c.x + sg(gi.x) * tanhf(gg.x);
+    c.y = sg(gf.y) * c.y + sg(gi.y) * tanhf(gg.y);
+    c.z = sg(gf.z) * c.z + sg(gi.z) * tanhf(gg.z);
+    c.w = sg(gf.w) * c.w + sg(gi.w) * tanhf(gg.w);
+    const float4 h = make_float4(sg(go.x) * tanhf(c.x), sg(go.y) * tanhf(c.y), sg(go.z) * tanhf(c.z), sg(go.w) * tanhf(c.w));
+    *reinterpret_cast<float4*>(p.c + (long long)r * p.H + u) = c;
+    *reinterpret_cast<float4*>(p.h + (long long)r * p.H + u) = h;
+    *reinterpret_cast<float4*>(p.h_lo + (long long)r * p.H + u) = tf32_lo4(h);
+    *reinterpret_cast<float4*>(p.y[g] + (long long)row * p.ld_y + u) = h;
+}
+}  // namespace apsb
+
+/* LSTM recurrence (torch.nn.LSTM semantics, gate order i, f, g, o, zero initial state, forward direction) of `groups`
+ * modules of one shape that advance together, with the per-frame product h_{t-1} W_hh^T on the tcgen05 engine (3xTF32):
+ * per frame ONE grouped GEMM launch (the modules' hidden states stacked along M, each row block using its own
+ * module's W_hh) whose epilogue adds the frame's input projections, and one cell kernel.  Replaces the fp32-FMA
+ * recurrence of aps_b200_lstm_group_fwd (same reference lines) where hidden % 32 == 0.
+ * xg: [groups, rows_pad, frames, 4 hidden] input projections incl. biases; w_hi / w_lo: [groups * 4 hidden, hidden];
+ * y[g]: [rows, frames, >= hidden] with ld_y floats between frames; work: caller-provided scratch of
+ * groups * rows_pad * (hidden * 5 + 4 * hidden) floats (cell, h, h_lo ping-pong pairs ..., gate pre-activations). */
+extern "C" int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t rows_pad, int64_t frames, int64_t hidden,
+                                          const float* w_hi, const float* w_lo, void* const* y, int64_t ld_y,
+                                          int32_t groups, float* work, void* stream) {
+    APSB_CHECK_ARG(xg && w_hi && w_lo && y && work, "null pointer argument");
+    APSB_CHECK_ARG(rows > 0 && frames > 0 && hidden > 0 && groups > 0 && groups <= APS_B200_LSTM_MAX_GROUPS, "bad shape");
+    APSB_CHECK_ARG(rows_pad >= rows && rows_pad % TC_BM == 0, "rows_pad must be a multiple of %d", TC_BM);
+    APSB_CHECK_ARG(hidden % 32 == 0, "the tensor-core recurrence needs hidden %% 32 == 0 (got %lld)", (long long)hidden);
+    APSB_CHECK_ARG(((uintptr_t)xg & 15) == 0 && ((uintptr_t)work & 15) == 0 && (ld_y & 3) == 0, "16-byte alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long R = (long long)groups * rows_pad, H = hidden;
+    APSB_CHECK_ARG(R < (1LL << 31), "too many rows");
+    float* cell = work;
+    float* hbuf[2] = {cell + R * H, cell + 3 * R * H};      // each: h then h_lo
+    float* pre = cell + 5 * R * H;
+    APSB_CUDA(cudaMemsetAsync(work, 0, (size_t)(5 * R * H) * sizeof(float), st));     // c = h = 0 before the first frame
+    LstmCellParams cp{};
+    cp.pre = pre; cp.c = cell; cp.ld_y = frames * ld_y; cp.rows = (int)rows; cp.rows_pad = (int)rows_pad; cp.H = (int)H;
+    cp.total = R * H / 4;
+    const unsigned cgrid = (unsigned)((cp.total + 255) / 256);
+    for (int64_t t = 0; t < frames; ++t) {
+        const float* hin = hbuf[t & 1];
+        float* hout = hbuf[(t + 1) & 1];
+        // pre = h_{t-1} W_hh^T + xg[:, :, t, :]
+        Epilogue e{};
+        e.act = ACT_NONE; e.alpha = 1.f; e.beta = 1.f; e.res = xg + t * 4 * H; e.ldres = frames * 4 * H; e.out = pre; e.ldo = 4 * H;
+        AGather a{};
+        a.mode = 0; a.x = hin; a.ld = H;
+        if (int rc = run_tc(a, w_hi, w_lo, H, R, 4 * H, H, e, st, hin + R * H, 1, 0, nullptr, 0, (int)rows_pad, groups)) return rc;
+        cp.h = hout; cp.h_lo = hout + R * H;
+        for (int g = 0; g < groups; ++g) cp.y[g] = static_cast<float*>(y[g]) + t * ld_y;
+        APSB_CUDA(launch_pdl(lstm_cell_kernel, dim3(cgrid), dim3(256), 0, st, cp));
+    }
+    APSB_LAUNCH_CHECK();
+    return 0;
 }

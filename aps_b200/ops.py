@@ -368,6 +368,40 @@ def lstm_multi(xs, mods, caches=None):
     lib = _lib.load()
     max_groups = 4                                               # APS_B200_LSTM_MAX_GROUPS
     inps = [x.contiguous().float() for x in xs]
+    # Recurrence on the tensor-core engine (aps_b200_lstm_group_tc_fwd): unidirectional layers whose hidden size is a
+    # multiple of 32, enough rows to fill 128-row tiles; APS_B200_LSTM=simt keeps the fp32-FMA recurrence kernel
+    tc_rec = (GEMM_ENGINE == "tc" and dirs == 1 and Hp == H and H % 32 == 0 and N >= 64 and len(mods) <= max_groups
+              and os.environ.get("APS_B200_LSTM", "tc") != "simt")
+    if tc_rec:
+        G = len(mods)
+        Np = (N + 127) // 128 * 128
+        for layer in range(m0.num_layers):
+            sfx = f"_l{layer}"
+            xg = th.empty(G, Np, T, 4 * H, dtype=th.float32, device=dev)
+            w_hhs = []
+            for g, (inp, mod, cache) in enumerate(zip(inps, mods, caches)):
+                w_ih = getattr(mod, "weight_ih" + sfx).detach()
+                bias = (getattr(mod, "bias_ih" + sfx).detach() + getattr(mod, "bias_hh" + sfx).detach()) if mod.bias else None
+                linear(inp.view(N * T, -1), w_ih, bias, cache=cache if isinstance(cache, SplitCache) else None,
+                       out=xg[g, :N].view(N * T, 4 * H))
+                w_hhs.append(getattr(mod, "weight_hh" + sfx).detach())
+            # stacked, split recurrent weights (cached in the first module's store, keyed by the parameters' versions)
+            store = caches[0].extra if isinstance(caches[0], SplitCache) else None
+            ver = tuple((w._version, w.data_ptr()) for w in w_hhs)
+            packed = store.get(("lstm_tc", layer)) if store is not None else None
+            if packed is None or packed[0] != ver:
+                packed = (ver,) + tf32_split(th.cat([w.float() for w in w_hhs], 0).contiguous()) + (w_hhs,)   # keeps the weights alive
+                if store is not None:
+                    store[("lstm_tc", layer)] = packed
+            w_hi, w_lo = packed[1], packed[2]
+            ys = [th.empty(N, T, H, dtype=th.float32, device=dev) for _ in mods]
+            work = th.empty(G * Np * H * 9, dtype=th.float32, device=dev)
+            yarr = (ctypes.c_void_p * G)(*[y.data_ptr() for y in ys])
+            with th.cuda.device(dev):
+                _lib.check(lib.aps_b200_lstm_group_tc_fwd(xg.data_ptr(), N, Np, T, H, w_hi.data_ptr(), w_lo.data_ptr(), yarr,
+                                                          H, G, work.data_ptr(), _lib.stream_ptr(dev)))
+            inps = ys
+        return inps
     for layer in range(m0.num_layers):
         ys = [th.empty(N, T, Hp * dirs, dtype=th.float32, device=dev) for _ in mods]
         jobs = []                                                # (xg, w_hh, cell, y pointer, reverse)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define APS_B200_ABI_VERSION 5
+#define APS_B200_ABI_VERSION 6
 
 /* library / device ------------------------------------------------------------------------ */
 int aps_b200_abi_version(void);
@@ -416,6 +416,17 @@ int aps_b200_lstm_fwd(const float* xg, int64_t ld_xg, int64_t rows, int64_t num_
 int aps_b200_lstm_group_fwd(const float* const* xg, int64_t ld_xg, int64_t rows, int64_t num_frames, int64_t hidden,
                             const float* const* w_hh, int reverse_mask, float* const* cell, float* const* y,
                             int64_t ld_y, int groups, void* stream);
+/* The same recurrence (forward direction) with the per-frame product h_{t-1} W_hh^T on the tcgen05 engine (3xTF32
+ * split, fp32-level accuracy): per frame ONE grouped GEMM launch — the groups' hidden states are stacked along M, a row
+ * block uses its own group's W_hh, the epilogue adds the frame's input projections — and one cell kernel (precise expf /
+ * tanhf).  hidden % 32 == 0; rows_pad = rows rounded up to a multiple of 128 (rows of a group beyond `rows` are never
+ * read back).  xg: [groups, rows_pad, num_frames, 4 hidden] input projections incl. both biases; w_hi / w_lo:
+ * aps_b200_tf32_split of the stacked W_hh [groups * 4 hidden, hidden]; y: host array of `groups` device pointers, each
+ * [rows, num_frames, ld_y >= hidden]; work: groups * rows_pad * hidden * 9 floats of scratch (cell state, two hidden
+ * (x, x_lo) pairs, gate pre-activations).  Same reference lines as above.                                         */
+int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t rows_pad, int64_t num_frames, int64_t hidden,
+                               const float* w_hi, const float* w_lo, void* const* y, int64_t ld_y, int32_t groups,
+                               float* work, void* stream);
 
 /* Time-domain separation objectives ----------------------------------------------------------
  * Si-SNR / SNR between every estimate and every reference of an utterance in ONE pass over the

@@ -50,7 +50,8 @@ def test_lstm_host_checks_without_gpu():
     (3, 1, 16, 8, 1, False),           # single frame: no recurrent product at all
     (40, 20, 64, 40, 2, False),        # hidden not a multiple of the 16-unit / 32-k tiles (DCCRN goldens use 40)
     (33, 25, 32, 64, 2, True),         # bidirectional, two layers
-    (70, 50, 256, 512, 2, False),      # the DCCRN bottleneck shape
+    (70, 50, 256, 512, 2, False),      # the DCCRN bottleneck shape (recurrence on the tensor-core engine: rows >= 64, H % 32 == 0)
+    (130, 30, 48, 96, 1, False),       # ... two 128-row blocks per module, the second mostly padding
     (6, 9, 10, 6, 2, False),           # hidden % 4 != 0: runs zero padded to 8 units (no library fallback)
     (12, 5, 20, 30, 2, True),          # ... bidirectional: the next layer's input columns are padded per direction
 ])
@@ -102,3 +103,21 @@ def test_lstm_multi_matches_single(bidir):
             assert th.equal(ops.lstm(x, m), y)
             want, _ = copy.deepcopy(m).cpu().double()(x.cpu().double())
             assert rel_err(y.cpu(), want) < 2e-5
+
+
+@gpu
+def test_lstm_tensor_core_recurrence_matches_simt(monkeypatch):
+    """Three modules advanced together on the grouped tensor-core recurrence (aps_b200_lstm_group_tc_fwd) against the
+    fp32-FMA recurrence kernel and fp64 torch: 200 frames, so a rounding difference would have time to grow."""
+    from aps_b200 import ops
+    th.manual_seed(21)
+    mods = [th.nn.LSTM(40, 64, num_layers=2, batch_first=True).eval().cuda() for _ in range(3)]
+    xs = [th.randn(100, 200, 40, device="cuda") for _ in range(3)]
+    with th.no_grad():
+        tc = ops.lstm_multi(xs, mods)
+        monkeypatch.setenv("APS_B200_LSTM", "simt")
+        simt = ops.lstm_multi(xs, mods)
+        for x, m, a, b in zip(xs, mods, tc, simt):
+            want, _ = copy.deepcopy(m).cpu().double()(x.cpu().double())
+            assert rel_err(a.cpu(), want) < 2e-5 and rel_err(b.cpu(), want) < 2e-5
+            assert rel_err(a, b) < 2e-5
