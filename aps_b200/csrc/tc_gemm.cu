@@ -1777,7 +1777,7 @@ static int launch_tc(const AGather& a, const float* W, const float* Wlo, long lo
         return launch_tc_cl<BN, 4, 1>(tB, tBl, tA, tAl, p, st);
     }
     if (grp_rows) {
-        APSB_CHECK_ARG(xlo && p.epi_vec && p.ksplit == 1 && grp_rows % TC_BM == 0, "grouped GEMM: needs the lo companion, aligned rows and 128-row groups");
+        APSB_CHECK_ARG(xlo && p.epi_vec && grp_rows % TC_BM == 0, "grouped GEMM: needs the lo companion, aligned rows and 128-row groups");
         p.grp_rows = grp_rows; p.grp_n = N;
         return launch_tc_cl<BN, 5, 1>(tB, tBl, tA, tAl, p, st);
     }
@@ -2110,7 +2110,10 @@ extern "C" int aps_b200_conv_transpose2d_nhwc_tc_fwd(const float* x, const float
 namespace apsb {
 // gates -> cell / hidden state of one frame for all groups (rows of the stacked [groups * rows_pad, .] buffers)
 struct LstmCellParams {
-    const float* pre;     // [R, 4H] gate pre-activations (i | f | g | o blocks of H), R = groups * rows_pad
+    const float* pre;     // [nparts][R, 4H] K-slice partial sums of h W_hh^T (i | f | g | o blocks of H), R = groups * rows_pad
+    const float* xg;      // [R, frames, 4H]: this frame's input projections (pointer already at the frame)
+    long long part_stride, ld_xg;
+    int nparts;
     float* c;             // [R, H] cell state, in place
     float* h;             // [R, H] next hidden state (the next frame's GEMM operand) ...
     float* h_lo;          // ... and its TF32 lo companion
@@ -2129,9 +2132,17 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const __grid_constant__ 
     const int r = (int)(idx / h4), u = (int)(idx - (long long)r * h4) * 4;
     const int g = r / p.rows_pad, row = r - g * p.rows_pad;
     if (row >= p.rows) return;                        // padding rows of a group
-    const float* pr = p.pre + (long long)r * 4 * p.H + u;
-    const float4 gi = __ldg(reinterpret_cast<const float4*>(pr)), gf = __ldg(reinterpret_cast<const float4*>(pr + p.H));
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(pr + 2 * p.H)), go = __ldg(reinterpret_cast<const float4*>(pr + 3 * p.H));
+    const float* xr = p.xg + (long long)r * p.ld_xg + u;
+    float4 gi = __ldg(reinterpret_cast<const float4*>(xr)), gf = __ldg(reinterpret_cast<const float4*>(xr + p.H));
+    float4 gg = __ldg(reinterpret_cast<const float4*>(xr + 2 * p.H)), go = __ldg(reinterpret_cast<const float4*>(xr + 3 * p.H));
+    auto add4 = [](float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
+    for (int s = 0; s < p.nparts; ++s) {              // fixed order: deterministic
+        const float* pr = p.pre + s * p.part_stride + (long long)r * 4 * p.H + u;
+        add4(gi, __ldg(reinterpret_cast<const float4*>(pr)));
+        add4(gf, __ldg(reinterpret_cast<const float4*>(pr + p.H)));
+        add4(gg, __ldg(reinterpret_cast<const float4*>(pr + 2 * p.H)));
+        add4(go, __ldg(reinterpret_cast<const float4*>(pr + 3 * p.H)));
+    }
     float4 c = *reinterpret_cast<const float4*>(p.c + (long long)r * p.H + u);
     auto sg = [](float x) { return 1.f / (1.f + expf(-x)); };     // precise: the recurrence amplifies rounding
     c.x = sg(gf.x) * c.x + sg(gi.x) * tanhf(gg.x);
@@ -2153,7 +2164,7 @@ __global__ void __launch_bounds__(256) lstm_cell_kernel(const __grid_constant__ 
  * recurrence of aps_b200_lstm_group_fwd (same reference lines) where hidden % 32 == 0.
  * xg: [groups, rows_pad, frames, 4 hidden] input projections incl. biases; w_hi / w_lo: [groups * 4 hidden, hidden];
  * y[g]: [rows, frames, >= hidden] with ld_y floats between frames; work: caller-provided scratch of
- * groups * rows_pad * (hidden * 5 + 4 * hidden) floats (cell, h, h_lo ping-pong pairs ..., gate pre-activations). */
+ * groups * rows_pad * hidden * 21 floats (cell, two (h, h_lo) pairs, up to four K slices of gate pre-activations). */
 extern "C" int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t rows_pad, int64_t frames, int64_t hidden,
                                           const float* w_hi, const float* w_lo, void* const* y, int64_t ld_y,
                                           int32_t groups, float* work, void* stream) {
@@ -2169,20 +2180,28 @@ extern "C" int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t
     float* hbuf[2] = {cell + R * H, cell + 3 * R * H};      // each: h then h_lo
     float* pre = cell + 5 * R * H;
     APSB_CUDA(cudaMemsetAsync(work, 0, (size_t)(5 * R * H) * sizeof(float), st));     // c = h = 0 before the first frame
+    // K slices: the per-frame GEMM is small (64 tiles of 128 x 128 at the DCCRN size) and strictly sequential over frames,
+    // so it is cut along K while the work items still fit one wave; the cell kernel adds the slices
+    int ks = 1;
+    {
+        const long long tiles128 = (R / TC_BM) * ((4 * H + 127) / 128);
+        while (ks < 4 && tiles128 * ks * 2 <= num_sms() && H / (ks * 2) >= 128) ks *= 2;
+    }
     LstmCellParams cp{};
     cp.pre = pre; cp.c = cell; cp.ld_y = frames * ld_y; cp.rows = (int)rows; cp.rows_pad = (int)rows_pad; cp.H = (int)H;
-    cp.total = R * H / 4;
+    cp.total = R * H / 4; cp.nparts = ks; cp.part_stride = R * 4 * H; cp.ld_xg = frames * 4 * H;
     const unsigned cgrid = (unsigned)((cp.total + 255) / 256);
     for (int64_t t = 0; t < frames; ++t) {
         const float* hin = hbuf[t & 1];
         float* hout = hbuf[(t + 1) & 1];
         // pre = h_{t-1} W_hh^T + xg[:, :, t, :]
         Epilogue e{};
-        e.act = ACT_NONE; e.alpha = 1.f; e.beta = 1.f; e.res = xg + t * 4 * H; e.ldres = frames * 4 * H; e.out = pre; e.ldo = 4 * H;
+        e.act = ACT_NONE; e.alpha = 1.f; e.beta = 1.f; e.out = pre; e.ldo = 4 * H;
         AGather a{};
         a.mode = 0; a.x = hin; a.ld = H;
-        if (int rc = run_tc(a, w_hi, w_lo, H, R, 4 * H, H, e, st, hin + R * H, 1, 0, nullptr, 0, (int)rows_pad, groups)) return rc;
-        cp.h = hout; cp.h_lo = hout + R * H;
+        // ks slices of RAW partial sums (ks = 1: the plain product); the input projections are added by the cell kernel
+        if (int rc = run_tc(a, w_hi, w_lo, H, R, 4 * H, H, e, st, hin + R * H, ks, R * 4 * H, nullptr, 0, (int)rows_pad, groups)) return rc;
+        cp.h = hout; cp.h_lo = hout + R * H; cp.xg = xg + t * 4 * H;
         for (int g = 0; g < groups; ++g) cp.y[g] = static_cast<float*>(y[g]) + t * ld_y;
         APSB_CUDA(launch_pdl(lstm_cell_kernel, dim3(cgrid), dim3(256), 0, st, cp));
     }

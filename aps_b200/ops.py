@@ -395,7 +395,7 @@ def lstm_multi(xs, mods, caches=None):
                     store[("lstm_tc", layer)] = packed
             w_hi, w_lo = packed[1], packed[2]
             ys = [th.empty(N, T, H, dtype=th.float32, device=dev) for _ in mods]
-            work = th.empty(G * Np * H * 9, dtype=th.float32, device=dev)
+            work = th.empty(G * Np * H * 21, dtype=th.float32, device=dev)
             yarr = (ctypes.c_void_p * G)(*[y.data_ptr() for y in ys])
             with th.cuda.device(dev):
                 _lib.check(lib.aps_b200_lstm_group_tc_fwd(xg.data_ptr(), N, Np, T, H, w_hi.data_ptr(), w_lo.data_ptr(), yarr,

@@ -422,8 +422,9 @@ int aps_b200_lstm_group_fwd(const float* const* xg, int64_t ld_xg, int64_t rows,
  * tanhf).  hidden % 32 == 0; rows_pad = rows rounded up to a multiple of 128 (rows of a group beyond `rows` are never
  * read back).  xg: [groups, rows_pad, num_frames, 4 hidden] input projections incl. both biases; w_hi / w_lo:
  * aps_b200_tf32_split of the stacked W_hh [groups * 4 hidden, hidden]; y: host array of `groups` device pointers, each
- * [rows, num_frames, ld_y >= hidden]; work: groups * rows_pad * hidden * 9 floats of scratch (cell state, two hidden
- * (x, x_lo) pairs, gate pre-activations).  Same reference lines as above.                                         */
+ * [rows, num_frames, ld_y >= hidden]; work: groups * rows_pad * hidden * 21 floats of scratch (cell state, two hidden
+ * (x, x_lo) pairs, up to four K slices of gate pre-activations: the small per-frame GEMM is cut along K while its work
+ * items fit one wave, the cell kernel adds the slices and the input projections).  Same reference lines as above.  */
 int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t rows_pad, int64_t num_frames, int64_t hidden,
                                const float* w_hi, const float* w_lo, void* const* y, int64_t ld_y, int32_t groups,
                                float* work, void* stream);
