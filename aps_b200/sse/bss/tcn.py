@@ -12,6 +12,7 @@ With `norm="BN"` (the default of the frequency-domain model) the eval-mode affin
 above; "cLN" / "gLN" / "IN" need per-utterance statistics over time and add one `ops.utt_norm` (two small
 launches) after each PReLU.
 """
+import os
 from typing import List, Optional, Union
 
 import torch as th
@@ -147,6 +148,22 @@ def _run_repeats(lin, conv: Conv1dRepeat, pk, x: th.Tensor, N: int, T: int) -> t
     """The repeat stack of tcn.py:162-226 on token rows [N*T, C]: three launches per block (see the module docstring)."""
     outs, skip, bi = [x], 0, 0
     nrep, nblk = len(conv.repeat), len(conv.repeat[0])
+    # Pair schedule (as in the encoder): every activation travels with its TF32 lo companion, written by the kernel that
+    # produces it, so both operand sides of the 1x1 convolutions arrive by TMA (no gather / split warps).  Needs
+    # epilogue-only norms (eval BatchNorm or none) and no skip links; APS_B200_TCN_PAIRS=0 turns it off.
+    pairs = (ops.GEMM_ENGINE == "tc" and not conv.skip_residual and x.shape[0] >= 128 and x.shape[1] % 4 == 0
+             and all(d["n1"][0] != "utt" and d["n2"][0] != "utt" and d["w1"].shape[0] % 4 == 0 for d in pk["blocks"])
+             and os.environ.get("APS_B200_TCN_PAIRS", "1") != "0")
+    if pairs:
+        x_lo = ops.lo_companion(x)
+        for d in pk["blocks"]:
+            (k1, n1), (k2, n2) = d["n1"], d["n2"]
+            h, h_lo = lin(x, d["w1"], d["b1"], act="prelu", slope=d["a1"], post=n1 if k1 == "bn" else None, x_lo=x_lo,
+                          want_lo=True)
+            h, h_lo = ops.dwconv1d(h, N, T, d["wd"], d["bd"], dilation=d["dil"], left_pad=d["lpad"], act="prelu",
+                                   slope=d["a2"], post=n2 if k2 == "bn" else None, want_lo=True)
+            x, x_lo = lin(h, d["w2"], d["b2"], residual=x, x_lo=h_lo, want_lo=True)
+        return x
     for r in range(nrep):
         if conv.skip_residual:
             for i in range(r):                       # in-place accumulation semantics of tcn.py:203-224
