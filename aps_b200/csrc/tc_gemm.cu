@@ -2167,6 +2167,8 @@ extern "C" int aps_b200_lstm_group_tc_fwd(const float* xg, int64_t rows, int64_t
     APSB_CHECK_ARG(rows_pad >= rows && rows_pad % TC_BM == 0, "rows_pad must be a multiple of %d", TC_BM);
     APSB_CHECK_ARG(hidden % 32 == 0, "the tensor-core recurrence needs hidden %% 32 == 0 (got %lld)", (long long)hidden);
     APSB_CHECK_ARG(((uintptr_t)xg & 15) == 0 && ((uintptr_t)work & 15) == 0 && (ld_y & 3) == 0, "16-byte alignment");
+    APSB_CHECK_ARG(ld_y >= hidden, "ld_y %lld smaller than hidden %lld", (long long)ld_y, (long long)hidden);
+    for (int g = 0; g < groups; ++g) APSB_CHECK_ARG(y[g] != nullptr, "null output pointer of group %d", g);
     cudaStream_t st = (cudaStream_t)stream;
     const long long R = (long long)groups * rows_pad, H = hidden;
     APSB_CHECK_ARG(R < (1LL << 31), "too many rows");
